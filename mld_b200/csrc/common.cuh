@@ -1,0 +1,56 @@
+// Shared device/host helpers for libmldb200 (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// ---------------------------------------------------------------------------------------
+// "split16" activation format.  Every activation tensor that feeds a GEMM is stored as two
+// fp16 planes hi = fp16(x), lo = fp16(x - hi); hi + lo carries ~22 significant bits.  The
+// tensor-core GEMMs compute A_hi*W_hi + A_lo*W_hi + A_hi*W_lo with fp32 accumulation, which
+// reproduces the reference's fp32 GEMMs to ~1e-6 relative (a single fp16/tf32 pass is ~5e-4
+// and does not survive 50 guided DDIM steps within the 1e-3 joint-position gate).
+// Planes are row-major [rows, cols]; lo plane = hi plane + plane_stride elements.
+// ---------------------------------------------------------------------------------------
+struct ActBuf {
+  __half* hi;            // plane 0
+  int64_t plane_stride;  // elements between the hi and lo planes
+  int rows, cols;        // logical shape (cols == leading dimension)
+  __host__ __device__ __half* lo() const { return hi + plane_stride; }
+};
+
+__device__ __forceinline__ void split_f32(float x, __half& hi, __half& lo) {
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+__device__ __forceinline__ float join_f32(__half hi, __half lo) {
+  return __half2float(hi) + __half2float(lo);
+}
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  // F.gelu default (exact erf form), cross_attention.py:408-409
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+enum ActKind { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SILU = 3 };
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_GELU: return gelu_erf(v);
+    case ACT_RELU: return fmaxf(v, 0.0f);
+    case ACT_SILU: return silu_f(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}

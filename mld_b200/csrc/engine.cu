@@ -1,0 +1,1103 @@
+// libmldb200 engine: weight packing, scheduler tables, transformer-stack orchestration,
+// CUDA-graph capture and the C ABI declared in include/mldb.h.
+#include "engine.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "gemm_tc.h"
+
+// ----------------------------------------------------------------------------- errors
+static thread_local std::string g_err;
+void mldb_set_err(const std::string& s) { g_err = s; }
+extern "C" const char* mldb_last_error(void) { return g_err.c_str(); }
+extern "C" int mldb_abi_version(void) { return MLDB_ABI_VERSION; }
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      char buf__[512];                                                                \
+      snprintf(buf__, sizeof buf__, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call, \
+               cudaGetErrorString(e__));                                              \
+      mldb_set_err(buf__);                                                            \
+      return MLDB_ERR_CUDA;                                                           \
+    }                                                                                 \
+  } while (0)
+
+#define FAIL(code, ...)                         \
+  do {                                          \
+    char buf__[512];                            \
+    snprintf(buf__, sizeof buf__, __VA_ARGS__); \
+    mldb_set_err(buf__);                        \
+    return (code);                              \
+  } while (0)
+
+#define TRY(expr)                 \
+  do {                            \
+    int rc__ = (expr);            \
+    if (rc__ != MLDB_OK) return rc__; \
+  } while (0)
+
+static inline void count_launch(mldb_handle* h, int n = 1) {
+  if (h->capturing) h->capture_nodes += n; else h->launches += n;
+}
+
+// ----------------------------------------------------------------------------- config
+extern "C" void mldb_default_config(mldb_config* c) {
+  memset(c, 0, sizeof *c);
+  c->abi_version = MLDB_ABI_VERSION;
+  c->cond_kind = MLDB_COND_TEXT;
+  c->arch = MLDB_ARCH_TRANS_ENC;
+  c->latent_dim = 256; c->n_lat = 1; c->num_heads = 4; c->ff_size = 1024; c->num_layers = 9;
+  c->text_dim = 768; c->nclasses = 12; c->nfeats = 263; c->diffusion_only = 0;
+  c->flip_sin_to_cos = 1; c->freq_shift = 0.0f; c->guidance_scale = 7.5f;
+  c->vae_kind = MLDB_VAE_MLD; c->vae_layers = 9; c->vae_heads = 4; c->vae_ff = 1024;
+  c->vae_nfeats = 263;
+  c->sched_kind = MLDB_SCHED_DDIM; c->num_train_timesteps = 1000;
+  c->beta_start = 0.00085; c->beta_end = 0.012; c->steps_offset = 1; c->set_alpha_to_one = 0;
+  c->eta = 0.0f; c->njoints = 22;
+}
+
+// ----------------------------------------------------------------------------- tensor spec
+static void spec_add(mldb_handle* h, const std::string& key, std::vector<int64_t> shape) {
+  RawTensor t; t.shape = std::move(shape);
+  h->raw[key] = std::move(t);
+}
+static void spec_attn(mldb_handle* h, const std::string& p, int d) {
+  spec_add(h, p + "in_proj_weight", {3 * d, d});
+  spec_add(h, p + "in_proj_bias", {3 * d});
+  spec_add(h, p + "out_proj.weight", {d, d});
+  spec_add(h, p + "out_proj.bias", {d});
+}
+static void spec_ln(mldb_handle* h, const std::string& p, int d) {
+  spec_add(h, p + "weight", {d});
+  spec_add(h, p + "bias", {d});
+}
+static void spec_layer(mldb_handle* h, const std::string& p, int d, int ff, bool dec) {
+  spec_attn(h, p + "self_attn.", d);
+  if (dec) spec_attn(h, p + "multihead_attn.", d);
+  spec_add(h, p + "linear1.weight", {ff, d});
+  spec_add(h, p + "linear1.bias", {ff});
+  spec_add(h, p + "linear2.weight", {d, ff});
+  spec_add(h, p + "linear2.bias", {d});
+  spec_ln(h, p + "norm1.", d);
+  spec_ln(h, p + "norm2.", d);
+  if (dec) spec_ln(h, p + "norm3.", d);
+}
+static void spec_skip_stack(mldb_handle* h, const std::string& p, int d, int ff, int layers, bool dec) {
+  const int nb = (layers - 1) / 2;
+  spec_ln(h, p + "norm.", d);
+  for (int i = 0; i < nb; ++i) spec_layer(h, p + "input_blocks." + std::to_string(i) + ".", d, ff, dec);
+  spec_layer(h, p + "middle_block.", d, ff, dec);
+  for (int i = 0; i < nb; ++i) spec_layer(h, p + "output_blocks." + std::to_string(i) + ".", d, ff, dec);
+  for (int i = 0; i < nb; ++i) {
+    spec_add(h, p + "linear_blocks." + std::to_string(i) + ".weight", {d, 2 * d});
+    spec_add(h, p + "linear_blocks." + std::to_string(i) + ".bias", {d});
+  }
+}
+
+static int build_spec(mldb_handle* h) {
+  const mldb_config& c = h->cfg;
+  const int d = c.latent_dim;
+  const std::string D = "denoiser.";
+  if (c.num_layers > 0) {   // num_layers == 0: VAE-only handle
+  if (c.diffusion_only) {
+    spec_add(h, D + "pose_embd.weight", {d, c.nfeats});
+    spec_add(h, D + "pose_embd.bias", {d});
+    spec_add(h, D + "pose_proj.weight", {c.nfeats, d});
+    spec_add(h, D + "pose_proj.bias", {c.nfeats});
+  }
+  const int tdim = c.cond_kind == MLDB_COND_TEXT ? c.text_dim : d;   // mld_denoiser.py:57,70
+  spec_add(h, D + "time_embedding.linear_1.weight", {d, tdim});
+  spec_add(h, D + "time_embedding.linear_1.bias", {d});
+  spec_add(h, D + "time_embedding.linear_2.weight", {d, d});
+  spec_add(h, D + "time_embedding.linear_2.bias", {d});
+  if (c.cond_kind == MLDB_COND_TEXT) {
+    if (c.text_dim != d) {
+      spec_add(h, D + "emb_proj.1.weight", {d, c.text_dim});
+      spec_add(h, D + "emb_proj.1.bias", {d});
+    }
+  } else {
+    spec_add(h, D + "emb_proj.action_embedding", {c.nclasses, d});
+  }
+  spec_add(h, D + "query_pos.pe", {500, 1, d});
+  spec_add(h, D + "mem_pos.pe", {500, 1, d});
+  if (c.arch == MLDB_ARCH_TRANS_ENC) {
+    spec_skip_stack(h, D + "encoder.", d, c.ff_size, c.num_layers, false);
+  } else {
+    for (int i = 0; i < c.num_layers; ++i)
+      spec_layer(h, D + "decoder.layers." + std::to_string(i) + ".", d, c.ff_size, true);
+    spec_ln(h, D + "decoder.norm.", d);
+  }
+  }
+  const std::string V = "vae.";
+  if (c.vae_kind == MLDB_VAE_MLD) {
+    spec_add(h, V + "global_motion_token", {2 * c.n_lat, d});
+    spec_add(h, V + "query_pos_encoder.pe", {500, 1, d});
+    spec_add(h, V + "query_pos_decoder.pe", {500, 1, d});
+    spec_skip_stack(h, V + "encoder.", d, c.vae_ff, c.vae_layers, false);
+    spec_skip_stack(h, V + "decoder.", d, c.vae_ff, c.vae_layers, true);
+    spec_add(h, V + "skel_embedding.weight", {d, c.vae_nfeats});
+    spec_add(h, V + "skel_embedding.bias", {d});
+    spec_add(h, V + "final_layer.weight", {c.vae_nfeats, d});
+    spec_add(h, V + "final_layer.bias", {c.vae_nfeats});
+  } else if (c.vae_kind == MLDB_VAE_ACTOR) {
+    spec_add(h, V + "decoder.sequence_pos_encoding.pe", {5000, 1, d});
+    for (int i = 0; i < c.vae_layers; ++i)
+      spec_layer(h, V + "decoder.seqTransDecoder.layers." + std::to_string(i) + ".", d, c.vae_ff, true);
+    spec_add(h, V + "decoder.final_layer.weight", {c.vae_nfeats, d});
+    spec_add(h, V + "decoder.final_layer.bias", {c.vae_nfeats});
+  }
+  return MLDB_OK;
+}
+
+// ----------------------------------------------------------------------------- alloc / pack
+static int dev_alloc(mldb_handle* h, void** p, size_t bytes) {
+  CK(cudaMalloc(p, bytes ? bytes : 16));
+  h->allocs.push_back(*p);
+  return MLDB_OK;
+}
+static int upload_f32(mldb_handle* h, const float* src, size_t n, float** out) {
+  TRY(dev_alloc(h, (void**)out, n * sizeof(float)));
+  CK(cudaMemcpy(*out, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  return MLDB_OK;
+}
+static const RawTensor& rt(mldb_handle* h, const std::string& k) { return h->raw.at(k); }
+
+// Pack rows [row0, row0+N) of a host [*, K] fp32 matrix into split fp16 planes scaled by 2^s.
+static int pack_linear(mldb_handle* h, const float* W, int N, int K, const float* bias, LinW* out) {
+  float mx = 0.0f;
+  for (int64_t i = 0; i < (int64_t)N * K; ++i) mx = std::max(mx, fabsf(W[i]));
+  int s = 0;
+  if (mx > 0.0f) {
+    s = (int)floorf(log2f(16384.0f / mx));
+    s = std::max(-14, std::min(14, s));
+  }
+  const float sc = ldexpf(1.0f, s);
+  std::vector<__half> buf((size_t)2 * N * K);
+  for (int64_t i = 0; i < (int64_t)N * K; ++i) {
+    const float w = W[i] * sc;
+    const __half hi = __float2half_rn(w);
+    buf[i] = hi;
+    buf[(size_t)N * K + i] = __float2half_rn(w - __half2float(hi));
+  }
+  TRY(dev_alloc(h, (void**)&out->w, buf.size() * sizeof(__half)));
+  CK(cudaMemcpy(out->w, buf.data(), buf.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  out->plane_stride = (int64_t)N * K;
+  out->N = N; out->K = K; out->inv_scale = ldexpf(1.0f, -s);
+  out->bias = nullptr;
+  if (bias) TRY(upload_f32(h, bias, N, &out->bias));
+  static int next_id = 0;
+  out->id = next_id++;
+  return MLDB_OK;
+}
+static int pack_named(mldb_handle* h, const std::string& wkey, const std::string& bkey, LinW* out,
+                      int row0 = 0, int nrows = -1) {
+  const RawTensor& w = rt(h, wkey);
+  const int K = (int)w.shape.back();
+  const int Nall = (int)w.shape[0];
+  if (nrows < 0) nrows = Nall;
+  const float* b = bkey.empty() ? nullptr : rt(h, bkey).host.data() + row0;
+  return pack_linear(h, w.host.data() + (size_t)row0 * K, nrows, K, b, out);
+}
+static int pack_ln(mldb_handle* h, const std::string& p, int d, LnW* out) {
+  TRY(upload_f32(h, rt(h, p + "weight").host.data(), d, &out->g));
+  TRY(upload_f32(h, rt(h, p + "bias").host.data(), d, &out->b));
+  return MLDB_OK;
+}
+static int pack_enc_layer(mldb_handle* h, const std::string& p, int d, EncW* w) {
+  TRY(pack_named(h, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", &w->in_proj));
+  TRY(pack_named(h, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", &w->out_proj));
+  TRY(pack_named(h, p + "linear1.weight", p + "linear1.bias", &w->l1));
+  TRY(pack_named(h, p + "linear2.weight", p + "linear2.bias", &w->l2));
+  TRY(pack_ln(h, p + "norm1.", d, &w->n1));
+  TRY(pack_ln(h, p + "norm2.", d, &w->n2));
+  return MLDB_OK;
+}
+static int pack_dec_layer(mldb_handle* h, const std::string& p, int d, DecW* w) {
+  TRY(pack_named(h, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", &w->sa_in));
+  TRY(pack_named(h, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", &w->sa_out));
+  // packed in_proj rows are [Wq; Wk; Wv] (nn.MultiheadAttention): q part and kv part
+  TRY(pack_named(h, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", &w->ca_q, 0, d));
+  TRY(pack_named(h, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", &w->ca_kv, d, 2 * d));
+  TRY(pack_named(h, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", &w->ca_out));
+  TRY(pack_named(h, p + "linear1.weight", p + "linear1.bias", &w->l1));
+  TRY(pack_named(h, p + "linear2.weight", p + "linear2.bias", &w->l2));
+  TRY(pack_ln(h, p + "norm1.", d, &w->n1));
+  TRY(pack_ln(h, p + "norm2.", d, &w->n2));
+  TRY(pack_ln(h, p + "norm3.", d, &w->n3));
+  return MLDB_OK;
+}
+static int pack_skip_stack(mldb_handle* h, const std::string& p, int d, int ff, int heads, int layers,
+                           bool dec, StackW* s) {
+  s->kind = dec ? STACK_SKIP_DEC : STACK_SKIP_ENC;
+  s->d = d; s->ff = ff; s->heads = heads; s->layers = layers;
+  const int nb = (layers - 1) / 2;
+  std::vector<std::string> names;
+  for (int i = 0; i < nb; ++i) names.push_back(p + "input_blocks." + std::to_string(i) + ".");
+  names.push_back(p + "middle_block.");
+  for (int i = 0; i < nb; ++i) names.push_back(p + "output_blocks." + std::to_string(i) + ".");
+  for (auto& n : names) {
+    if (dec) { s->dec.emplace_back(); TRY(pack_dec_layer(h, n, d, &s->dec.back())); }
+    else     { s->enc.emplace_back(); TRY(pack_enc_layer(h, n, d, &s->enc.back())); }
+  }
+  for (int i = 0; i < nb; ++i) {
+    s->skip.emplace_back();
+    const std::string lp = p + "linear_blocks." + std::to_string(i) + ".";
+    TRY(pack_named(h, lp + "weight", lp + "bias", &s->skip.back()));
+  }
+  TRY(pack_ln(h, p + "norm.", d, &s->norm));
+  return MLDB_OK;
+}
+static int upload_pe(mldb_handle* h, const std::string& key, float** out, int* rows = nullptr) {
+  const RawTensor& t = rt(h, key);
+  if (rows) *rows = (int)t.shape[0];
+  return upload_f32(h, t.host.data(), t.host.size(), out);
+}
+
+// ----------------------------------------------------------------------------- scheduler
+// betas = linspace(sqrt(b0), sqrt(b1), T, fp32) ** 2 ; alphas_cumprod = cumprod(1 - betas)
+// (diffusers scaled_linear schedule; fp32 throughout like torch).
+static void build_alphas(const mldb_config& c, std::vector<float>* out) {
+  // Bit-exact with torch on CPU (checked in tests/test_scheduler.py): linspace evaluates
+  // start + step*i (first half) / end - step*(T-1-i) (second half) with one rounding (FMA);
+  // cumprod accumulates in double (at::acc_type<float> on CPU) and rounds each output.
+  const int T = c.num_train_timesteps;
+  out->resize(T);
+  const float s0 = (float)sqrt(c.beta_start), s1 = (float)sqrt(c.beta_end);
+  const float step = (s1 - s0) / (float)(T - 1);
+  double prod = 1.0;
+  for (int i = 0; i < T; ++i) {
+    const float v = (i < T / 2) ? fmaf(step, (float)i, s0) : fmaf(-step, (float)(T - 1 - i), s1);
+    const float beta = v * v;
+    const float alpha = 1.0f - beta;
+    prod *= (double)alpha;
+    (*out)[i] = (float)prod;
+  }
+}
+extern "C" int mldb_scheduler_table(const mldb_config* cfg, float* alphas_cumprod_out) {
+  if (!cfg || !alphas_cumprod_out) FAIL(MLDB_ERR_INVALID, "null argument");
+  std::vector<float> a;
+  build_alphas(*cfg, &a);
+  memcpy(alphas_cumprod_out, a.data(), a.size() * sizeof(float));
+  return MLDB_OK;
+}
+// Integer timestep schedule, bit-exact with diffusers set_timesteps.
+extern "C" int mldb_scheduler_timesteps(const mldb_config* cfg, int32_t n, int64_t* out) {
+  if (!cfg || !out || n <= 0 || n > cfg->num_train_timesteps) FAIL(MLDB_ERR_INVALID, "bad n");
+  const int64_t ratio = cfg->num_train_timesteps / n;
+  const int64_t off = cfg->sched_kind == MLDB_SCHED_DDIM ? cfg->steps_offset : 0;
+  for (int i = 0; i < n; ++i) out[i] = (int64_t)(n - 1 - i) * ratio + off;
+  return MLDB_OK;
+}
+static StepCoef make_coef(const mldb_handle* h, int64_t t, int n_inference) {
+  const mldb_config& c = h->cfg;
+  const std::vector<float>& ac = h->alphas_cumprod;
+  StepCoef k{};
+  const int64_t prev_t = t - c.num_train_timesteps / n_inference;
+  const float a_t = ac[t];
+  k.c0 = sqrtf(a_t);
+  k.c1 = sqrtf(1.0f - a_t);
+  if (c.sched_kind == MLDB_SCHED_DDIM) {
+    const float a_prev = prev_t >= 0 ? ac[prev_t] : (c.set_alpha_to_one ? 1.0f : ac[0]);
+    k.kind = 0;
+    k.c2 = sqrtf(a_prev);
+    k.c3 = sqrtf(1.0f - a_prev - 0.0f);   // eta == 0 => std_dev_t == 0
+    k.sigma = 0.0f;
+  } else {
+    const float a_prev = prev_t >= 0 ? ac[prev_t] : 1.0f;
+    const float bpt = 1.0f - a_t, bpp = 1.0f - a_prev;
+    const float cur_alpha = a_t / a_prev, cur_beta = 1.0f - cur_alpha;
+    k.kind = 1;
+    k.c2 = (sqrtf(a_prev) * cur_beta) / bpt;
+    k.c3 = sqrtf(cur_alpha) * bpp / bpt;
+    k.sigma = t > 0 ? sqrtf(std::max(bpp / bpt * cur_beta, 1e-20f)) : 0.0f;
+  }
+  return k;
+}
+
+// ----------------------------------------------------------------------------- op dispatch
+static void op_gemm(mldb_handle* h, const GemmArgs& g, cudaStream_t st) {
+  if (h->use_tc && tc_gemm_supported(h->tc, g)) tc_gemm(h->tc, g, nullptr, st);
+  else simt_gemm(g, st);
+  count_launch(h);
+}
+// GEMM followed by residual + LayerNorm (one fused tcgen05 kernel when the tile covers a row)
+static void op_gemm_ln(mldb_handle* h, GemmArgs g, LnArgs l, float* cf32, cudaStream_t st) {
+  if (h->use_tc && tc_gemm_ln_supported(h->tc, g, l)) {
+    tc_gemm(h->tc, g, &l, st);
+    count_launch(h);
+    return;
+  }
+  g.out = ActBuf{}; g.out_f32 = cf32; g.ldc = g.w.N;
+  op_gemm(h, g, st);
+  l.c = cf32; l.ldc = g.w.N;
+  simt_ln(l, st);
+  count_launch(h);
+}
+static void op_ln(mldb_handle* h, const LnArgs& l, cudaStream_t st) { simt_ln(l, st); count_launch(h); }
+static void op_attn(mldb_handle* h, const AttnArgs& a, cudaStream_t st) {
+  simt_attention(a, st);
+  count_launch(h);
+}
+
+// ----------------------------------------------------------------------------- workspaces
+static int alloc_act(mldb_handle* h, int rows, int cols, ActBuf* out) {
+  const int64_t rp = ((int64_t)rows + 127) / 128 * 128;
+  __half* p = nullptr;
+  TRY(dev_alloc(h, (void**)&p, (size_t)2 * rp * cols * sizeof(__half)));
+  CK(cudaMemset(p, 0, (size_t)2 * rp * cols * sizeof(__half)));
+  out->hi = p; out->plane_stride = rp * cols; out->rows = rows; out->cols = cols;
+  return MLDB_OK;
+}
+static int alloc_stack_ws(mldb_handle* h, const StackW& sw, int nseq, int L, int Lmem, StackWs* ws) {
+  ws->nseq = nseq; ws->L = L; ws->M = nseq * L; ws->d = sw.d; ws->ff = sw.ff; ws->Lmem = Lmem;
+  const int M = ws->M, d = sw.d;
+  TRY(alloc_act(h, M, d, &ws->x0));
+  TRY(alloc_act(h, M, d, &ws->cur[0]));
+  TRY(alloc_act(h, M, d, &ws->cur[1]));
+  TRY(alloc_act(h, M, d, &ws->x1));
+  TRY(alloc_act(h, M, d, &ws->att));
+  TRY(alloc_act(h, M, 3 * d, &ws->qkv));
+  TRY(alloc_act(h, M, sw.ff, &ws->h));
+  if (sw.kind != STACK_SKIP_ENC) {
+    TRY(alloc_act(h, M, d, &ws->x2));
+    TRY(alloc_act(h, M, d, &ws->qc));
+    TRY(alloc_act(h, nseq * Lmem, 2 * d, &ws->kvm));
+  }
+  if (sw.kind != STACK_PLAIN_DEC) {
+    TRY(alloc_act(h, M, d, &ws->cat));
+    const int nb = (sw.layers - 1) / 2;
+    ws->ys.resize(nb);
+    for (int i = 0; i < nb; ++i) TRY(alloc_act(h, M, d, &ws->ys[i]));
+  }
+  TRY(dev_alloc(h, (void**)&ws->cf32, (size_t)M * d * sizeof(float)));
+  return MLDB_OK;
+}
+
+struct SeqInfo {
+  const int32_t* lengths = nullptr;  // key-padding: valid keys = kv_prefix + lengths[s % len_mod]
+  int kv_prefix = 0;
+  int len_mod = 0;
+};
+
+static void self_attn_block(mldb_handle* h, const LinW& in_proj, const LinW& out_proj, const LnW& n,
+                            ActBuf xin, ActBuf xout, StackWs& ws, const SeqInfo& si, int heads,
+                            cudaStream_t st) {
+  const int d = ws.d;
+  GemmArgs g; g.a1 = xin; g.K1 = d; g.M = ws.M; g.w = in_proj; g.out = ws.qkv;
+  op_gemm(h, g, st);
+  AttnArgs a; a.q = ws.qkv; a.q_col0 = 0; a.Lq = ws.L; a.kv = ws.qkv; a.k_col0 = d; a.v_col0 = 2 * d;
+  a.Lk = ws.L; a.nseq = ws.nseq; a.heads = heads; a.hd = d / heads; a.lengths = si.lengths;
+  a.kv_prefix = si.kv_prefix; a.len_mod = si.len_mod; a.out = ws.att;
+  op_attn(h, a, st);
+  GemmArgs g2; g2.a1 = ws.att; g2.K1 = d; g2.M = ws.M; g2.w = out_proj;
+  LnArgs l; l.res = xin; l.gamma = n.g; l.beta = n.b; l.M = ws.M; l.d = d; l.out = xout;
+  op_gemm_ln(h, g2, l, ws.cf32, st);
+}
+static void ffn_block(mldb_handle* h, const LinW& l1, const LinW& l2, const LnW& n, ActBuf xin,
+                      ActBuf xout, StackWs& ws, int act, cudaStream_t st) {
+  GemmArgs g; g.a1 = xin; g.K1 = ws.d; g.M = ws.M; g.w = l1; g.act = act; g.out = ws.h;
+  op_gemm(h, g, st);
+  GemmArgs g2; g2.a1 = ws.h; g2.K1 = ws.ff; g2.M = ws.M; g2.w = l2;
+  LnArgs l; l.res = xin; l.gamma = n.g; l.beta = n.b; l.M = ws.M; l.d = ws.d; l.out = xout;
+  op_gemm_ln(h, g2, l, ws.cf32, st);
+}
+// TransformerEncoderLayer.forward_post (cross_attention.py:259-272)
+static void enc_layer(mldb_handle* h, const StackW& sw, const EncW& w, ActBuf xin, ActBuf xout,
+                      StackWs& ws, const SeqInfo& si, cudaStream_t st) {
+  self_attn_block(h, w.in_proj, w.out_proj, w.n1, xin, ws.x1, ws, si, sw.heads, st);
+  ffn_block(h, w.l1, w.l2, w.n2, ws.x1, xout, ws, ACT_GELU, st);
+}
+// TransformerDecoderLayer.forward_post (cross_attention.py:323-345)
+static void dec_layer(mldb_handle* h, const StackW& sw, const DecW& w, ActBuf xin, ActBuf xout,
+                      ActBuf mem, StackWs& ws, const SeqInfo& si, cudaStream_t st) {
+  const int d = ws.d;
+  self_attn_block(h, w.sa_in, w.sa_out, w.n1, xin, ws.x1, ws, si, sw.heads, st);
+  // cross attention: query = tgt, key = value = memory, no memory mask
+  GemmArgs gq; gq.a1 = ws.x1; gq.K1 = d; gq.M = ws.M; gq.w = w.ca_q; gq.out = ws.qc;
+  op_gemm(h, gq, st);
+  GemmArgs gk; gk.a1 = mem; gk.K1 = d; gk.M = ws.nseq * ws.Lmem; gk.w = w.ca_kv; gk.out = ws.kvm;
+  op_gemm(h, gk, st);
+  AttnArgs a; a.q = ws.qc; a.q_col0 = 0; a.Lq = ws.L; a.kv = ws.kvm; a.k_col0 = 0; a.v_col0 = d;
+  a.Lk = ws.Lmem; a.nseq = ws.nseq; a.heads = sw.heads; a.hd = d / sw.heads; a.out = ws.att;
+  op_attn(h, a, st);
+  GemmArgs go; go.a1 = ws.att; go.K1 = d; go.M = ws.M; go.w = w.ca_out;
+  LnArgs l; l.res = ws.x1; l.gamma = w.n2.g; l.beta = w.n2.b; l.M = ws.M; l.d = d; l.out = ws.x2;
+  op_gemm_ln(h, go, l, ws.cf32, st);
+  ffn_block(h, w.l1, w.l2, w.n3, ws.x2, xout, ws, ACT_GELU, st);
+}
+static void any_layer(mldb_handle* h, const StackW& sw, int li, ActBuf xin, ActBuf xout, ActBuf mem,
+                      StackWs& ws, const SeqInfo& si, cudaStream_t st) {
+  if (sw.kind == STACK_SKIP_ENC) enc_layer(h, sw, sw.enc[li], xin, xout, ws, si, st);
+  else dec_layer(h, sw, sw.dec[li], xin, xout, mem, ws, si, st);
+}
+// SkipTransformerEncoder/Decoder.forward (cross_attention.py:41-64, 89-125) and the plain
+// decoder stacks (cross_attention.py:204-233; torch nn.TransformerDecoder for ActorVae).
+// Returns the buffer holding the last layer's output (before the stack's final norm).
+static ActBuf run_stack(mldb_handle* h, const StackW& sw, ActBuf x0, ActBuf mem, StackWs& ws,
+                        const SeqInfo& si, cudaStream_t st) {
+  if (sw.kind == STACK_PLAIN_DEC) {
+    ActBuf x = x0;
+    for (int i = 0; i < sw.layers; ++i) {
+      any_layer(h, sw, i, x, ws.cur[i & 1], mem, ws, si, st);
+      x = ws.cur[i & 1];
+    }
+    return x;
+  }
+  const int nb = (sw.layers - 1) / 2;
+  ActBuf x = x0;
+  for (int i = 0; i < nb; ++i) {
+    any_layer(h, sw, i, x, ws.ys[i], mem, ws, si, st);
+    x = ws.ys[i];
+  }
+  any_layer(h, sw, nb, x, ws.cur[0], mem, ws, si, st);
+  x = ws.cur[0];
+  for (int i = 0; i < nb; ++i) {
+    GemmArgs g; g.a1 = x; g.K1 = sw.d; g.a2 = ws.ys[nb - 1 - i]; g.K2 = sw.d; g.M = ws.M;
+    g.w = sw.skip[i]; g.out = ws.cat;
+    op_gemm(h, g, st);
+    any_layer(h, sw, nb + 1 + i, ws.cat, ws.cur[(i + 1) & 1], mem, ws, si, st);
+    x = ws.cur[(i + 1) & 1];
+  }
+  return x;
+}
+
+// ----------------------------------------------------------------------------- create/destroy
+extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out) {
+  if (!cfg || !out) FAIL(MLDB_ERR_INVALID, "null argument");
+  if (cfg->abi_version != MLDB_ABI_VERSION) FAIL(MLDB_ERR_INVALID, "abi_version mismatch");
+  if (cfg->latent_dim % cfg->num_heads || cfg->latent_dim % 32) FAIL(MLDB_ERR_INVALID, "latent_dim must be a multiple of 32 and of num_heads");
+  if (cfg->latent_dim > 1024) FAIL(MLDB_ERR_UNSUPPORTED, "latent_dim > 1024");
+  if (cfg->arch == MLDB_ARCH_TRANS_ENC && cfg->num_layers > 0 && cfg->num_layers % 2 != 1) FAIL(MLDB_ERR_INVALID, "skip encoder needs an odd layer count");
+  if (cfg->arch == MLDB_ARCH_TRANS_ENC && cfg->diffusion_only) FAIL(MLDB_ERR_UNSUPPORTED, "diffusion_only requires arch trans_dec");
+  if (cfg->vae_kind == MLDB_VAE_MLD && cfg->vae_layers % 2 != 1) FAIL(MLDB_ERR_INVALID, "MldVae needs an odd layer count");
+  if (cfg->sched_kind == MLDB_SCHED_DDIM && cfg->eta != 0.0f) FAIL(MLDB_ERR_UNSUPPORTED, "DDIM eta != 0");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) FAIL(MLDB_ERR_INVALID, "no such CUDA device %d (no CPU fallback exists)", device);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) FAIL(MLDB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libmldb200 is sm_100a only", device, prop.major, prop.minor);
+  CK(cudaSetDevice(device));
+  mldb_handle* h = new mldb_handle();
+  h->cfg = *cfg; h->device = device; h->sm_count = prop.multiProcessorCount;
+  build_spec(h);
+  build_alphas(h->cfg, &h->alphas_cumprod);
+  cudaError_t e = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete h; FAIL(MLDB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  h->tc = tc_create(device);
+  if (!h->tc) { delete h; return MLDB_ERR_CUDA; }
+  const char* env = getenv("MLDB_GEMM");
+  if (env && !strcmp(env, "simt")) h->use_tc = false;
+  env = getenv("MLDB_GRAPH");
+  if (env && !strcmp(env, "0")) h->use_graph = false;
+  *out = h;
+  return MLDB_OK;
+}
+
+extern "C" void mldb_destroy(mldb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : h->plans) {
+    if (kv.second->exec) cudaGraphExecDestroy(kv.second->exec);
+    delete kv.second;
+  }
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  tc_destroy(h->tc);
+  delete h;
+}
+
+extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* value) {
+  if (!h || !name || !value) FAIL(MLDB_ERR_INVALID, "null argument");
+  if (!strcmp(name, "gemm")) {
+    if (!strcmp(value, "tc")) h->use_tc = true;
+    else if (!strcmp(value, "simt")) h->use_tc = false;
+    else FAIL(MLDB_ERR_INVALID, "gemm must be tc|simt");
+  } else if (!strcmp(name, "graph")) {
+    h->use_graph = strcmp(value, "0") != 0;
+  } else {
+    FAIL(MLDB_ERR_INVALID, "unknown option %s", name);
+  }
+  // plans hold captured graphs of the previous configuration
+  for (auto& kv : h->plans) {
+    if (kv.second->exec) { cudaGraphExecDestroy(kv.second->exec); kv.second->exec = nullptr; }
+  }
+  return MLDB_OK;
+}
+
+extern "C" int64_t mldb_launch_count(const mldb_handle* h) { return h ? h->launches : 0; }
+
+// ----------------------------------------------------------------------------- weights
+extern "C" int mldb_load_tensor(mldb_handle* h, const char* key, const void* data,
+                                const int64_t* shape, int32_t ndim, int32_t dtype) {
+  if (!h || !key || !data || !shape) FAIL(MLDB_ERR_INVALID, "null argument");
+  if (dtype != MLDB_DTYPE_F32) FAIL(MLDB_ERR_UNSUPPORTED, "only fp32 tensors are accepted");
+  if (h->finalized) FAIL(MLDB_ERR_STATE, "weights already finalized");
+  auto it = h->raw.find(key);
+  if (it == h->raw.end()) {
+    // ActorVae's encoder half is not on the sampling path: accept and ignore
+    if (h->cfg.vae_kind == MLDB_VAE_ACTOR && !strncmp(key, "vae.encoder.", 12)) return MLDB_OK;
+    FAIL(MLDB_ERR_INVALID, "unexpected state-dict key '%s'", key);
+  }
+  RawTensor& t = it->second;
+  if ((int)t.shape.size() != ndim) FAIL(MLDB_ERR_INVALID, "key '%s': rank %d, expected %d", key, ndim, (int)t.shape.size());
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    if (shape[i] != t.shape[i]) FAIL(MLDB_ERR_INVALID, "key '%s': dim %d is %lld, expected %lld", key, i, (long long)shape[i], (long long)t.shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.host.resize(n);
+  CK(cudaSetDevice(h->device));
+  CK(cudaMemcpy(t.host.data(), data, n * sizeof(float), cudaMemcpyDefault));
+  t.loaded = true;
+  return MLDB_OK;
+}
+
+extern "C" int mldb_finalize_weights(mldb_handle* h, void* stream) {
+  (void)stream;
+  if (!h) FAIL(MLDB_ERR_INVALID, "null handle");
+  if (h->finalized) FAIL(MLDB_ERR_STATE, "already finalized");
+  for (auto& kv : h->raw)
+    if (!kv.second.loaded) FAIL(MLDB_ERR_STATE, "missing state-dict key '%s' (strict load)", kv.first.c_str());
+  CK(cudaSetDevice(h->device));
+  const mldb_config& c = h->cfg;
+  const int d = c.latent_dim;
+  const std::string D = "denoiser.", V = "vae.";
+  if (c.num_layers > 0) {
+  TRY(pack_named(h, D + "time_embedding.linear_1.weight", D + "time_embedding.linear_1.bias", &h->time_l1));
+  TRY(pack_named(h, D + "time_embedding.linear_2.weight", D + "time_embedding.linear_2.bias", &h->time_l2));
+  if (c.cond_kind == MLDB_COND_TEXT) {
+    if (c.text_dim != d) TRY(pack_named(h, D + "emb_proj.1.weight", D + "emb_proj.1.bias", &h->emb_proj));
+  } else {
+    TRY(upload_f32(h, rt(h, D + "emb_proj.action_embedding").host.data(), (size_t)c.nclasses * d, &h->action_emb));
+  }
+  TRY(upload_pe(h, D + "query_pos.pe", &h->query_pe));
+  TRY(upload_pe(h, D + "mem_pos.pe", &h->mem_pe));
+  if (c.diffusion_only) {
+    TRY(pack_named(h, D + "pose_embd.weight", D + "pose_embd.bias", &h->pose_embd));
+    TRY(pack_named(h, D + "pose_proj.weight", D + "pose_proj.bias", &h->pose_proj));
+  }
+  if (c.arch == MLDB_ARCH_TRANS_ENC) {
+    TRY(pack_skip_stack(h, D + "encoder.", d, c.ff_size, c.num_heads, c.num_layers, false, &h->den));
+  } else {
+    h->den.kind = STACK_PLAIN_DEC; h->den.d = d; h->den.ff = c.ff_size; h->den.heads = c.num_heads;
+    h->den.layers = c.num_layers;
+    for (int i = 0; i < c.num_layers; ++i) {
+      h->den.dec.emplace_back();
+      TRY(pack_dec_layer(h, D + "decoder.layers." + std::to_string(i) + ".", d, &h->den.dec.back()));
+    }
+    TRY(pack_ln(h, D + "decoder.norm.", d, &h->den.norm));
+  }
+  }
+  if (c.vae_kind == MLDB_VAE_MLD) {
+    TRY(pack_skip_stack(h, V + "encoder.", d, c.vae_ff, c.vae_heads, c.vae_layers, false, &h->venc));
+    TRY(pack_skip_stack(h, V + "decoder.", d, c.vae_ff, c.vae_heads, c.vae_layers, true, &h->vdec));
+    TRY(upload_pe(h, V + "query_pos_decoder.pe", &h->vae_dec_pe, &h->vae_dec_pe_rows));
+    TRY(upload_pe(h, V + "query_pos_encoder.pe", &h->vae_enc_pe));
+    TRY(upload_f32(h, rt(h, V + "global_motion_token").host.data(), (size_t)2 * c.n_lat * d, &h->global_token));
+    TRY(pack_named(h, V + "skel_embedding.weight", V + "skel_embedding.bias", &h->skel_emb));
+    TRY(pack_named(h, V + "final_layer.weight", V + "final_layer.bias", &h->final_layer));
+  } else if (c.vae_kind == MLDB_VAE_ACTOR) {
+    h->vdec.kind = STACK_PLAIN_DEC; h->vdec.d = d; h->vdec.ff = c.vae_ff; h->vdec.heads = c.vae_heads;
+    h->vdec.layers = c.vae_layers;
+    for (int i = 0; i < c.vae_layers; ++i) {
+      h->vdec.dec.emplace_back();
+      TRY(pack_dec_layer(h, V + "decoder.seqTransDecoder.layers." + std::to_string(i) + ".", d, &h->vdec.dec.back()));
+    }
+    TRY(upload_pe(h, V + "decoder.sequence_pos_encoding.pe", &h->vae_dec_pe, &h->vae_dec_pe_rows));
+    TRY(pack_named(h, V + "decoder.final_layer.weight", V + "decoder.final_layer.bias", &h->final_layer));
+  }
+  for (auto& kv : h->raw) { kv.second.host.clear(); kv.second.host.shrink_to_fit(); }
+  h->finalized = true;
+  return MLDB_OK;
+}
+
+extern "C" int mldb_set_mean_std(mldb_handle* h, const float* mean, const float* stdv, int32_t nfeats) {
+  if (!h || !mean || !stdv || nfeats <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(h->device));
+  if (!h->mean || h->nstat != nfeats) {
+    TRY(dev_alloc(h, (void**)&h->mean, nfeats * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&h->stdv, nfeats * sizeof(float)));
+    h->nstat = nfeats;
+  }
+  CK(cudaMemcpy(h->mean, mean, nfeats * sizeof(float), cudaMemcpyDefault));
+  CK(cudaMemcpy(h->stdv, stdv, nfeats * sizeof(float), cudaMemcpyDefault));
+  return MLDB_OK;
+}
+
+// ----------------------------------------------------------------------------- scheduler API
+// Time tokens for a list of timesteps: time_embedding(time_proj(t)) (mld_denoiser.py:151-155)
+// + the positional row the token will occupy.  out [n, d] fp32.
+static int time_tokens(mldb_handle* h, const int64_t* d_ts, int64_t t_scalar, int n, const float* pe_row,
+                       float* out, float* scratch_feats, float* scratch_h, cudaStream_t st) {
+  const mldb_config& c = h->cfg;
+  const int d = c.latent_dim;
+  const int tdim = c.cond_kind == MLDB_COND_TEXT ? c.text_dim : d;
+  const int half = tdim / 2;
+  k_timestep_features<<<(n * half + 255) / 256, 256, 0, st>>>(d_ts, t_scalar, n, tdim, c.flip_sin_to_cos, c.freq_shift, scratch_feats);
+  count_launch(h);
+  GemmArgs g; g.a_kind = A_F32; g.a_f32 = scratch_feats; g.lda = tdim; g.M = n; g.w = h->time_l1;
+  g.act = ACT_SILU; g.out_f32 = scratch_h; g.ldc = d;
+  simt_gemm(g, st); count_launch(h);
+  GemmArgs g2; g2.a_kind = A_F32; g2.a_f32 = scratch_h; g2.lda = d; g2.M = n; g2.w = h->time_l2;
+  g2.out_f32 = out; g2.ldc = d; g2.in_group = 1; g2.out_group = 1; g2.out_off = 0;
+  // addtab row index is (out_off + r % in_group) = 0 -> pe_row
+  g2.addtab = pe_row;
+  simt_gemm(g2, st); count_launch(h);
+  return MLDB_OK;
+}
+
+extern "C" int mldb_scheduler_set_timesteps(mldb_handle* h, int32_t n, int64_t* timesteps_out) {
+  if (!h) FAIL(MLDB_ERR_INVALID, "null handle");
+  if (!h->finalized) FAIL(MLDB_ERR_STATE, "finalize weights first");
+  if (n <= 0 || n > h->cfg.num_train_timesteps) FAIL(MLDB_ERR_INVALID, "bad number of inference steps %d", n);
+  CK(cudaSetDevice(h->device));
+  const mldb_config& c = h->cfg;
+  h->timesteps.resize(n);
+  TRY(mldb_scheduler_timesteps(&c, n, h->timesteps.data()));
+  h->coefs_host.resize(n);
+  for (int i = 0; i < n; ++i) h->coefs_host[i] = make_coef(h, h->timesteps[i], n);
+  const int d = c.latent_dim;
+  const int tdim = c.cond_kind == MLDB_COND_TEXT ? c.text_dim : d;
+  TRY(dev_alloc(h, (void**)&h->d_timesteps, n * sizeof(int64_t)));
+  TRY(dev_alloc(h, (void**)&h->d_coefs, n * sizeof(StepCoef)));
+  TRY(dev_alloc(h, (void**)&h->d_tt, (size_t)n * d * sizeof(float)));
+  CK(cudaMemcpy(h->d_timesteps, h->timesteps.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d_coefs, h->coefs_host.data(), n * sizeof(StepCoef), cudaMemcpyHostToDevice));
+  if (c.num_layers == 0) {   // scheduler-only use (no denoiser loaded)
+    h->sched_epoch++;
+    if (timesteps_out) memcpy(timesteps_out, h->timesteps.data(), n * sizeof(int64_t));
+    return MLDB_OK;
+  }
+  float *feats = nullptr, *hid = nullptr;
+  TRY(dev_alloc(h, (void**)&feats, (size_t)n * tdim * sizeof(float)));
+  TRY(dev_alloc(h, (void**)&hid, (size_t)n * d * sizeof(float)));
+  // the time token sits at row n_lat of the encoder sequence (mld_denoiser.py:171,187) or at
+  // row 0 of the decoder memory (mld_denoiser.py:215)
+  const float* pe_row = c.arch == MLDB_ARCH_TRANS_ENC ? h->query_pe + (size_t)c.n_lat * d : h->mem_pe;
+  TRY(time_tokens(h, h->d_timesteps, 0, n, pe_row, h->d_tt, feats, hid, h->cap_stream));
+  CK(cudaStreamSynchronize(h->cap_stream));
+  h->sched_epoch++;
+  if (timesteps_out) memcpy(timesteps_out, h->timesteps.data(), n * sizeof(int64_t));
+  return MLDB_OK;
+}
+
+extern "C" int mldb_scheduler_step(mldb_handle* h, const float* model_output, int64_t timestep,
+                                   const float* sample, const float* noise, int64_t count,
+                                   float* prev_sample, void* stream) {
+  if (!h || !model_output || !sample || !prev_sample) FAIL(MLDB_ERR_INVALID, "null argument");
+  if (h->timesteps.empty()) FAIL(MLDB_ERR_STATE, "call mldb_scheduler_set_timesteps first");
+  if (timestep < 0 || timestep >= h->cfg.num_train_timesteps) FAIL(MLDB_ERR_INVALID, "timestep out of range");
+  CK(cudaSetDevice(h->device));
+  StepCoef k = make_coef(h, timestep, (int)h->timesteps.size());
+  if (k.kind == 1 && k.sigma != 0.0f && !noise) FAIL(MLDB_ERR_INVALID, "DDPM step at t > 0 needs the injected noise tensor");
+  k_sched_step<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(model_output, sample, noise, prev_sample, count, k);
+  count_launch(h);
+  CK(cudaGetLastError());
+  return MLDB_OK;
+}
+
+// ----------------------------------------------------------------------------- plans
+static Plan* find_plan(mldb_handle* h, int kind, int B, int S, int T) {
+  char key[64];
+  snprintf(key, sizeof key, "%d:%d:%d:%d", kind, B, S, T);
+  auto it = h->plans.find(key);
+  return it == h->plans.end() ? nullptr : it->second;
+}
+static Plan* add_plan(mldb_handle* h, int kind, int B, int S, int T) {
+  char key[64];
+  snprintf(key, sizeof key, "%d:%d:%d:%d", kind, B, S, T);
+  Plan* p = new Plan();
+  p->kind = kind; p->B = B; p->S = S; p->T = T;
+  h->plans[key] = p;
+  return p;
+}
+
+// Run `record` either directly on `st` or as a (cached) CUDA graph.
+template <typename F>
+static int run_graphed(mldb_handle* h, Plan* p, cudaStream_t st, F record) {
+  if (!h->use_graph) { record(st); CK(cudaGetLastError()); return MLDB_OK; }
+  if (!p->exec || p->sched_epoch != h->sched_epoch) {
+    if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    h->capturing = true; h->capture_nodes = 0;
+    cudaError_t e = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      record(h->cap_stream);
+      e = cudaStreamEndCapture(h->cap_stream, &graph);
+    }
+    h->capturing = false;
+    if (e != cudaSuccess) FAIL(MLDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&p->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) FAIL(MLDB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    p->graph_nodes = h->capture_nodes;
+    p->sched_epoch = h->sched_epoch;
+  }
+  CK(cudaGraphLaunch(p->exec, st));
+  h->launches += p->graph_nodes;
+  return MLDB_OK;
+}
+
+static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+// ----------------------------------------------------------------------------- denoiser (trans_enc)
+// Gather + place the action tokens (EmbedAction.forward, mld_denoiser.py:250-262): rows of the
+// first (uncond) half are zero when guidance is on.
+__global__ void k_action_tokens(ActBuf X, int Ntok, int Bx, int pos, int d, const int64_t* __restrict__ ids,
+                                const float* __restrict__ table, int nclasses, int cfg_on,
+                                const float* __restrict__ pe_row) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Bx * d) return;
+  const int n = (int)(idx % d), s = (int)(idx / d);
+  float v = 0.0f;
+  if (!(cfg_on && s < Bx / 2)) {
+    int64_t id = ids[s];
+    id = id < 0 ? 0 : (id >= nclasses ? nclasses - 1 : id);
+    v = table[id * d + n];
+  }
+  v += pe_row[n];
+  __half hh, ll;
+  split_f32(v, hh, ll);
+  const int64_t o = ((int64_t)s * Ntok + pos) * X.cols + n;
+  X.hi[o] = hh;
+  X.lo()[o] = ll;
+}
+
+static int enc_plan(mldb_handle* h, int kind, int B, int Bx, int S, Plan** out) {
+  Plan* p = find_plan(h, kind, B, S, 0);
+  if (!p) {
+    const mldb_config& c = h->cfg;
+    p = add_plan(h, kind, B, S, 0);
+    p->Bx = Bx;
+    const int Sc = c.cond_kind == MLDB_COND_TEXT ? S : 1;
+    p->Ntok = c.n_lat + 1 + Sc;
+    if (p->Ntok > 500) FAIL(MLDB_ERR_INVALID, "sequence of %d tokens exceeds the learned PE table (500)", p->Ntok);
+    TRY(alloc_stack_ws(h, h->den, Bx, p->Ntok, 0, &p->ws));
+    const size_t per = (size_t)c.n_lat * c.latent_dim;
+    TRY(dev_alloc(h, (void**)&p->latents, (size_t)B * per * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&p->eps, (size_t)Bx * per * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&p->tt_single, (size_t)3 * std::max(c.text_dim, c.latent_dim) * sizeof(float) + 64));
+  }
+  *out = p;
+  return MLDB_OK;
+}
+
+// condition tokens -> X0 (once per batch; step invariant, hoisted out of the loop although the
+// reference recomputes emb_proj every step, mld_denoiser.py:165)
+static int place_condition(mldb_handle* h, Plan* p, const void* cond, cudaStream_t st) {
+  const mldb_config& c = h->cfg;
+  const int d = c.latent_dim, Bx = p->Bx;
+  if (c.cond_kind == MLDB_COND_TEXT) {
+    const int S = p->S;
+    if (c.text_dim != d) {
+      GemmArgs g; g.a_kind = A_F32_RELU; g.a_f32 = (const float*)cond; g.lda = c.text_dim;
+      g.M = Bx * S; g.w = h->emb_proj; g.out = p->ws.x0;
+      g.in_group = S; g.out_group = p->Ntok; g.out_off = c.n_lat + 1; g.addtab = h->query_pe;
+      op_gemm(h, g, st);
+    } else {
+      k_rows_to_split<<<nblk((int64_t)Bx * S * d), 256, 0, st>>>(p->ws.x0, (const float*)cond, d, Bx * S, d, S,
+                                                                p->Ntok, c.n_lat + 1, 0, h->query_pe);
+      count_launch(h);
+    }
+  } else {
+    const int cfg_on = c.guidance_scale > 1.0f;
+    k_action_tokens<<<nblk((int64_t)Bx * d), 256, 0, st>>>(p->ws.x0, p->Ntok, Bx, c.n_lat + 1, d, (const int64_t*)cond,
+                                                          h->action_emb, c.nclasses, cfg_on,
+                                                          h->query_pe + (size_t)(c.n_lat + 1) * d);
+    count_launch(h);
+  }
+  CK(cudaGetLastError());
+  return MLDB_OK;
+}
+
+// one denoiser pass over the assembled tokens: eps[Bx, n_lat*d] = norm(stack(X0))[:n_lat]
+static void denoiser_pass(mldb_handle* h, Plan* p, const float* latents, int lat_mod, const float* tt,
+                          float* eps_out, cudaStream_t st) {
+  const mldb_config& c = h->cfg;
+  const int d = c.latent_dim;
+  k_assemble_tokens<<<nblk((int64_t)p->Bx * (c.n_lat + 1) * d), 256, 0, st>>>(
+      p->ws.x0, p->Ntok, p->Bx, lat_mod, c.n_lat, d, latents, h->query_pe, tt);
+  count_launch(h);
+  SeqInfo si;
+  ActBuf x = run_stack(h, h->den, p->ws.x0, ActBuf{}, p->ws, si, st);
+  // encoder.norm on the latent tokens only (cross_attention.py:62-63, mld_denoiser.py:206)
+  LnArgs l; l.res = x; l.gamma = h->den.norm.g; l.beta = h->den.norm.b; l.M = p->Bx * c.n_lat; l.d = d;
+  l.sel_group = c.n_lat; l.in_group = p->Ntok; l.out_f32 = eps_out; l.ld_out = d;
+  op_ln(h, l, st);
+}
+
+static int check_ready(mldb_handle* h, bool need_sched) {
+  if (!h) FAIL(MLDB_ERR_INVALID, "null handle");
+  if (!h->finalized) FAIL(MLDB_ERR_STATE, "weights not finalized");
+  if (need_sched && h->timesteps.empty()) FAIL(MLDB_ERR_STATE, "call mldb_scheduler_set_timesteps first");
+  CK(cudaSetDevice(h->device));
+  return MLDB_OK;
+}
+
+extern "C" int mldb_denoise(mldb_handle* h, const float* sample, int64_t timestep, const void* cond,
+                            const int32_t* lengths, int32_t Bx, int32_t S_ctx, int32_t T, float* out,
+                            void* stream) {
+  (void)lengths; (void)T;
+  TRY(check_ready(h, false));
+  if (!sample || !cond || !out || Bx <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  const mldb_config& c = h->cfg;
+  if (c.num_layers == 0) FAIL(MLDB_ERR_STATE, "this handle has no denoiser");
+  if (c.arch != MLDB_ARCH_TRANS_ENC) FAIL(MLDB_ERR_UNSUPPORTED, "mldb_denoise: arch trans_dec is not built yet");
+  if (c.cond_kind == MLDB_COND_TEXT && S_ctx <= 0) FAIL(MLDB_ERR_INVALID, "S_ctx must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* p = nullptr;
+  TRY(enc_plan(h, 3, Bx, Bx, S_ctx, &p));
+  TRY(place_condition(h, p, cond, st));
+  // time token for this timestep
+  const int d = c.latent_dim;
+  const int tdim = c.cond_kind == MLDB_COND_TEXT ? c.text_dim : d;
+  float* feats = p->tt_single + 16;
+  float* hid = feats + tdim;
+  float* tt = hid + std::max(tdim, d);
+  TRY(time_tokens(h, nullptr, timestep, 1, h->query_pe + (size_t)c.n_lat * d, tt, feats, hid, st));
+  denoiser_pass(h, p, sample, Bx, tt, out, st);
+  CK(cudaGetLastError());
+  return MLDB_OK;
+}
+
+static int run_reverse(mldb_handle* h, const void* cond, const float* init_noise, const int32_t* lengths,
+                       int B, int S, int T, float* latents_out, cudaStream_t st, Plan** plan_out) {
+  (void)lengths; (void)T;
+  const mldb_config& c = h->cfg;
+  if (c.num_layers == 0) FAIL(MLDB_ERR_STATE, "this handle has no denoiser");
+  if (c.arch != MLDB_ARCH_TRANS_ENC) FAIL(MLDB_ERR_UNSUPPORTED, "reverse diffusion for arch trans_dec is not built yet");
+  const bool cfg_on = c.guidance_scale > 1.0f;
+  const int Bx = cfg_on ? 2 * B : B;
+  Plan* p = nullptr;
+  TRY(enc_plan(h, 0, B, Bx, S, &p));
+  const int d = c.latent_dim;
+  const int64_t per = (int64_t)c.n_lat * d;
+  TRY(place_condition(h, p, cond, st));
+  // latents = init_noise * init_noise_sigma (== 1 for DDIM/DDPM), mld.py:310
+  CK(cudaMemcpyAsync(p->latents, init_noise, (size_t)B * per * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const int nsteps = (int)h->timesteps.size();
+  TRY(run_graphed(h, p, st, [&](cudaStream_t s) {
+    for (int i = 0; i < nsteps; ++i) {                                           // mld.py:323
+      denoiser_pass(h, p, p->latents, B, h->d_tt + (size_t)i * d, p->eps, s);
+      k_cfg_sched<<<nblk(B * per), 256, 0, s>>>(p->eps, p->latents, nullptr, B * per, cfg_on ? 1 : 0,
+                                               c.guidance_scale, h->d_coefs, i);
+      count_launch(h);
+    }
+  }));
+  if (latents_out) {                                                             // mld.py:359
+    k_permute_01<<<nblk(B * per), 256, 0, st>>>(p->latents, latents_out, B, c.n_lat, d);
+    count_launch(h);
+  }
+  CK(cudaGetLastError());
+  if (plan_out) *plan_out = p;
+  return MLDB_OK;
+}
+
+extern "C" int mldb_diffusion_reverse(mldb_handle* h, const void* cond, const float* init_noise,
+                                      const float* step_noise, const int32_t* lengths, int32_t B,
+                                      int32_t S_ctx, int32_t T, float* latents_out, void* stream) {
+  TRY(check_ready(h, true));
+  if (!cond || !init_noise || !latents_out || B <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  if (step_noise) FAIL(MLDB_ERR_UNSUPPORTED, "per-step noise injection (DDPM) is not built yet");
+  return run_reverse(h, cond, init_noise, lengths, B, S_ctx, T, latents_out, (cudaStream_t)stream, nullptr);
+}
+
+// ----------------------------------------------------------------------------- VAE decode
+// z rows: [n_lat, B, d] fp32 -> memory tokens split [B * n_lat, d] (row = b * n_lat + j)
+__global__ void k_mem_tokens(ActBuf mem, const float* __restrict__ z, int n_lat, int B, int d) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n_lat * B * d) return;
+  const int n = (int)(idx % d);
+  const int b = (int)((idx / d) % B);
+  const int j = (int)(idx / ((int64_t)d * B));
+  __half hh, ll;
+  split_f32(z[idx], hh, ll);
+  const int64_t o = ((int64_t)b * n_lat + j) * mem.cols + n;
+  mem.hi[o] = hh;
+  mem.lo()[o] = ll;
+}
+
+static int dec_plan(mldb_handle* h, int B, int T, Plan** out) {
+  Plan* p = find_plan(h, 1, B, 0, T);
+  if (!p) {
+    const mldb_config& c = h->cfg;
+    if (T > h->vae_dec_pe_rows) FAIL(MLDB_ERR_INVALID, "T=%d exceeds the positional table (%d rows)", T, h->vae_dec_pe_rows);
+    p = add_plan(h, 1, B, 0, T);
+    TRY(alloc_stack_ws(h, h->vdec, B, T, c.n_lat, &p->ws));
+    TRY(alloc_act(h, B * c.n_lat, c.latent_dim, &p->mem));
+    TRY(dev_alloc(h, (void**)&p->lengths, (size_t)B * sizeof(int32_t)));
+    TRY(dev_alloc(h, (void**)&p->feats, (size_t)B * T * c.vae_nfeats * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&p->joints, (size_t)B * T * c.njoints * 3 * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&p->latents, (size_t)B * c.n_lat * c.latent_dim * sizeof(float)));
+  }
+  *out = p;
+  return MLDB_OK;
+}
+
+// z_is_plan_latents: z already sits in [n_lat,B,d] order in a device buffer
+static int run_decode(mldb_handle* h, const float* z, const int32_t* lengths, int B, int T,
+                      float* feats_out, cudaStream_t st, Plan** plan_out) {
+  const mldb_config& c = h->cfg;
+  if (c.vae_kind == MLDB_VAE_NONE) FAIL(MLDB_ERR_STATE, "no VAE configured");
+  Plan* p = nullptr;
+  TRY(dec_plan(h, B, T, &p));
+  const int d = c.latent_dim, F = c.vae_nfeats;
+  CK(cudaMemcpyAsync(p->lengths, lengths, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(p->latents, z, (size_t)B * c.n_lat * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  float* fout = feats_out ? feats_out : p->feats;
+  TRY(run_graphed(h, p, st, [&](cudaStream_t s) {
+    k_mem_tokens<<<nblk((int64_t)c.n_lat * B * d), 256, 0, s>>>(p->mem, p->latents, c.n_lat, B, d);
+    count_launch(h);
+    // queries = zeros + PE rows (mld_vae.py:190,224; actor_vae.py:219-225)
+    k_rows_to_split<<<nblk((int64_t)B * T * d), 256, 0, s>>>(p->ws.x0, nullptr, 0, B * T, d, T, T, 0, 0, h->vae_dec_pe);
+    count_launch(h);
+    SeqInfo si; si.lengths = p->lengths; si.kv_prefix = 0;
+    ActBuf x = run_stack(h, h->vdec, p->ws.x0, p->mem, p->ws, si, s);
+    if (h->vdec.norm.g) {
+      LnArgs l; l.res = x; l.gamma = h->vdec.norm.g; l.beta = h->vdec.norm.b; l.M = B * T; l.d = d; l.out = p->ws.x1;
+      op_ln(h, l, s);
+      x = p->ws.x1;
+    }
+    // final_layer + output[~mask.T] = 0 (mld_vae.py:243-245); rows are already [B, T]
+    GemmArgs g; g.a1 = x; g.K1 = d; g.M = B * T; g.w = h->final_layer; g.out_f32 = p->feats; g.ldc = F;
+    g.in_group = T; g.out_group = T; g.out_off = 0; g.zero_lengths = p->lengths;
+    op_gemm(h, g, s);
+  }));
+  if (fout != p->feats)
+    CK(cudaMemcpyAsync(fout, p->feats, (size_t)B * T * F * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (plan_out) *plan_out = p;
+  return MLDB_OK;
+}
+
+extern "C" int mldb_vae_decode(mldb_handle* h, const float* z, const int32_t* lengths, int32_t B,
+                               int32_t T, float* feats_out, void* stream) {
+  TRY(check_ready(h, false));
+  if (!z || !lengths || !feats_out || B <= 0 || T <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  return run_decode(h, z, lengths, B, T, feats_out, (cudaStream_t)stream, nullptr);
+}
+
+// ----------------------------------------------------------------------------- VAE encode
+__global__ void k_rows_out_permuted(const float* __restrict__ src, float* __restrict__ mu, float* __restrict__ logvar,
+                                    int B, int n_lat, int d) {
+  // src rows (b, j) j < 2*n_lat -> mu[j, b, :] (j < n_lat) / logvar[j - n_lat, b, :]
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)B * 2 * n_lat * d) return;
+  const int n = (int)(idx % d);
+  const int j = (int)((idx / d) % (2 * n_lat));
+  const int b = (int)(idx / ((int64_t)d * 2 * n_lat));
+  if (j < n_lat) mu[((int64_t)j * B + b) * d + n] = src[idx];
+  else logvar[((int64_t)(j - n_lat) * B + b) * d + n] = src[idx];
+}
+
+extern "C" int mldb_vae_encode(mldb_handle* h, const float* feats, const int32_t* lengths, int32_t B,
+                               int32_t T, float* mu, float* logvar, void* stream) {
+  TRY(check_ready(h, false));
+  if (!feats || !lengths || !mu || !logvar || B <= 0 || T <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  const mldb_config& c = h->cfg;
+  if (c.vae_kind != MLDB_VAE_MLD) FAIL(MLDB_ERR_UNSUPPORTED, "encode is built for MldVae only");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int d = c.latent_dim, G = 2 * c.n_lat, L = G + T;
+  if (L > 500) FAIL(MLDB_ERR_INVALID, "sequence too long for the learned PE table");
+  Plan* p = find_plan(h, 2, B, 0, T);
+  if (!p) {
+    p = add_plan(h, 2, B, 0, T);
+    TRY(alloc_stack_ws(h, h->venc, B, L, 0, &p->ws));
+    TRY(dev_alloc(h, (void**)&p->lengths, (size_t)B * sizeof(int32_t)));
+    TRY(dev_alloc(h, (void**)&p->stage_f32, (size_t)B * G * d * sizeof(float)));
+  }
+  CK(cudaMemcpyAsync(p->lengths, lengths, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  // skel_embedding rows -> token rows (b, G + t) + PE (mld_vae.py:139-161)
+  GemmArgs g; g.a_kind = A_F32; g.a_f32 = feats; g.lda = c.vae_nfeats; g.M = B * T; g.w = h->skel_emb;
+  g.out = p->ws.x0; g.in_group = T; g.out_group = L; g.out_off = G; g.addtab = h->vae_enc_pe;
+  op_gemm(h, g, st);
+  // global motion tokens (b, 0..G-1) = token + PE (mld_vae.py:146,157)
+  k_rows_to_split<<<nblk((int64_t)B * G * d), 256, 0, st>>>(p->ws.x0, h->global_token, d, B * G, d, G, L, 0, 1, h->vae_enc_pe);
+  count_launch(h);
+  SeqInfo si; si.lengths = p->lengths; si.kv_prefix = G;
+  ActBuf x = run_stack(h, h->venc, p->ws.x0, ActBuf{}, p->ws, si, st);
+  LnArgs l; l.res = x; l.gamma = h->venc.norm.g; l.beta = h->venc.norm.b; l.M = B * G; l.d = d;
+  l.sel_group = G; l.in_group = L; l.out_f32 = p->stage_f32; l.ld_out = d;
+  op_ln(h, l, st);
+  k_rows_out_permuted<<<nblk((int64_t)B * G * d), 256, 0, st>>>(p->stage_f32, mu, logvar, B, c.n_lat, d);
+  count_launch(h);
+  CK(cudaGetLastError());
+  return MLDB_OK;
+}
+
+// ----------------------------------------------------------------------------- feats2joints
+static int run_f2j(mldb_handle* h, const float* feats, int B, int T, float* joints, cudaStream_t st) {
+  const mldb_config& c = h->cfg;
+  const int F = c.vae_kind != MLDB_VAE_NONE ? c.vae_nfeats : c.nfeats;
+  if (!h->mean || h->nstat != F) FAIL(MLDB_ERR_STATE, "call mldb_set_mean_std with %d features first", F);
+  if (F < 4 + (c.njoints - 1) * 3) FAIL(MLDB_ERR_UNSUPPORTED, "feats2joints needs the HumanML3D/KIT layout");
+  k_feats2joints<<<B, 256, (size_t)4 * T * sizeof(float), st>>>(feats, h->mean, h->stdv, T, F, c.njoints, joints);
+  count_launch(h);
+  CK(cudaGetLastError());
+  return MLDB_OK;
+}
+extern "C" int mldb_feats2joints(mldb_handle* h, const float* feats, int32_t B, int32_t T,
+                                 float* joints_out, void* stream) {
+  TRY(check_ready(h, false));
+  if (!feats || !joints_out || B <= 0 || T <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  return run_f2j(h, feats, B, T, joints_out, (cudaStream_t)stream);
+}
+
+// ----------------------------------------------------------------------------- full sample
+extern "C" int mldb_sample(mldb_handle* h, const void* cond, const float* init_noise,
+                           const int32_t* lengths, int32_t B, int32_t S_ctx, int32_t T,
+                           float* latents_out, float* feats_out, float* joints_out, void* stream) {
+  TRY(check_ready(h, true));
+  if (!cond || !init_noise || !lengths || B <= 0 || T <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan *rp = nullptr, *dp = nullptr;
+  TRY(dec_plan(h, B, T, &dp));
+  const mldb_config& c = h->cfg;
+  // reverse diffusion writes [n_lat, B, d] into the decode plan's staging buffer
+  float* z = latents_out;
+  if (!z) {
+    if (!dp->stage_f32) TRY(dev_alloc(h, (void**)&dp->stage_f32, (size_t)B * c.n_lat * c.latent_dim * sizeof(float)));
+    z = dp->stage_f32;
+  }
+  TRY(run_reverse(h, cond, init_noise, lengths, B, S_ctx, T, z, st, &rp));
+  TRY(run_decode(h, z, lengths, B, T, feats_out, st, &dp));
+  if (joints_out) TRY(run_f2j(h, feats_out ? feats_out : dp->feats, B, T, joints_out, st));
+  return MLDB_OK;
+}
+
+extern "C" int mldb_sample_host(mldb_handle* h, const void* cond_host, const float* init_noise_host,
+                                const int32_t* lengths_host, int32_t B, int32_t S_ctx, int32_t T,
+                                float* joints_host, void* stream) {
+  TRY(check_ready(h, true));
+  if (!cond_host || !init_noise_host || !lengths_host || !joints_host || B <= 0 || T <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mldb_config& c = h->cfg;
+  Plan* dp = nullptr;
+  TRY(dec_plan(h, B, T, &dp));
+  const bool cfg_on = c.guidance_scale > 1.0f;
+  const int Bx = cfg_on ? 2 * B : B;
+  const size_t cond_bytes = c.cond_kind == MLDB_COND_TEXT ? (size_t)Bx * S_ctx * c.text_dim * sizeof(float)
+                                                         : (size_t)Bx * sizeof(int64_t);
+  const size_t noise_bytes = (size_t)B * c.n_lat * c.latent_dim * sizeof(float);
+  if (dp->cond_cap < cond_bytes) {
+    TRY(dev_alloc(h, (void**)&dp->cond_f, cond_bytes));
+    dp->cond_cap = cond_bytes;
+  }
+  if (!dp->noise_in) {
+    TRY(dev_alloc(h, (void**)&dp->noise_in, noise_bytes));
+    TRY(dev_alloc(h, (void**)&dp->cond_i, (size_t)B * sizeof(int32_t)));
+  }
+  CK(cudaMemcpyAsync(dp->cond_f, cond_host, cond_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dp->noise_in, init_noise_host, noise_bytes, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dp->cond_i, lengths_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  TRY(mldb_sample(h, dp->cond_f, dp->noise_in, (const int32_t*)dp->cond_i, B, S_ctx, T, nullptr, nullptr, dp->joints, stream));
+  CK(cudaMemcpyAsync(joints_host, dp->joints, (size_t)B * T * c.njoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  return MLDB_OK;
+}

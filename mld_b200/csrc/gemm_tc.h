@@ -1,0 +1,13 @@
+// tcgen05 (5th-gen tensor core) split-fp16 GEMM with fused epilogues - interface.
+#pragma once
+#include "ops.cuh"
+
+struct TcCtx;
+TcCtx* tc_create(int device);
+void tc_destroy(TcCtx* c);
+// can this GEMM run on the tensor-core kernel (shape / alignment constraints)?
+bool tc_gemm_supported(const TcCtx* c, const GemmArgs& g);
+// ... with the residual + LayerNorm epilogue fused (the tile must cover a full row)?
+bool tc_gemm_ln_supported(const TcCtx* c, const GemmArgs& g, const LnArgs& l);
+// enqueue; ln == nullptr for the plain epilogue
+void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st);

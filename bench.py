@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""Benchmark of the MLD sampling path: motions/sec @ 50-step DDIM text-to-motion, batch 256
+(BASELINE.json configs[2]: 77-token CLIP context, latent 1x256, decode to 196x263, joints).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+One "step" = one full pass of the hot path over one batch of synthetic input: 50 x (denoiser on
+2B sequences + CFG + DDIM update) + VAE decode + feats2joints (+ the all-gather of finished
+motions when N > 1).  Weak scaling: B = 256 motions per GPU.  Rank 0 prints ONE JSON line.
+``--impl reference`` times the CPU restatement of the reference path (the oracle, pinned against
+the reference's own modules; the reference itself is Python and does not exist on the GPU box)
+on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU, S_CTX, T_MAX, N_STEPS_DDIM = 256, 77, 196, 50
+WORKLOAD = "text-to-motion B=256/GPU, 77-token CLIP ctx, 50 DDIM steps (CFG 7.5), decode 196x263, joints"
+# algorithmic FLOPs per motion as the reference executes it
+FLOP_PER_MOTION = 132.77e9
+CPU_SAMPLE_B = 16
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int = 0):
+        self.rows, self._p, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self._p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                        "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self._p = None
+
+    def _read(self):
+        for line in self._p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self._p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self._p.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_sample(torch, B: int, threads: int):
+    """One bounded sample of the workload on the host cores through the oracle (fp32, eval)."""
+    from mld_b200 import synth
+    from oracle import mld_oracle as O
+    torch.set_num_threads(threads)
+    dsd, vsd = synth.denoiser_state_dict(1234), synth.mld_vae_state_dict(4321)
+    mean, std = synth.mean_std()
+    ctx, noise = synth.text_context(B, S_CTX, seed=1), synth.init_noise(B, seed=2)
+
+    def run():
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            O.mld_forward(dsd, O.DenoiserCfg(), vsd, O.VaeCfg(), O.DDIMScheduler(), N_STEPS_DDIM, ctx, noise,
+                          [T_MAX] * B, mean, std)
+            return time.perf_counter() - t0
+    return run
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    run = cpu_reference_sample(torch, CPU_SAMPLE_B, cores)
+    for _ in range(args.warmup):
+        run()
+    times = [run() for _ in range(args.steps)]
+    total = sum(times)
+    value = CPU_SAMPLE_B * args.steps / total
+    sample = f"{CPU_SAMPLE_B} motions per step of the B=256 workload (same shapes, 50 DDIM steps, decode, joints)"
+    print(json.dumps({
+        "impl": "reference", "metric": "motions/sec @ 50-step DDIM text-to-motion, batch 256", "value": value,
+        "unit": "motions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "cpu_sample_motions": CPU_SAMPLE_B},
+        "cpu_baseline": {"value": value, "unit": "motions/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "motions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    g.build()
+    from mld_b200 import synth
+    from mld_b200.engine import Engine, make_config
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = B_PER_GPU
+    dsd, vsd = synth.denoiser_state_dict(1234), synth.mld_vae_state_dict(4321)
+    mean, std = synth.mean_std()
+    eng = Engine(make_config(), local_rank)
+    eng.load_state_dict(dsd, "denoiser.")
+    eng.load_state_dict(vsd, "vae.")
+    eng.finalize()
+    eng.set_mean_std(mean, std)
+    eng.set_timesteps(N_STEPS_DDIM)
+
+    lengths = [T_MAX] * B
+    ctx_h = synth.text_context(B, S_CTX, seed=1 + rank).pin_memory()
+    noise_h = synth.init_noise(B, seed=2 + rank).pin_memory()
+    len_h = torch.tensor(lengths, dtype=torch.int32).pin_memory()
+    joints_h = torch.empty((B, T_MAX, 22, 3), dtype=torch.float32).pin_memory()
+    ctx_d, noise_d, len_d = ctx_h.to(dev), noise_h.to(dev), len_h.to(dev)
+    gathered = torch.empty((world * B, T_MAX, 22, 3), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        out = eng.sample(ctx_d, noise_d, len_d_list, want=("joints",))["joints"]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)     # the one collective of the path
+        return out
+
+    def step_e2e():
+        if world == 1:
+            eng.sample_host(ctx_h, noise_h, len_h, joints_h, T_MAX)    # C-ABI call with HOST buffers
+        else:
+            c, z = ctx_h.to(dev, non_blocking=True), noise_h.to(dev, non_blocking=True)
+            out = eng.sample(c, z, len_d_list, want=("joints",))["joints"]
+            dist.all_gather_into_tensor(gathered, out)
+            joints_h.copy_(out, non_blocking=True)
+
+    class _L(list):     # lengths list with a cached max (avoids a sync per call)
+        pass
+    len_d_list = _L(lengths)
+
+    def timed(fn, K, W):
+        for _ in range(W):
+            fn()
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = eng.launch_count
+        e0.record()
+        for a, b in evs:
+            a.record()
+            fn()
+            b.record()
+        e1.record()
+        barrier()
+        total_ms = e0.elapsed_time(e1)
+        per = [a.elapsed_time(b) for a, b in evs]
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)      # max over ranks
+        return float(t.item()), per, eng.launch_count - l0
+
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    total_ms, per, launches = timed(step_device, args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    e2e_ms, _, _ = timed(step_e2e, args.steps, 1)
+
+    value = world * B * args.steps / (total_ms / 1e3)
+    e2e_value = world * B * args.steps / (e2e_ms / 1e3)
+    peaks, peak_src = _peaks()
+
+    # dominant kernel: the FFN up-projection GEMM (+GELU) of one encoder layer, timed in isolation
+    roof = None
+    if rank == 0:
+        M = 2 * B * (1 + 1 + S_CTX)
+        ops = {"qkv": 2.0 * M * 256 * 768, "ffn1": 2.0 * M * 256 * 1024, "ffn2_ln": 2.0 * M * 1024 * 256,
+               "outproj_ln": 2.0 * M * 256 * 256, "attn": 4.0 * M * (1 + 1 + S_CTX) * 256}
+        times = {k: eng.profile_op(k, B, S_CTX, 10) for k in ops}
+        layer_ms = eng.profile_op("layer", B, S_CTX, 5)
+        dom = max(times, key=times.get)
+        peak = peaks.get("bf16_tflops", 1590.0)
+        achieved = ops[dom] / (times[dom] * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "op_ms": {k: round(v, 4) for k, v in times.items()}, "layer_ms": round(layer_ms, 4),
+                "path_tflops": FLOP_PER_MOTION * value / 1e12,
+                "path_frac_of_sustained": FLOP_PER_MOTION * value / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        run = cpu_reference_sample(torch, CPU_SAMPLE_B, cores)
+        run()
+        dt = min(run(), run())
+        cpu = {"value": CPU_SAMPLE_B / dt, "unit": "motions/s", "cores": cores, "kind": "port",
+               "sample": f"{CPU_SAMPLE_B} motions of the same workload (77-token ctx, 50 DDIM steps, decode, joints), "
+                         f"best of 2 after 1 warm-up, oracle port pinned to the reference modules"}
+
+    if rank == 0:
+        h2d = ctx_h.numel() * 4 + noise_h.numel() * 4 + len_h.numel() * 4
+        d2h = joints_h.numel() * 4
+        print(json.dumps({
+            "metric": "motions/sec @ 50-step DDIM text-to-motion, batch 256", "value": value, "unit": "motions/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "ddim_step_p50_ms": statistics.median(per) / N_STEPS_DDIM, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f16x2-split (fp32-equivalent, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "parallelism": f"batch-sharded dp{world}",
+                       "l2": "working set (ctx 121 MB + activations > 700 MB) exceeds the 126 MB L2; no flush needed",
+                       "weights": "random-init (seeded), reference architecture"},
+            "e2e": {"value": e2e_value, "unit": "motions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -188,6 +188,13 @@ int mldb_sample_host(mldb_handle* h, const void* cond_host, const float* init_no
                      const int32_t* lengths_host, int32_t B, int32_t S_ctx, int32_t T,
                      float* joints_host, void* stream);
 
+/* Profiling aid used by bench.py's roofline leg: time one operator of denoiser layer 0 in
+ * isolation on the (B, S_ctx) workspace (`iters` back-to-back launches between CUDA events on an
+ * internal stream; synchronous).  op: "qkv" | "attn" | "outproj_ln" | "ffn1" | "ffn2_ln" | "layer".
+ * avg_ms_out: HOST float. */
+int mldb_profile_op(mldb_handle* h, const char* op, int32_t B, int32_t S_ctx, int32_t iters,
+                    float* avg_ms_out);
+
 /* Introspection */
 const char* mldb_last_error(void);
 int mldb_abi_version(void);

@@ -1101,3 +1101,59 @@ extern "C" int mldb_sample_host(mldb_handle* h, const void* cond_host, const flo
   CK(cudaMemcpyAsync(joints_host, dp->joints, (size_t)B * T * c.njoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
   return MLDB_OK;
 }
+
+// ----------------------------------------------------------------------------- profiling aid
+// Time one operator of denoiser layer 0 in isolation on the real workspace of the (B, S_ctx)
+// reverse plan: `iters` back-to-back launches bracketed by CUDA events on `stream`.
+// op: "qkv" | "attn" | "outproj_ln" | "ffn1" | "ffn2_ln" | "layer".  avg_ms_out: HOST float.
+extern "C" int mldb_profile_op(mldb_handle* h, const char* op, int32_t B, int32_t S_ctx, int32_t iters,
+                               float* avg_ms_out) {
+  TRY(check_ready(h, false));
+  if (!op || !avg_ms_out || iters <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  const mldb_config& c = h->cfg;
+  if (c.num_layers == 0 || c.arch != MLDB_ARCH_TRANS_ENC) FAIL(MLDB_ERR_UNSUPPORTED, "needs the trans_enc denoiser");
+  const bool cfg_on = c.guidance_scale > 1.0f;
+  Plan* p = nullptr;
+  TRY(enc_plan(h, 0, B, cfg_on ? 2 * B : B, S_ctx, &p));
+  cudaStream_t st = h->cap_stream;
+  StackWs& ws = p->ws;
+  const EncW& w = h->den.enc[0];
+  const int d = ws.d;
+  SeqInfo si;
+  auto run = [&]() -> int {
+    if (!strcmp(op, "qkv")) {
+      GemmArgs g; g.a1 = ws.x0; g.K1 = d; g.M = ws.M; g.w = w.in_proj; g.out = ws.qkv; op_gemm(h, g, st);
+    } else if (!strcmp(op, "attn")) {
+      AttnArgs a; a.q = ws.qkv; a.Lq = ws.L; a.kv = ws.qkv; a.k_col0 = d; a.v_col0 = 2 * d; a.Lk = ws.L;
+      a.nseq = ws.nseq; a.heads = c.num_heads; a.hd = d / c.num_heads; a.out = ws.att; op_attn(h, a, st);
+    } else if (!strcmp(op, "outproj_ln")) {
+      GemmArgs g; g.a1 = ws.att; g.K1 = d; g.M = ws.M; g.w = w.out_proj;
+      LnArgs l; l.res = ws.x0; l.gamma = w.n1.g; l.beta = w.n1.b; l.M = ws.M; l.d = d; l.out = ws.x1;
+      op_gemm_ln(h, g, l, ws.cf32, st);
+    } else if (!strcmp(op, "ffn1")) {
+      GemmArgs g; g.a1 = ws.x1; g.K1 = d; g.M = ws.M; g.w = w.l1; g.act = ACT_GELU; g.out = ws.h; op_gemm(h, g, st);
+    } else if (!strcmp(op, "ffn2_ln")) {
+      GemmArgs g; g.a1 = ws.h; g.K1 = ws.ff; g.M = ws.M; g.w = w.l2;
+      LnArgs l; l.res = ws.x1; l.gamma = w.n2.g; l.beta = w.n2.b; l.M = ws.M; l.d = d; l.out = ws.cur[0];
+      op_gemm_ln(h, g, l, ws.cf32, st);
+    } else if (!strcmp(op, "layer")) {
+      enc_layer(h, h->den, w, ws.x0, ws.cur[0], ws, si, st);
+    } else {
+      FAIL(MLDB_ERR_INVALID, "unknown op %s", op);
+    }
+    return MLDB_OK;
+  };
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) TRY(run());
+  CK(cudaEventRecord(e0, st));
+  for (int i = 0; i < iters; ++i) TRY(run());
+  CK(cudaEventRecord(e1, st));
+  CK(cudaStreamSynchronize(st));
+  float ms = 0.0f;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  CK(cudaGetLastError());
+  *avg_ms_out = ms / (float)iters;
+  return MLDB_OK;
+}

@@ -66,6 +66,12 @@ class Engine:
     def set_option(self, name: str, value: str):
         check(self.lib.mldb_set_option(self._h, name.encode(), value.encode()), "mldb_set_option")
 
+    def profile_op(self, op: str, B: int, S_ctx: int, iters: int = 20) -> float:
+        """Average ms of one operator of denoiser layer 0 in isolation (bench.py roofline leg)."""
+        ms = C.c_float()
+        check(self.lib.mldb_profile_op(self._h, op.encode(), B, S_ctx, iters, C.byref(ms)), "mldb_profile_op")
+        return float(ms.value)
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.mldb_launch_count(self._h))

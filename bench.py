@@ -32,6 +32,18 @@ FLOP_PER_MOTION = 132.77e9
 CPU_SAMPLE_B = 16
 
 
+_T0 = time.time()
+
+
+def _log(msg: str):
+    print(f"[bench +{time.time() - _T0:6.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
+def _cpu_threads() -> int:
+    # torch's intra-op pool on hundreds of threads thrashes on these small GEMMs; cap it
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -97,11 +109,14 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    cores = os.cpu_count() or 1
+    cores = _cpu_threads()
     run = cpu_reference_sample(torch, CPU_SAMPLE_B, cores)
     for _ in range(args.warmup):
-        run()
-    times = [run() for _ in range(args.steps)]
+        _log(f"reference warm-up: {run():.2f}s")
+    times = []
+    for _ in range(args.steps):
+        times.append(run())
+        _log(f"reference step: {times[-1]:.2f}s")
     total = sum(times)
     value = CPU_SAMPLE_B * args.steps / total
     sample = f"{CPU_SAMPLE_B} motions per step of the B=256 workload (same shapes, 50 DDIM steps, decode, joints)"
@@ -152,6 +167,7 @@ def main():
     eng.finalize()
     eng.set_mean_std(mean, std)
     eng.set_timesteps(N_STEPS_DDIM)
+    _log("engine ready")
 
     lengths = [T_MAX] * B
     ctx_h = synth.text_context(B, S_CTX, seed=1 + rank).pin_memory()
@@ -211,7 +227,9 @@ def main():
         clocks.start()
     total_ms, per, launches = timed(step_device, args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else None
+    _log(f"device-resident: {total_ms / args.steps:.1f} ms/step")
     e2e_ms, _, _ = timed(step_e2e, args.steps, 1)
+    _log(f"e2e: {e2e_ms / args.steps:.1f} ms/step")
 
     value = world * B * args.steps / (total_ms / 1e3)
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
@@ -223,7 +241,10 @@ def main():
         M = 2 * B * (1 + 1 + S_CTX)
         ops = {"qkv": 2.0 * M * 256 * 768, "ffn1": 2.0 * M * 256 * 1024, "ffn2_ln": 2.0 * M * 1024 * 256,
                "outproj_ln": 2.0 * M * 256 * 256, "attn": 4.0 * M * (1 + 1 + S_CTX) * 256}
-        times = {k: eng.profile_op(k, B, S_CTX, 10) for k in ops}
+        times = {}
+        for k in ops:
+            times[k] = eng.profile_op(k, B, S_CTX, 10)
+            _log(f"op {k}: {times[k]:.3f} ms")
         layer_ms = eng.profile_op("layer", B, S_CTX, 5)
         dom = max(times, key=times.get)
         peak = peaks.get("bf16_tflops", 1590.0)
@@ -236,10 +257,12 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = _cpu_threads()
+        _log(f"cpu baseline on {cores} threads")
         run = cpu_reference_sample(torch, CPU_SAMPLE_B, cores)
         run()
         dt = min(run(), run())
+        _log(f"cpu baseline: {dt:.2f}s per {CPU_SAMPLE_B} motions")
         cpu = {"value": CPU_SAMPLE_B / dt, "unit": "motions/s", "cores": cores, "kind": "port",
                "sample": f"{CPU_SAMPLE_B} motions of the same workload (77-token ctx, 50 DDIM steps, decode, joints), "
                          f"best of 2 after 1 warm-up, oracle port pinned to the reference modules"}

@@ -195,6 +195,14 @@ int mldb_sample_host(mldb_handle* h, const void* cond_host, const float* init_no
 int mldb_profile_op(mldb_handle* h, const char* op, int32_t B, int32_t S_ctx, int32_t iters,
                     float* avg_ms_out);
 
+/* Debug aid for the kernel unit tests: y = act(A W^T + b), or LayerNorm(A W^T + b + R) when gamma is
+ * given, through the engine's GEMM operators (use_tc: 1 = tcgen05 path, 0 = CUDA-core path).
+ * A [M,K], R [M,N], out [M,N]: fp32 DEVICE; W [N,K], bias/gamma/beta [N]: fp32 HOST.  0 < K1 < K feeds
+ * A as two concatenated sources (the skip-connection GEMM).  Synchronous. */
+int mldb_debug_gemm(mldb_handle* h, const float* A, const float* W, const float* bias, const float* gamma,
+                    const float* beta, const float* R, int32_t M, int32_t N, int32_t K, int32_t K1,
+                    int32_t act, int32_t use_tc, float* out, void* stream);
+
 /* Introspection */
 const char* mldb_last_error(void);
 int mldb_abi_version(void);

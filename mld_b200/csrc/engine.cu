@@ -1157,3 +1157,60 @@ extern "C" int mldb_profile_op(mldb_handle* h, const char* op, int32_t B, int32_
   *avg_ms_out = ms / (float)iters;
   return MLDB_OK;
 }
+
+// ----------------------------------------------------------------------------- debug aid
+// y = act(A W^T + b) or LayerNorm(A W^T + b + R) through the engine's GEMM operators, so tests can
+// compare the tcgen05 kernels with the CUDA-core kernels (and with torch) shape by shape.
+//   A [M,K] fp32 device; W [N,K], bias [N], gamma/beta [N] fp32 HOST (gamma == NULL: no LN);
+//   R [M,N] fp32 device or NULL; K1 < K splits A into two concatenated sources (skip connection);
+//   out [M,N] fp32 device.  use_tc: 1 tensor-core path, 0 CUDA-core path.  Synchronous.
+__global__ void k_split_to_f32(ActBuf X, float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = join_f32(X.hi[i], X.lo()[i]);
+}
+extern "C" int mldb_debug_gemm(mldb_handle* h, const float* A, const float* W, const float* bias,
+                               const float* gamma, const float* beta, const float* R, int32_t M, int32_t N,
+                               int32_t K, int32_t K1, int32_t act, int32_t use_tc, float* out, void* stream) {
+  if (!h || !A || !W || !out || M <= 0 || N <= 0 || K <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_alloc0 = h->allocs.size();
+  LinW w;
+  TRY(pack_linear(h, W, N, K, bias, &w));
+  if (K1 <= 0 || K1 >= K) K1 = K;
+  ActBuf a1, a2{}, res{}, o{};
+  TRY(alloc_act(h, M, K1, &a1));
+  k_rows_to_split<<<nblk((int64_t)M * K1), 256, 0, st>>>(a1, A, K, M, K1, 1 << 30, 0, 0, 0, nullptr);
+  if (K1 < K) {
+    TRY(alloc_act(h, M, K - K1, &a2));
+    k_rows_to_split<<<nblk((int64_t)M * (K - K1)), 256, 0, st>>>(a2, A + K1, K, M, K - K1, 1 << 30, 0, 0, 0, nullptr);
+  }
+  float *g = nullptr, *b = nullptr, *cf32 = nullptr;
+  const bool saved = h->use_tc;
+  h->use_tc = use_tc != 0;
+  GemmArgs ga; ga.a1 = a1; ga.K1 = K1; ga.a2 = a2; ga.K2 = K - K1; ga.M = M; ga.w = w; ga.act = act;
+  int rc = MLDB_OK;
+  if (gamma) {
+    TRY(upload_f32(h, gamma, N, &g));
+    TRY(upload_f32(h, beta, N, &b));
+    TRY(dev_alloc(h, (void**)&cf32, (size_t)M * N * sizeof(float)));
+    TRY(alloc_act(h, M, N, &o));
+    if (R) {
+      TRY(alloc_act(h, M, N, &res));
+      k_rows_to_split<<<nblk((int64_t)M * N), 256, 0, st>>>(res, R, N, M, N, 1 << 30, 0, 0, 0, nullptr);
+    }
+    LnArgs l; l.res = res; l.gamma = g; l.beta = b; l.M = M; l.d = N; l.out = o;
+    op_gemm_ln(h, ga, l, cf32, st);
+    k_split_to_f32<<<nblk((int64_t)M * N), 256, 0, st>>>(o, out, (int64_t)M * N);
+  } else {
+    ga.out_f32 = out; ga.ldc = N;
+    op_gemm(h, ga, st);
+  }
+  h->use_tc = saved;
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  // release the temporaries
+  while (h->allocs.size() > n_alloc0) { cudaFree(h->allocs.back()); h->allocs.pop_back(); }
+  if (e != cudaSuccess) FAIL(MLDB_ERR_CUDA, "debug gemm: %s", cudaGetErrorString(e));
+  return rc;
+}

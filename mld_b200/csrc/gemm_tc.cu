@@ -1,8 +1,489 @@
-// placeholder until the tcgen05 kernel lands
+// tcgen05 (5th-gen tensor core) split-fp16 GEMM for sm_100a with fused epilogues.
+//
+//   D[128 x BN] (fp32, TMEM) = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T        per 128-row tile
+//
+// A = activations in the split16 format (two fp16 planes, row-major [M, K]); W = nn.Linear weight
+// [N, K] (PyTorch's [out, in] layout is already the K-major B operand), also split into hi/lo
+// planes.  Three kind::f16 MMAs per K-step reproduce the reference's fp32 GEMM to ~1e-6.
+//
+// CTA = 6 warps: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer
+// (one lane), warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Operands stream through a
+// STAGES-deep ring of 128B-swizzled shared-memory tiles (BK = 64 halves = one swizzle row) filled
+// by cp.async.bulk.tensor (TMA) and released by tcgen05.commit; the accumulator is read back with
+// tcgen05.ld.  Epilogues: bias (+ positional table) + activation -> split16 / fp32 store, or
+// bias + residual + LayerNorm over the full row (BN == N == 256) -> split16 store, with the row's
+// pre-norm values parked in TMEM between the statistics passes.
 #include "gemm_tc.h"
-struct TcCtx { int device; };
-TcCtx* tc_create(int device) { return new TcCtx{device}; }
+
+#include <cuda.h>
+#include <stdio.h>
+
+#include <string>
+
+void mldb_set_err(const std::string& s);
+
+namespace {
+
+constexpr int BM = 128, BK = 64;
+constexpr int NUM_THREADS = 192;
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  long long t0 = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && (++spins & 1023u) == 0) {         // a lost arrival must not hang the GPU
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();  // ~2 s
+    }
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4 | LBO (ignored for swizzled K-major; 1) << 16 | SBO = 1024 B (8 rows x 128 B)
+// << 32 | version 1 << 46 | layout SWIZZLE_128B (2) << 61.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bit 4), A = B = F16 (0),
+// both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
+__host__ __device__ constexpr uint32_t make_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// ------------------------------------------------------------------------------ parameters
+struct TcParams {
+  int M, N, kblocks, kb1;
+  float inv_scale;
+  const float* bias;
+  const float* addtab;
+  int act;
+  __half* out_hi; __half* out_lo; int ld_out, out_col0;
+  float* out_f32; int ldc;
+  int in_group, out_group, out_off;
+  const int32_t* zero_lengths;
+  // residual + LayerNorm epilogue
+  int ln;
+  const __half* res_hi; const __half* res_lo; int ld_res;
+  const float* rowvec; int rv_group;
+  const float* gamma; const float* beta;
+  const float* gamma2; const float* beta2;
+};
+
+template <int BN>
+struct TileCfg {
+  static constexpr int STAGES = BN == 256 ? 2 : 3;
+  static constexpr int A_BYTES = BM * BK * 2;          // one plane of the A tile (16 KB)
+  static constexpr int W_BYTES = BN * BK * 2;          // one plane of the W tile
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int AUX_BYTES = 4 * BN * 4 + 256;   // bias, gamma, beta (+ spare) + barriers
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;   // + alignment slack
+};
+
+__device__ __forceinline__ void store_split_chunk(const float (&v)[32], __half* hi, __half* lo) {
+  uint32_t ph[16], pl[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    __half h0, l0, h1, l1;
+    split_f32(v[2 * i], h0, l0);
+    split_f32(v[2 * i + 1], h1, l1);
+    __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+    ph[i] = *reinterpret_cast<uint32_t*>(&hh);
+    pl[i] = *reinterpret_cast<uint32_t*>(&ll);
+  }
+  uint4* dh = reinterpret_cast<uint4*>(hi);
+  uint4* dl = reinterpret_cast<uint4*>(lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    dh[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+    dl[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+  }
+}
+
+__device__ __forceinline__ void load_split_chunk(const __half* hi, const __half* lo, float (&v)[32]) {
+  const uint4* sh = reinterpret_cast<const uint4*>(hi);
+  const uint4* sl = reinterpret_cast<const uint4*>(lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 a = sh[i], b = sl[i];
+    const uint32_t ah[4] = {a.x, a.y, a.z, a.w}, bl[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 h2 = *reinterpret_cast<const __half2*>(&ah[j]);
+      const __half2 l2 = *reinterpret_cast<const __half2*>(&bl[j]);
+      const float2 hf = __half22float2(h2), lf = __half22float2(l2);
+      v[i * 8 + j * 2] = hf.x + lf.x;
+      v[i * 8 + j * 2 + 1] = hf.y + lf.y;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ the kernel
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
+          const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
+          const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
+          const TcParams p) {
+  using Cfg = TileCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
+  float* s_bias = reinterpret_cast<float*>(aux);
+  float* s_gamma = s_bias + BN;
+  float* s_beta = s_gamma + BN;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 4 * BN * 4);   // full[S], empty[S], tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bars[s]), 1);
+      mbar_init(smem_u32(&bars[STAGES + s]), 1);
+    }
+    mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmA1h); tma_prefetch_desc(&tmA1l); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < BN; i += 128) {
+      const int n = n0 + i;
+      s_bias[i] = (p.bias && n < p.N) ? p.bias[n] : 0.0f;
+      if (p.ln) { s_gamma[i] = p.gamma[n]; s_beta[i] = p.beta[n]; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(smem_u32(&bars[STAGES + s]), ph ^ 1u);
+        const uint32_t full = smem_u32(&bars[s]);
+        mbar_expect_tx(full, Cfg::STAGE_BYTES);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        const uint32_t sAh = smem_u32(st), sAl = sAh + Cfg::A_BYTES, sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
+        if (kb < p.kb1) {
+          tma_load_2d(sAh, &tmA1h, full, kb * BK, m0);
+          tma_load_2d(sAl, &tmA1l, full, kb * BK, m0);
+        } else {
+          tma_load_2d(sAh, &tmA2h, full, (kb - p.kb1) * BK, m0);
+          tma_load_2d(sAl, &tmA2l, full, (kb - p.kb1) * BK, m0);
+        }
+        tma_load_2d(sWh, &tmWh, full, kb * BK, n0);
+        tma_load_2d(sWl, &tmWl, full, kb * BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc(BN);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+        mbar_wait(smem_u32(&bars[s]), ph);
+        tc_fence_after();
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        const uint32_t sAh = smem_u32(st), sAl = sAh + Cfg::A_BYTES, sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint32_t off = kk * 32;   // 16 halves = 32 bytes inside the 128B swizzle row
+          const uint64_t ah = make_desc(sAh + off), al = make_desc(sAl + off);
+          const uint64_t wh = make_desc(sWh + off), wl = make_desc(sWl + off);
+          umma(tmem_base, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
+          umma(tmem_base, ah, wl, idesc, 1u);
+          umma(tmem_base, ah, wh, idesc, 1u);
+        }
+        umma_commit(smem_u32(&bars[STAGES + s]));   // frees the stage when these MMAs retire
+      }
+      umma_commit(smem_u32(&bars[2 * STAGES]));     // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    const int m = m0 + row;
+    const bool row_ok = m < p.M;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    mbar_wait(smem_u32(&bars[2 * STAGES]), 0);
+    tc_fence_after();
+    uint32_t r[32];
+    float v[32];
+    if (!p.ln) {
+      int seq = 0, pos = m;
+      if (row_ok && p.in_group < p.M) { seq = m / p.in_group; pos = m - seq * p.in_group; }
+      const int64_t orow = (int64_t)seq * p.out_group + p.out_off + pos;
+      const bool zero = row_ok && p.zero_lengths != nullptr && pos >= p.zero_lengths[seq];
+      const float* tab = p.addtab ? p.addtab + (int64_t)(p.out_off + pos) * p.N : nullptr;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        tmem_ld32(trow + c * 32, r);            // warp-collective: no divergence around it
+        const int nb = n0 + c * 32;
+        if (row_ok && nb < p.N) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(r[i]) * p.inv_scale + s_bias[c * 32 + i];
+          if (tab && nb + i < p.N) x += tab[nb + i];
+          x = apply_act(x, p.act);
+          v[i] = zero ? 0.0f : x;
+        }
+        if (p.out_hi) {
+          if (nb + 32 <= p.N) {
+            const int64_t o = orow * p.ld_out + p.out_col0 + nb;
+            store_split_chunk(v, p.out_hi + o, p.out_lo + o);
+          } else {
+            for (int i = 0; i < 32 && nb + i < p.N; ++i) {
+              __half h, l;
+              split_f32(v[i], h, l);
+              const int64_t o = orow * p.ld_out + p.out_col0 + nb + i;
+              p.out_hi[o] = h; p.out_lo[o] = l;
+            }
+          }
+        }
+        if (p.out_f32) {
+          float* dst = p.out_f32 + orow * p.ldc + nb;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (nb + i < p.N) dst[i] = v[i];
+        }
+        }
+        __syncwarp();
+      }
+    } else {
+      // x = acc*s + bias + residual (+ rowvec); y = LayerNorm(x) (two-pass statistics, eps 1e-5).
+      const float* rv = (row_ok && p.rowvec) ? p.rowvec + (int64_t)(m / p.rv_group) * BN : nullptr;
+      float sum = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        tmem_ld32(trow + c * 32, r);
+        if (row_ok && p.res_hi) {
+          const int64_t o = (int64_t)m * p.ld_res + c * 32;
+          load_split_chunk(p.res_hi + o, p.res_lo + o, v);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float x = __uint_as_float(r[i]) * p.inv_scale + s_bias[c * 32 + i] + v[i];
+          if (rv) x += rv[c * 32 + i];
+          sum += x;
+          r[i] = __float_as_uint(x);
+        }
+        tmem_st32(trow + c * 32, r);
+      }
+      const float mean = sum * (1.0f / BN);
+      float sq = 0.0f;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        tmem_ld32(trow + c * 32, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float dlt = __uint_as_float(r[i]) - mean;
+          sq += dlt * dlt;
+        }
+      }
+      const float rstd = rsqrtf(sq * (1.0f / BN) + 1e-5f);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        tmem_ld32(trow + c * 32, r);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          v[i] = (__uint_as_float(r[i]) - mean) * rstd * s_gamma[c * 32 + i] + s_beta[c * 32 + i];
+        if (row_ok) {
+          const int64_t o = (int64_t)m * p.ld_out + c * 32;
+          store_split_chunk(v, p.out_hi + o, p.out_lo + o);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+  }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                        CUtensorMapFloatOOBfill);
+
+struct TcCtx {
+  int device = 0;
+  PFN_tmapEncodeTiled encode = nullptr;
+  bool ok = true;
+};
+
+TcCtx* tc_create(int device) {
+  TcCtx* c = new TcCtx();
+  c->device = device;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    mldb_set_err("cuTensorMapEncodeTiled is not available from the driver");
+    delete c;
+    return nullptr;
+  }
+  c->encode = (PFN_tmapEncodeTiled)fn;
+  e = cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::SMEM_BYTES);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::SMEM_BYTES);
+  if (e != cudaSuccess) {
+    mldb_set_err(std::string("cudaFuncSetAttribute(k_gemm_tc): ") + cudaGetErrorString(e));
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
 void tc_destroy(TcCtx* c) { delete c; }
-bool tc_gemm_supported(const TcCtx*, const GemmArgs&) { return false; }
-bool tc_gemm_ln_supported(const TcCtx*, const GemmArgs&, const LnArgs&) { return false; }
-void tc_gemm(TcCtx*, const GemmArgs&, const LnArgs*, cudaStream_t) {}
+
+// 2-D map over one fp16 plane [rows, cols] (cols contiguous), box = 64 cols x box_rows, 128B swizzle.
+// Out-of-bounds rows/cols are zero-filled, so M and N need not be tile multiples.
+static bool make_map(const TcCtx* c, CUtensorMap* m, const __half* base, int rows, int cols, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+static int pick_bn(const GemmArgs& g) { return (g.w.N % 256 == 0) ? 256 : 128; }
+
+bool tc_gemm_supported(const TcCtx* c, const GemmArgs& g) {
+  if (!c || !c->ok) return false;
+  if (g.a_kind != A_SPLIT || g.M < 32) return false;
+  if (g.K1 <= 0 || g.K1 % BK || g.K2 % BK || g.a1.cols != g.K1) return false;
+  if (g.K2 > 0 && g.a2.cols != g.K2) return false;
+  if (g.w.K != g.K1 + g.K2) return false;
+  if (((uintptr_t)g.a1.hi & 15) || ((uintptr_t)g.w.w & 15)) return false;
+  if (g.out.hi && ((g.out.cols % 8) || (g.out_col0 % 8))) return false;
+  if (!g.out.hi && !g.out_f32) return false;
+  return true;
+}
+
+bool tc_gemm_ln_supported(const TcCtx* c, const GemmArgs& g, const LnArgs& l) {
+  if (!tc_gemm_supported(c, g)) return false;
+  if (g.w.N != 256 || l.d != 256 || g.act != ACT_NONE) return false;
+  if (l.in_group != 0 || l.c != nullptr || l.out_f32 != nullptr || !l.out.hi) return false;
+  if (l.out.cols != 256 || (l.res.hi && l.res.cols != 256)) return false;
+  if (l.gamma2) return false;
+  return true;
+}
+
+void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
+  CUtensorMap mA1h, mA1l, mA2h, mA2l, mWh, mWl;
+  const int bn = ln ? 256 : pick_bn(g);
+  bool ok = make_map(c, &mA1h, g.a1.hi, g.M, g.K1, BM) && make_map(c, &mA1l, g.a1.lo(), g.M, g.K1, BM);
+  if (g.K2 > 0) ok = ok && make_map(c, &mA2h, g.a2.hi, g.M, g.K2, BM) && make_map(c, &mA2l, g.a2.lo(), g.M, g.K2, BM);
+  else { mA2h = mA1h; mA2l = mA1l; }
+  ok = ok && make_map(c, &mWh, g.w.w, g.w.N, g.w.K, bn) && make_map(c, &mWl, g.w.w + g.w.plane_stride, g.w.N, g.w.K, bn);
+  if (!ok) {
+    fprintf(stderr, "libmldb200: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)\n", g.M, g.w.N, g.w.K);
+    c->ok = false;
+    return;
+  }
+  TcParams p{};
+  p.M = g.M; p.N = g.w.N; p.kblocks = g.w.K / BK; p.kb1 = g.K1 / BK;
+  p.inv_scale = g.w.inv_scale; p.bias = g.w.bias; p.addtab = g.addtab; p.act = g.act;
+  p.in_group = g.in_group; p.out_group = g.out_group; p.out_off = g.out_off; p.zero_lengths = g.zero_lengths;
+  if (ln) {
+    p.ln = 1;
+    p.out_hi = ln->out.hi; p.out_lo = ln->out.lo(); p.ld_out = ln->out.cols; p.out_col0 = 0;
+    p.res_hi = ln->res.hi; p.res_lo = ln->res.hi ? ln->res.lo() : nullptr; p.ld_res = ln->res.cols;
+    p.rowvec = ln->rowvec; p.rv_group = ln->rv_group > 0 ? ln->rv_group : 1;
+    p.gamma = ln->gamma; p.beta = ln->beta; p.gamma2 = ln->gamma2; p.beta2 = ln->beta2;
+  } else {
+    p.out_hi = g.out.hi; p.out_lo = g.out.hi ? g.out.lo() : nullptr; p.ld_out = g.out.cols; p.out_col0 = g.out_col0;
+    p.out_f32 = g.out_f32; p.ldc = g.ldc;
+  }
+  dim3 grid((g.M + BM - 1) / BM, (g.w.N + bn - 1) / bn);
+  if (bn == 256)
+    k_gemm_tc<256><<<grid, NUM_THREADS, TileCfg<256>::SMEM_BYTES, st>>>(mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
+  else
+    k_gemm_tc<128><<<grid, NUM_THREADS, TileCfg<128>::SMEM_BYTES, st>>>(mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
+}

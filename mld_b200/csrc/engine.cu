@@ -341,7 +341,8 @@ static void op_gemm_ln(mldb_handle* h, GemmArgs g, LnArgs l, float* cf32, cudaSt
 }
 static void op_ln(mldb_handle* h, const LnArgs& l, cudaStream_t st) { simt_ln(l, st); count_launch(h); }
 static void op_attn(mldb_handle* h, const AttnArgs& a, cudaStream_t st) {
-  simt_attention(a, st);
+  if (h->use_tc && mma_attention_supported(a)) mma_attention(a, st);
+  else simt_attention(a, st);
   count_launch(h);
 }
 
@@ -490,6 +491,8 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   build_alphas(h->cfg, &h->alphas_cumprod);
   cudaError_t e = cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { delete h; FAIL(MLDB_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+  simt_init();
+  mma_attention_init();
   h->tc = tc_create(device);
   if (!h->tc) { delete h; return MLDB_ERR_CUDA; }
   const char* env = getenv("MLDB_GEMM");

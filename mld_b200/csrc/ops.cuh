@@ -66,5 +66,10 @@ struct AttnArgs {
 void simt_gemm(const GemmArgs& a, cudaStream_t st);
 void simt_ln(const LnArgs& a, cudaStream_t st);
 void simt_attention(const AttnArgs& a, cudaStream_t st);
+// --- mma.sync tensor-core attention (attn_mma.cu) ---
+bool mma_attention_supported(const AttnArgs& a);
+void mma_attention_init();
+void mma_attention(const AttnArgs& a, cudaStream_t st);
+void simt_init();
 // --- tcgen05 implementations (gemm_tc.cu) ---
 struct TcCtx;

@@ -261,12 +261,12 @@ size_t simt_attention_smem(const AttnArgs& a) {
   return ((size_t)a.Lk * (2 * a.hd + 1) + (size_t)ATT_WARPS * (a.hd + a.Lk)) * sizeof(float);
 }
 
+void simt_init() {
+  // opt in to the full 227 KB once (not during stream capture)
+  cudaFuncSetAttribute(k_attn_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+}
+
 void simt_attention(const AttnArgs& a, cudaStream_t st) {
-  static size_t configured = 0;
   const size_t smem = simt_attention_smem(a);
-  if (smem > configured) {
-    cudaFuncSetAttribute(k_attn_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
   k_attn_simt<<<a.nseq * a.heads, ATT_WARPS * 32, smem, st>>>(a);
 }

@@ -71,6 +71,6 @@ def test_whole_path_tc_equals_cuda_core_path(built_lib):
     l_tc = eng.launch_count
     eng.set_option("gemm", "simt")
     b = eng.sample(ctx, noise, lengths, want=("latents", "joints"))
-    assert _rel(a["latents"], b["latents"]) < 2e-5
-    assert _rel(a["joints"], b["joints"]) < 2e-5
+    assert _rel(a["latents"], b["latents"]) < 1e-4
+    assert _rel(a["joints"], b["joints"]) < 1e-4
     assert l_tc > 0

@@ -14,7 +14,7 @@
 
 namespace {
 
-constexpr int AW = 4;            // warps per CTA
+constexpr int AW_MAX = 8;        // warps per CTA: one per 16-row query tile, at most 8
 constexpr int KCHUNK = 64;       // keys per online-softmax chunk
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
@@ -37,7 +37,7 @@ __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
 }
 
 template <int HD>
-__global__ void __launch_bounds__(AW * 32) k_attn_mma(const AttnArgs a) {
+__global__ void __launch_bounds__(AW_MAX * 32) k_attn_mma(const AttnArgs a) {
   constexpr int PITCH = HD + 8;              // halves per smem row (144 B / 272 B: conflict-free ldmatrix)
   constexpr int NT_D = HD / 8;               // n8 tiles across the head dimension
   constexpr int KS = HD / 16;                // k16 steps across the head dimension
@@ -54,10 +54,11 @@ __global__ void __launch_bounds__(AW * 32) k_attn_mma(const AttnArgs a) {
   __half* Vh = Kl + (size_t)LkP * PITCH;
   __half* Vl = Vh + (size_t)LkP * PITCH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nthreads = blockDim.x, AW = blockDim.x >> 5;
 
   // ---- stage the head slices (16-byte vectors; rows beyond L are zero)
   constexpr int VPR = HD / 8;                // uint4 per row
-  for (int i = tid; i < LqP * VPR; i += AW * 32) {
+  for (int i = tid; i < LqP * VPR; i += nthreads) {
     const int r = i / VPR, c = i - r * VPR;
     uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
     if (r < Lq) {
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(AW * 32) k_attn_mma(const AttnArgs a) {
     *reinterpret_cast<uint4*>(Qh + (size_t)r * PITCH + c * 8) = vh;
     *reinterpret_cast<uint4*>(Ql + (size_t)r * PITCH + c * 8) = vl;
   }
-  for (int i = tid; i < LkP * VPR; i += AW * 32) {
+  for (int i = tid; i < LkP * VPR; i += nthreads) {
     const int r = i / VPR, c = i - r * VPR;
     uint4 kh = make_uint4(0, 0, 0, 0), kl = kh, vh = kh, vl = kh;
     if (r < Lk) {
@@ -248,6 +249,8 @@ void mma_attention_init() {
 }
 
 void mma_attention(const AttnArgs& a, cudaStream_t st) {
-  if (a.hd == 64) k_attn_mma<64><<<a.nseq * a.heads, AW * 32, attn_smem<64>(a), st>>>(a);
-  else k_attn_mma<128><<<a.nseq * a.heads, AW * 32, attn_smem<128>(a), st>>>(a);
+  const int qtiles = (a.Lq + 15) / 16;
+  const int nw = qtiles < AW_MAX ? qtiles : AW_MAX;     // L = 79 -> 5 warps, one tile each
+  if (a.hd == 64) k_attn_mma<64><<<a.nseq * a.heads, nw * 32, attn_smem<64>(a), st>>>(a);
+  else k_attn_mma<128><<<a.nseq * a.heads, nw * 32, attn_smem<128>(a), st>>>(a);
 }

@@ -25,7 +25,6 @@ void mldb_set_err(const std::string& s);
 namespace {
 
 constexpr int BM = 128, BK = 64;
-constexpr int NUM_THREADS = 192;
 
 // ------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,6 +117,7 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
 // ------------------------------------------------------------------------------ parameters
 struct TcParams {
   int M, N, kblocks, kb1;
+  int m_tiles, n_tiles;
   float inv_scale;
   const float* bias;
   const float* addtab;
@@ -134,26 +134,32 @@ struct TcParams {
   const float* gamma2; const float* beta2;
 };
 
+constexpr int EPI_WARPS = 8;                         // two warps per TMEM lane quarter
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;     // producer warp + MMA warp + epilogue warps
+constexpr int MAX_N = 1024;                          // bias staging capacity
+
 template <int BN>
 struct TileCfg {
   static constexpr int STAGES = BN == 256 ? 2 : 3;
   static constexpr int A_BYTES = BM * BK * 2;          // one plane of the A tile (16 KB)
   static constexpr int W_BYTES = BN * BK * 2;          // one plane of the W tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int AUX_BYTES = 4 * BN * 4 + 256;   // bias, gamma, beta (+ spare) + barriers
+  static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator
+  // bias[MAX_N] + gamma[256] + beta[256] + LN partials [2][2][128] + barriers
+  static constexpr int AUX_BYTES = MAX_N * 4 + 2 * 256 * 4 + 4 * 128 * 4 + 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;   // + alignment slack
 };
 
+// fp32 x32 -> split16 hi/lo planes (64 B each) with packed conversions
 __device__ __forceinline__ void store_split_chunk(const float (&v)[32], __half* hi, __half* lo) {
   uint32_t ph[16], pl[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    __half h0, l0, h1, l1;
-    split_f32(v[2 * i], h0, l0);
-    split_f32(v[2 * i + 1], h1, l1);
-    __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
-    ph[i] = *reinterpret_cast<uint32_t*>(&hh);
-    pl[i] = *reinterpret_cast<uint32_t*>(&ll);
+    const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
   }
   uint4* dh = reinterpret_cast<uint4*>(hi);
   uint4* dl = reinterpret_cast<uint4*>(lo);
@@ -182,7 +188,15 @@ __device__ __forceinline__ void load_split_chunk(const __half* hi, const __half*
   }
 }
 
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // ------------------------------------------------------------------------------ the kernel
+// Persistent: CTA c walks tiles c, c + gridDim.x, ...; tile t -> (m = t / n_tiles, n = t % n_tiles).
+// The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
+// the TMA/MMA main loop of tile i + 1.
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
@@ -194,34 +208,41 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
-  float* s_bias = reinterpret_cast<float*>(aux);
-  float* s_gamma = s_bias + BN;
-  float* s_beta = s_gamma + BN;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(aux + 4 * BN * 4);   // full[S], empty[S], tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  float* s_bias = reinterpret_cast<float*>(aux);              // [MAX_N]
+  float* s_gamma = s_bias + MAX_N;                            // [256]
+  float* s_beta = s_gamma + 256;                              // [256]
+  float* s_part = s_beta + 256;                               // [2 passes][2 halves][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 4 * 128);
+  // bars: full[S], empty[S], tmem_full[2], tmem_empty[2]
+  uint64_t* bar_full = bars;
+  uint64_t* bar_empty = bars + STAGES;
+  uint64_t* bar_tfull = bars + 2 * STAGES;
+  uint64_t* bar_tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int ntiles = p.m_tiles * p.n_tiles;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_u32(&bars[s]), 1);
-      mbar_init(smem_u32(&bars[STAGES + s]), 1);
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    mbar_init(smem_u32(&bars[2 * STAGES]), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_tfull[s]), 1);
+      mbar_init(smem_u32(&bar_tempty[s]), EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmA1h); tma_prefetch_desc(&tmA1l); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < BN; i += 128) {
-      const int n = n0 + i;
-      s_bias[i] = (p.bias && n < p.N) ? p.bias[n] : 0.0f;
-      if (p.ln) { s_gamma[i] = p.gamma[n]; s_beta[i] = p.beta[n]; }
-    }
+    for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.0f;
+    if (p.ln)
+      for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) { s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
   }
   tc_fence_before();
   __syncthreads();
@@ -231,153 +252,186 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   if (warp == 0) {
     if (lane == 0) {
       // ---------------------------------------------------------------- TMA producer
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(smem_u32(&bars[STAGES + s]), ph ^ 1u);
-        const uint32_t full = smem_u32(&bars[s]);
-        mbar_expect_tx(full, Cfg::STAGE_BYTES);
-        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-        const uint32_t sAh = smem_u32(st), sAl = sAh + Cfg::A_BYTES, sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
-        if (kb < p.kb1) {
-          tma_load_2d(sAh, &tmA1h, full, kb * BK, m0);
-          tma_load_2d(sAl, &tmA1l, full, kb * BK, m0);
-        } else {
-          tma_load_2d(sAh, &tmA2h, full, (kb - p.kb1) * BK, m0);
-          tma_load_2d(sAl, &tmA2l, full, (kb - p.kb1) * BK, m0);
+      int kbg = 0;                                   // k-block counter across tiles (ring position)
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+        for (int kb = 0; kb < p.kblocks; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
+          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+          const uint32_t full = smem_u32(&bar_full[s]);
+          mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          const uint32_t sAh = smem_u32(smem + s * Cfg::STAGE_BYTES), sAl = sAh + Cfg::A_BYTES;
+          const uint32_t sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
+          if (kb < p.kb1) {
+            tma_load_2d(sAh, &tmA1h, full, kb * BK, m0);
+            tma_load_2d(sAl, &tmA1l, full, kb * BK, m0);
+          } else {
+            tma_load_2d(sAh, &tmA2h, full, (kb - p.kb1) * BK, m0);
+            tma_load_2d(sAl, &tmA2l, full, (kb - p.kb1) * BK, m0);
+          }
+          tma_load_2d(sWh, &tmWh, full, kb * BK, n0);
+          tma_load_2d(sWl, &tmWl, full, kb * BK, n0);
         }
-        tma_load_2d(sWh, &tmWh, full, kb * BK, n0);
-        tma_load_2d(sWl, &tmWl, full, kb * BK, n0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc = make_idesc(BN);
-      for (int kb = 0; kb < p.kblocks; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-        mbar_wait(smem_u32(&bars[s]), ph);
+      int kbg = 0, it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(smem_u32(&bar_tempty[as]), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained it
         tc_fence_after();
-        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-        const uint32_t sAh = smem_u32(st), sAl = sAh + Cfg::A_BYTES, sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
+        const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < p.kblocks; ++kb, ++kbg) {
+          const int s = kbg % STAGES;
+          const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
+          mbar_wait(smem_u32(&bar_full[s]), ph);
+          tc_fence_after();
+          const uint32_t sAh = smem_u32(smem + s * Cfg::STAGE_BYTES), sAl = sAh + Cfg::A_BYTES;
+          const uint32_t sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint32_t off = kk * 32;   // 16 halves = 32 bytes inside the 128B swizzle row
-          const uint64_t ah = make_desc(sAh + off), al = make_desc(sAl + off);
-          const uint64_t wh = make_desc(sWh + off), wl = make_desc(sWl + off);
-          umma(tmem_base, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
-          umma(tmem_base, ah, wl, idesc, 1u);
-          umma(tmem_base, ah, wh, idesc, 1u);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint32_t off = kk * 32;   // 16 halves = 32 bytes inside the 128B swizzle row
+            const uint64_t ah = make_desc(sAh + off), al = make_desc(sAl + off);
+            const uint64_t wh = make_desc(sWh + off), wl = make_desc(sWl + off);
+            umma(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma(tacc, ah, wl, idesc, 1u);
+            umma(tacc, ah, wh, idesc, 1u);
+          }
+          umma_commit(smem_u32(&bar_empty[s]));      // frees the stage when these MMAs retire
         }
-        umma_commit(smem_u32(&bars[STAGES + s]));   // frees the stage when these MMAs retire
+        umma_commit(smem_u32(&bar_tfull[as]));       // accumulator complete
       }
-      umma_commit(smem_u32(&bars[2 * STAGES]));     // accumulator complete
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int hf = (warp - 2) >> 2;                  // which half of the tile's columns
     const int row = q * 32 + lane;
-    const int m = m0 + row;
-    const bool row_ok = m < p.M;
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    mbar_wait(smem_u32(&bars[2 * STAGES]), 0);
-    tc_fence_after();
+    constexpr int CH = BN / 64;                      // 32-column chunks per warp
     uint32_t r[32];
     float v[32];
-    if (!p.ln) {
-      int seq = 0, pos = m;
-      if (row_ok && p.in_group < p.M) { seq = m / p.in_group; pos = m - seq * p.in_group; }
-      const int64_t orow = (int64_t)seq * p.out_group + p.out_off + pos;
-      const bool zero = row_ok && p.zero_lengths != nullptr && pos >= p.zero_lengths[seq];
-      const float* tab = p.addtab ? p.addtab + (int64_t)(p.out_off + pos) * p.N : nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+      const int m = m0 + row;
+      const bool row_ok = m < p.M;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + hf * (BN / 2));
+      mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      if (!p.ln) {
+        int seq = 0, pos = m;
+        if (row_ok && p.in_group < p.M) { seq = m / p.in_group; pos = m - seq * p.in_group; }
+        const int64_t orow = (int64_t)seq * p.out_group + p.out_off + pos;
+        const bool zero = row_ok && p.zero_lengths != nullptr && pos >= p.zero_lengths[seq];
+        const float* tab = p.addtab ? p.addtab + (int64_t)(p.out_off + pos) * p.N : nullptr;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        tmem_ld32(trow + c * 32, r);            // warp-collective: no divergence around it
-        const int nb = n0 + c * 32;
-        if (row_ok && nb < p.N) {
+        for (int c = 0; c < CH; ++c) {
+          tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
+          const int nb = n0 + hf * (BN / 2) + c * 32;
+          if (row_ok && nb < p.N) {
+            const bool full = nb + 32 <= p.N;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(r[i]) * p.inv_scale + s_bias[c * 32 + i];
-          if (tab && nb + i < p.N) x += tab[nb + i];
-          x = apply_act(x, p.act);
-          v[i] = zero ? 0.0f : x;
-        }
-        if (p.out_hi) {
-          if (nb + 32 <= p.N) {
-            const int64_t o = orow * p.ld_out + p.out_col0 + nb;
-            store_split_chunk(v, p.out_hi + o, p.out_lo + o);
-          } else {
-            for (int i = 0; i < 32 && nb + i < p.N; ++i) {
-              __half h, l;
-              split_f32(v[i], h, l);
-              const int64_t o = orow * p.ld_out + p.out_col0 + nb + i;
-              p.out_hi[o] = h; p.out_lo[o] = l;
+            for (int i = 0; i < 32; ++i) {
+              float x = __uint_as_float(r[i]) * p.inv_scale + s_bias[min(nb + i, MAX_N - 1)];
+              if (tab && (full || nb + i < p.N)) x += tab[nb + i];
+              x = apply_act(x, p.act);
+              v[i] = zero ? 0.0f : x;
+            }
+            if (p.out_hi) {
+              const int64_t o = orow * p.ld_out + p.out_col0 + nb;
+              if (full) {
+                store_split_chunk(v, p.out_hi + o, p.out_lo + o);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  if (nb + i < p.N) {
+                    __half h, l;
+                    split_f32(v[i], h, l);
+                    p.out_hi[o + i] = h; p.out_lo[o + i] = l;
+                  }
+                }
+              }
+            }
+            if (p.out_f32) {
+              float* dst = p.out_f32 + orow * p.ldc + nb;
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (full || nb + i < p.N) dst[i] = v[i];
             }
           }
+          __syncwarp();
         }
-        if (p.out_f32) {
-          float* dst = p.out_f32 + orow * p.ldc + nb;
+      } else {
+        // x = acc*s + bias + residual (+ rowvec); y = LayerNorm(x) over the 256-wide row (two-pass
+        // statistics, eps 1e-5).  Two warps share a row (column halves) and exchange partial sums
+        // through shared memory; the pre-norm row is parked in TMEM between the passes.
+        const float* rv = (row_ok && p.rowvec) ? p.rowvec + (int64_t)(m / p.rv_group) * BN : nullptr;
+        const int cb = hf * (BN / 2);
+        float sum = 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < CH; ++c) {
+          tmem_ld32(trow + c * 32, r);
+          if (row_ok && p.res_hi) {
+            const int64_t o = (int64_t)m * p.ld_res + cb + c * 32;
+            load_split_chunk(p.res_hi + o, p.res_lo + o, v);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(r[i]) * p.inv_scale + s_bias[cb + c * 32 + i] + v[i];
+            if (rv) x += rv[cb + c * 32 + i];
+            sum += x;
+            r[i] = __float_as_uint(x);
+          }
+          tmem_st32(trow + c * 32, r);
+        }
+        s_part[hf * 128 + row] = sum;
+        epi_bar_sync();
+        const float mean = (s_part[row] + s_part[128 + row]) * (1.0f / BN);
+        float sq = 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < CH; ++c) {
+          tmem_ld32(trow + c * 32, r);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float dlt = __uint_as_float(r[i]) - mean;
+            sq += dlt * dlt;
+          }
+        }
+        s_part[256 + hf * 128 + row] = sq;
+        epi_bar_sync();
+        const float rstd = rsqrtf((s_part[256 + row] + s_part[256 + 128 + row]) * (1.0f / BN) + 1e-5f);
+#pragma unroll 1
+        for (int c = 0; c < CH; ++c) {
+          tmem_ld32(trow + c * 32, r);
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (nb + i < p.N) dst[i] = v[i];
-        }
-        }
-        __syncwarp();
-      }
-    } else {
-      // x = acc*s + bias + residual (+ rowvec); y = LayerNorm(x) (two-pass statistics, eps 1e-5).
-      const float* rv = (row_ok && p.rowvec) ? p.rowvec + (int64_t)(m / p.rv_group) * BN : nullptr;
-      float sum = 0.0f;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        tmem_ld32(trow + c * 32, r);
-        if (row_ok && p.res_hi) {
-          const int64_t o = (int64_t)m * p.ld_res + c * 32;
-          load_split_chunk(p.res_hi + o, p.res_lo + o, v);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.0f;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float x = __uint_as_float(r[i]) * p.inv_scale + s_bias[c * 32 + i] + v[i];
-          if (rv) x += rv[c * 32 + i];
-          sum += x;
-          r[i] = __float_as_uint(x);
-        }
-        tmem_st32(trow + c * 32, r);
-      }
-      const float mean = sum * (1.0f / BN);
-      float sq = 0.0f;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        tmem_ld32(trow + c * 32, r);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float dlt = __uint_as_float(r[i]) - mean;
-          sq += dlt * dlt;
+            v[i] = (__uint_as_float(r[i]) - mean) * rstd * s_gamma[cb + c * 32 + i] + s_beta[cb + c * 32 + i];
+          if (row_ok) {
+            const int64_t o = (int64_t)m * p.ld_out + cb + c * 32;
+            store_split_chunk(v, p.out_hi + o, p.out_lo + o);
+          }
+          __syncwarp();
         }
       }
-      const float rstd = rsqrtf(sq * (1.0f / BN) + 1e-5f);
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        tmem_ld32(trow + c * 32, r);
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          v[i] = (__uint_as_float(r[i]) - mean) * rstd * s_gamma[c * 32 + i] + s_beta[c * 32 + i];
-        if (row_ok) {
-          const int64_t o = (int64_t)m * p.ld_out + c * 32;
-          store_split_chunk(v, p.out_hi + o, p.out_lo + o);
-        }
-      }
+      // this warp is done reading the accumulator stage: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -391,6 +445,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 
 struct TcCtx {
   int device = 0;
+  int sm_count = 148;
   PFN_tmapEncodeTiled encode = nullptr;
   bool ok = true;
 };
@@ -407,6 +462,7 @@ TcCtx* tc_create(int device) {
     return nullptr;
   }
   c->encode = (PFN_tmapEncodeTiled)fn;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   e = cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::SMEM_BYTES);
   if (e == cudaSuccess)
     e = cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::SMEM_BYTES);
@@ -436,13 +492,12 @@ static int pick_bn(const GemmArgs& g) { return (g.w.N % 256 == 0) ? 256 : 128; }
 
 bool tc_gemm_supported(const TcCtx* c, const GemmArgs& g) {
   if (!c || !c->ok) return false;
-  if (g.a_kind != A_SPLIT || g.M < 32) return false;
+  if (g.a_kind != A_SPLIT || g.M < 1 || g.w.N > MAX_N) return false;
   if (g.K1 <= 0 || g.K1 % BK || g.K2 % BK || g.a1.cols != g.K1) return false;
   if (g.K2 > 0 && g.a2.cols != g.K2) return false;
   if (g.w.K != g.K1 + g.K2) return false;
   if (((uintptr_t)g.a1.hi & 15) || ((uintptr_t)g.w.w & 15)) return false;
   if (g.out.hi && ((g.out.cols % 8) || (g.out_col0 % 8))) return false;
-  if (!g.out.hi && !g.out_f32) return false;
   return true;
 }
 
@@ -481,7 +536,10 @@ void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
     p.out_hi = g.out.hi; p.out_lo = g.out.hi ? g.out.lo() : nullptr; p.ld_out = g.out.cols; p.out_col0 = g.out_col0;
     p.out_f32 = g.out_f32; p.ldc = g.ldc;
   }
-  dim3 grid((g.M + BM - 1) / BM, (g.w.N + bn - 1) / bn);
+  p.m_tiles = (g.M + BM - 1) / BM;
+  p.n_tiles = (g.w.N + bn - 1) / bn;
+  const int ntiles = p.m_tiles * p.n_tiles;
+  dim3 grid(ntiles < c->sm_count ? ntiles : c->sm_count);
   if (bn == 256)
     k_gemm_tc<256><<<grid, NUM_THREADS, TileCfg<256>::SMEM_BYTES, st>>>(mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
   else

@@ -837,6 +837,83 @@ static void denoiser_pass(mldb_handle* h, Plan* p, const float* latents, int lat
   op_ln(h, l, st);
 }
 
+// ----------------------------------------------------------------------------- denoiser (trans_dec)
+// The no-VAE model (configs/modules_novae/denoiser.yaml): frames are the decoder targets, the
+// memory is [time, text...] (mld_denoiser.py:208-221).  No key-padding mask is passed on either
+// attention (padded frames attend and are attended, like the reference); padded output frames are
+// zeroed after pose_proj (:219-221).
+static int decden_plan(mldb_handle* h, int kind, int B, int Bx, int S, int T, Plan** out) {
+  Plan* p = find_plan(h, kind, B, S, T);
+  if (!p) {
+    const mldb_config& c = h->cfg;
+    if (T > 500 || 1 + S > 500) FAIL(MLDB_ERR_INVALID, "sequence exceeds the learned PE table (500)");
+    p = add_plan(h, kind, B, S, T);
+    p->Bx = Bx;
+    p->Ntok = T;
+    const int Lmem = 1 + (c.cond_kind == MLDB_COND_TEXT ? S : 1);
+    TRY(alloc_stack_ws(h, h->den, Bx, T, Lmem, &p->ws));
+    TRY(alloc_act(h, Bx * Lmem, c.latent_dim, &p->mem));
+    const size_t per = (size_t)T * c.nfeats;
+    TRY(dev_alloc(h, (void**)&p->latents, (size_t)B * per * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&p->eps, (size_t)Bx * per * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&p->stage_f32, (size_t)Bx * per * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&p->lengths, (size_t)Bx * sizeof(int32_t)));
+    TRY(dev_alloc(h, (void**)&p->tt_single, (size_t)3 * std::max(c.text_dim, c.latent_dim) * sizeof(float) + 64));
+  }
+  *out = p;
+  return MLDB_OK;
+}
+
+static int place_condition_dec(mldb_handle* h, Plan* p, const void* cond, cudaStream_t st) {
+  const mldb_config& c = h->cfg;
+  const int d = c.latent_dim, Bx = p->Bx, Lmem = p->ws.Lmem;
+  if (c.cond_kind == MLDB_COND_TEXT) {
+    const int S = p->S;
+    if (c.text_dim != d) {
+      GemmArgs g; g.a_kind = A_F32_RELU; g.a_f32 = (const float*)cond; g.lda = c.text_dim;
+      g.M = Bx * S; g.w = h->emb_proj; g.out = p->mem;
+      g.in_group = S; g.out_group = Lmem; g.out_off = 1; g.addtab = h->mem_pe;
+      op_gemm(h, g, st);
+    } else {
+      k_rows_to_split<<<nblk((int64_t)Bx * S * d), 256, 0, st>>>(p->mem, (const float*)cond, d, Bx * S, d, S, Lmem, 1, 0, h->mem_pe);
+      count_launch(h);
+    }
+  } else {
+    const int cfg_on = c.guidance_scale > 1.0f;
+    k_action_tokens<<<nblk((int64_t)Bx * d), 256, 0, st>>>(p->mem, Lmem, Bx, 1, d, (const int64_t*)cond, h->action_emb,
+                                                          c.nclasses, cfg_on, h->mem_pe + (size_t)d);
+    count_launch(h);
+  }
+  CK(cudaGetLastError());
+  return MLDB_OK;
+}
+
+// model_in: [Bx, T, F] fp32 (device); lengths: device int32[Bx]; eps_out [Bx, T, F]
+static void denoiser_pass_dec(mldb_handle* h, Plan* p, const float* model_in, const float* tt, float* eps_out,
+                              cudaStream_t st) {
+  const mldb_config& c = h->cfg;
+  const int d = c.latent_dim, Bx = p->Bx, T = p->T, F = c.nfeats, Lmem = p->ws.Lmem;
+  // memory row 0 = time token (mem_pos.pe[0] already added)
+  k_rows_to_split<<<nblk((int64_t)Bx * d), 256, 0, st>>>(p->mem, tt, d, Bx, d, 1, Lmem, 0, 1, nullptr);
+  count_launch(h);
+  // pose_embd + query_pos (mld_denoiser.py:210,214)
+  GemmArgs g; g.a_kind = A_F32; g.a_f32 = model_in; g.lda = F; g.M = Bx * T; g.w = h->pose_embd;
+  g.out = p->ws.x0; g.in_group = T; g.out_group = T; g.out_off = 0; g.addtab = h->query_pe;
+  op_gemm(h, g, st);
+  SeqInfo si;
+  ActBuf x = run_stack(h, h->den, p->ws.x0, p->mem, p->ws, si, st);
+  LnArgs l; l.res = x; l.gamma = h->den.norm.g; l.beta = h->den.norm.b; l.M = Bx * T; l.d = d; l.out = p->ws.x1;
+  op_ln(h, l, st);
+  GemmArgs go; go.a1 = p->ws.x1; go.K1 = d; go.M = Bx * T; go.w = h->pose_proj; go.out_f32 = eps_out; go.ldc = F;
+  go.in_group = T; go.out_group = T; go.out_off = 0; go.zero_lengths = p->lengths;
+  op_gemm(h, go, st);
+}
+
+__global__ void k_dup_lengths(const int32_t* __restrict__ src, int32_t* __restrict__ dst, int B, int Bx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Bx) dst[i] = src[i % B];
+}
+
 static int check_ready(mldb_handle* h, bool need_sched) {
   if (!h) FAIL(MLDB_ERR_INVALID, "null handle");
   if (!h->finalized) FAIL(MLDB_ERR_STATE, "weights not finalized");
@@ -853,10 +930,25 @@ extern "C" int mldb_denoise(mldb_handle* h, const float* sample, int64_t timeste
   if (!sample || !cond || !out || Bx <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
   const mldb_config& c = h->cfg;
   if (c.num_layers == 0) FAIL(MLDB_ERR_STATE, "this handle has no denoiser");
-  if (c.arch != MLDB_ARCH_TRANS_ENC) FAIL(MLDB_ERR_UNSUPPORTED, "mldb_denoise: arch trans_dec is not built yet");
   if (c.cond_kind == MLDB_COND_TEXT && S_ctx <= 0) FAIL(MLDB_ERR_INVALID, "S_ctx must be positive");
   cudaStream_t st = (cudaStream_t)stream;
   Plan* p = nullptr;
+  if (c.arch == MLDB_ARCH_TRANS_DEC) {
+    if (!c.diffusion_only) FAIL(MLDB_ERR_UNSUPPORTED, "arch trans_dec is built for the no-VAE model (diffusion_only)");
+    if (!lengths || T <= 0) FAIL(MLDB_ERR_INVALID, "the no-VAE denoiser needs lengths and T");
+    TRY(decden_plan(h, 4, Bx, Bx, S_ctx, T, &p));
+    TRY(place_condition_dec(h, p, cond, st));
+    CK(cudaMemcpyAsync(p->lengths, lengths, (size_t)Bx * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    const int d = c.latent_dim;
+    const int tdim = c.cond_kind == MLDB_COND_TEXT ? c.text_dim : d;
+    float* feats = p->tt_single + 16;
+    float* hid = feats + tdim;
+    float* tt = hid + std::max(tdim, d);
+    TRY(time_tokens(h, nullptr, timestep, 1, h->mem_pe, tt, feats, hid, st));
+    denoiser_pass_dec(h, p, sample, tt, out, st);
+    CK(cudaGetLastError());
+    return MLDB_OK;
+  }
   TRY(enc_plan(h, 3, Bx, Bx, S_ctx, &p));
   TRY(place_condition(h, p, cond, st));
   // time token for this timestep
@@ -871,14 +963,46 @@ extern "C" int mldb_denoise(mldb_handle* h, const float* sample, int64_t timeste
   return MLDB_OK;
 }
 
-static int run_reverse(mldb_handle* h, const void* cond, const float* init_noise, const int32_t* lengths,
-                       int B, int S, int T, float* latents_out, cudaStream_t st, Plan** plan_out) {
-  (void)lengths; (void)T;
+static int run_reverse(mldb_handle* h, const void* cond, const float* init_noise, const float* step_noise,
+                       const int32_t* lengths, int B, int S, int T, float* latents_out, cudaStream_t st,
+                       Plan** plan_out) {
   const mldb_config& c = h->cfg;
   if (c.num_layers == 0) FAIL(MLDB_ERR_STATE, "this handle has no denoiser");
-  if (c.arch != MLDB_ARCH_TRANS_ENC) FAIL(MLDB_ERR_UNSUPPORTED, "reverse diffusion for arch trans_dec is not built yet");
   const bool cfg_on = c.guidance_scale > 1.0f;
   const int Bx = cfg_on ? 2 * B : B;
+  if (c.arch == MLDB_ARCH_TRANS_DEC) {
+    // no-VAE model: latents are the motion itself, [B, T, F]; DDPM draws noise every step, which
+    // the caller injects (step_noise [n_steps, B, T, F]).  Eager loop: 1000 big steps, no graph.
+    if (!c.diffusion_only) FAIL(MLDB_ERR_UNSUPPORTED, "arch trans_dec is built for the no-VAE model (diffusion_only)");
+    if (!lengths || T <= 0) FAIL(MLDB_ERR_INVALID, "the no-VAE model needs lengths and T");
+    Plan* p = nullptr;
+    TRY(decden_plan(h, 5, B, Bx, S, T, &p));
+    const int64_t per = (int64_t)T * c.nfeats;
+    TRY(place_condition_dec(h, p, cond, st));
+    k_dup_lengths<<<nblk(Bx), 256, 0, st>>>(lengths, p->lengths, B, Bx);
+    count_launch(h);
+    CK(cudaMemcpyAsync(p->latents, init_noise, (size_t)B * per * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const int nsteps = (int)h->timesteps.size();
+    for (int i = 0; i < nsteps; ++i) {
+      for (int rep = 0; rep < (cfg_on ? 2 : 1); ++rep)        // torch.cat([latents] * 2), mld.py:325
+        CK(cudaMemcpyAsync(p->stage_f32 + (size_t)rep * B * per, p->latents, (size_t)B * per * sizeof(float),
+                           cudaMemcpyDeviceToDevice, st));
+      denoiser_pass_dec(h, p, p->stage_f32, h->d_tt + (size_t)i * c.latent_dim, p->eps, st);
+      const float* nz = step_noise ? step_noise + (size_t)i * B * per : nullptr;
+      if (!nz && h->coefs_host[i].kind == 1 && h->coefs_host[i].sigma != 0.0f)
+        FAIL(MLDB_ERR_INVALID, "DDPM needs step_noise [n_steps, B, T, F]");
+      k_cfg_sched<<<nblk(B * per), 256, 0, st>>>(p->eps, p->latents, nz, B * per, cfg_on ? 1 : 0, c.guidance_scale,
+                                               h->d_coefs, i);
+      count_launch(h);
+    }
+    if (latents_out) {                                        // [T, B, F] (mld.py:359)
+      k_permute_01<<<nblk(B * per), 256, 0, st>>>(p->latents, latents_out, B, T, c.nfeats);
+      count_launch(h);
+    }
+    CK(cudaGetLastError());
+    if (plan_out) *plan_out = p;
+    return MLDB_OK;
+  }
   Plan* p = nullptr;
   TRY(enc_plan(h, 0, B, Bx, S, &p));
   const int d = c.latent_dim;
@@ -909,8 +1033,9 @@ extern "C" int mldb_diffusion_reverse(mldb_handle* h, const void* cond, const fl
                                       int32_t S_ctx, int32_t T, float* latents_out, void* stream) {
   TRY(check_ready(h, true));
   if (!cond || !init_noise || !latents_out || B <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
-  if (step_noise) FAIL(MLDB_ERR_UNSUPPORTED, "per-step noise injection (DDPM) is not built yet");
-  return run_reverse(h, cond, init_noise, lengths, B, S_ctx, T, latents_out, (cudaStream_t)stream, nullptr);
+  if (step_noise && h->cfg.arch != MLDB_ARCH_TRANS_DEC)
+    FAIL(MLDB_ERR_UNSUPPORTED, "per-step noise is only used by the no-VAE DDPM model");
+  return run_reverse(h, cond, init_noise, step_noise, lengths, B, S_ctx, T, latents_out, (cudaStream_t)stream, nullptr);
 }
 
 // ----------------------------------------------------------------------------- VAE decode
@@ -1069,7 +1194,8 @@ extern "C" int mldb_sample(mldb_handle* h, const void* cond, const float* init_n
     if (!dp->stage_f32) TRY(dev_alloc(h, (void**)&dp->stage_f32, (size_t)B * c.n_lat * c.latent_dim * sizeof(float)));
     z = dp->stage_f32;
   }
-  TRY(run_reverse(h, cond, init_noise, lengths, B, S_ctx, T, z, st, &rp));
+  if (c.arch != MLDB_ARCH_TRANS_ENC) FAIL(MLDB_ERR_UNSUPPORTED, "mldb_sample is built for the latent (VAE) models");
+  TRY(run_reverse(h, cond, init_noise, nullptr, lengths, B, S_ctx, T, z, st, &rp));
   TRY(run_decode(h, z, lengths, B, T, feats_out, st, &dp));
   if (joints_out) TRY(run_f2j(h, feats_out ? feats_out : dp->feats, B, T, joints_out, st));
   return MLDB_OK;

@@ -229,3 +229,47 @@ def test_dropin_modules_and_pipeline(engines):
         u, c = eps.chunk(2)
         lat = sched.step(u + 7.5 * (c - u), t, lat, eta=0.0).prev_sample
     assert _rel(lat.cpu(), torch.from_numpy(g["latents"][2])) < 1e-3
+
+
+# ------------------------------------------------------------------ no-VAE model (BASELINE configs[4] shape)
+@pytest.fixture(scope="module")
+def novae(built_lib):
+    from mld_b200.engine import Engine, make_config
+    nsd = synth.denoiser_state_dict(seed=3456, arch="trans_dec", d=512, diffusion_only=True)
+    eng = Engine(make_config(arch="trans_dec", latent_dim=(1, 512), diffusion_only=True, vae="none",
+                             scheduler="ddpm"), 0)
+    eng.load_state_dict(nsd, "denoiser.")
+    eng.finalize()
+    return eng, nsd
+
+
+def test_novae_denoiser_vs_reference_golden(novae):
+    eng, _ = novae
+    g = golden("denoiser_novae.npz")
+    gen = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 24, 263, generator=gen).repeat(2, 1, 1)
+    ctx = synth.text_context(2, 1, seed=32)
+    y = eng.denoise(x, 999, ctx, [24, 16] * 2)
+    assert y.shape == (4, 24, 263)
+    assert _rel(y, g["y"]) < 2e-4
+    assert float(y[1, 16:].abs().max()) == 0.0 and float(y[3, 16:].abs().max()) == 0.0
+
+
+def test_novae_ddpm_loop_vs_oracle(novae):
+    """Raw-motion diffusion with per-step injected noise (DDPM, fixed_small variance, CFG 7.5)."""
+    eng, nsd = novae
+    B, T, steps = 2, 24, 8
+    lengths = [24, 16]
+    ts = eng.set_timesteps(steps)
+    ref = O.DDPMScheduler()
+    ref.set_timesteps(steps)
+    assert torch.equal(ts, ref.timesteps)
+    gen = torch.Generator().manual_seed(41)
+    x0 = torch.randn(B, T, 263, generator=gen)
+    nz = torch.randn(steps, B, T, 263, generator=gen)
+    ctx = synth.text_context(B, 1, seed=42)
+    z = eng.diffusion_reverse(ctx, x0, lengths, step_noise=nz)
+    cfg = O.DenoiserCfg(arch="trans_dec", latent_dim=512, diffusion_only=True)
+    zo = O.diffusion_reverse(nsd, cfg, O.DDPMScheduler(), steps, ctx, x0, lengths, step_noise=nz)
+    assert z.shape == (T, B, 263)
+    assert _rel(z, zo) < 1e-3

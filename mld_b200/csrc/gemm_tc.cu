@@ -193,6 +193,22 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// x[i] = act(acc[i] * s + bias[i]) for one 32-column chunk; bias read as float4 broadcasts.
+template <int ACT>
+__device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&v)[32], const float* sb, float s) {
+  const float4* b4 = reinterpret_cast<const float4*>(sb);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = b4[i];
+    float x0 = fmaf(__uint_as_float(r[4 * i + 0]), s, b.x), x1 = fmaf(__uint_as_float(r[4 * i + 1]), s, b.y);
+    float x2 = fmaf(__uint_as_float(r[4 * i + 2]), s, b.z), x3 = fmaf(__uint_as_float(r[4 * i + 3]), s, b.w);
+    if (ACT == ACT_GELU) { x0 = gelu_erf(x0); x1 = gelu_erf(x1); x2 = gelu_erf(x2); x3 = gelu_erf(x3); }
+    if (ACT == ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+    if (ACT == ACT_SILU) { x0 = silu_f(x0); x1 = silu_f(x1); x2 = silu_f(x2); x3 = silu_f(x3); }
+    v[4 * i + 0] = x0; v[4 * i + 1] = x1; v[4 * i + 2] = x2; v[4 * i + 3] = x3;
+  }
+}
+
 // ------------------------------------------------------------------------------ the kernel
 // Persistent: CTA c walks tiles c, c + gridDim.x, ...; tile t -> (m = t / n_tiles, n = t % n_tiles).
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
@@ -329,39 +345,55 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         const int64_t orow = (int64_t)seq * p.out_group + p.out_off + pos;
         const bool zero = row_ok && p.zero_lengths != nullptr && pos >= p.zero_lengths[seq];
         const float* tab = p.addtab ? p.addtab + (int64_t)(p.out_off + pos) * p.N : nullptr;
+        const bool fast = tab == nullptr && !zero && p.out_hi != nullptr && p.out_f32 == nullptr;
+        const float inv_scale = p.inv_scale;
+        const int act = p.act, N = p.N;
+        __half* const ohi = p.out_hi;
+        __half* const olo = p.out_lo;
+        const int64_t obase = orow * p.ld_out + p.out_col0;
 #pragma unroll 1
         for (int c = 0; c < CH; ++c) {
           tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
           const int nb = n0 + hf * (BN / 2) + c * 32;
-          if (row_ok && nb < p.N) {
-            const bool full = nb + 32 <= p.N;
+          if (row_ok && nb < N) {
+            const bool full = nb + 32 <= N;
+            if (fast && full) {
+              switch (act) {                          // warp-uniform, once per chunk
+                case ACT_NONE: epi_chunk_fast<ACT_NONE>(r, v, s_bias + nb, inv_scale); break;
+                case ACT_GELU: epi_chunk_fast<ACT_GELU>(r, v, s_bias + nb, inv_scale); break;
+                case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, s_bias + nb, inv_scale); break;
+                default:       epi_chunk_fast<ACT_SILU>(r, v, s_bias + nb, inv_scale); break;
+              }
+              store_split_chunk(v, ohi + obase + nb, olo + obase + nb);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = __uint_as_float(r[i]) * p.inv_scale + s_bias[min(nb + i, MAX_N - 1)];
-              if (tab && (full || nb + i < p.N)) x += tab[nb + i];
-              x = apply_act(x, p.act);
-              v[i] = zero ? 0.0f : x;
-            }
-            if (p.out_hi) {
-              const int64_t o = orow * p.ld_out + p.out_col0 + nb;
-              if (full) {
-                store_split_chunk(v, p.out_hi + o, p.out_lo + o);
-              } else {
+              for (int i = 0; i < 32; ++i) {
+                float x = __uint_as_float(r[i]) * inv_scale + s_bias[min(nb + i, MAX_N - 1)];
+                if (tab && (full || nb + i < N)) x += tab[nb + i];
+                x = apply_act(x, act);
+                v[i] = zero ? 0.0f : x;
+              }
+              if (ohi) {
+                const int64_t o = obase + nb;
+                if (full) {
+                  store_split_chunk(v, ohi + o, olo + o);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  if (nb + i < p.N) {
-                    __half h, l;
-                    split_f32(v[i], h, l);
-                    p.out_hi[o + i] = h; p.out_lo[o + i] = l;
+                  for (int i = 0; i < 32; ++i) {
+                    if (nb + i < N) {
+                      __half h, l;
+                      split_f32(v[i], h, l);
+                      ohi[o + i] = h; olo[o + i] = l;
+                    }
                   }
                 }
               }
-            }
-            if (p.out_f32) {
-              float* dst = p.out_f32 + orow * p.ldc + nb;
+              if (p.out_f32) {
+                float* dst = p.out_f32 + orow * p.ldc + nb;
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (full || nb + i < p.N) dst[i] = v[i];
+                for (int i = 0; i < 32; ++i)
+                  if (full || nb + i < N) dst[i] = v[i];
+              }
             }
           }
           __syncwarp();
@@ -383,12 +415,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = 0.0f;
           }
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias + cb + c * 32);
+            const float sc = p.inv_scale;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(r[i]) * p.inv_scale + s_bias[cb + c * 32 + i] + v[i];
-            if (rv) x += rv[cb + c * 32 + i];
-            sum += x;
-            r[i] = __float_as_uint(x);
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = b4[i];
+              float x0 = fmaf(__uint_as_float(r[4 * i + 0]), sc, b.x) + v[4 * i + 0];
+              float x1 = fmaf(__uint_as_float(r[4 * i + 1]), sc, b.y) + v[4 * i + 1];
+              float x2 = fmaf(__uint_as_float(r[4 * i + 2]), sc, b.z) + v[4 * i + 2];
+              float x3 = fmaf(__uint_as_float(r[4 * i + 3]), sc, b.w) + v[4 * i + 3];
+              if (rv) {
+                const float4 q4 = *reinterpret_cast<const float4*>(rv + cb + c * 32 + 4 * i);
+                x0 += q4.x; x1 += q4.y; x2 += q4.z; x3 += q4.w;
+              }
+              sum += (x0 + x1) + (x2 + x3);
+              r[4 * i + 0] = __float_as_uint(x0); r[4 * i + 1] = __float_as_uint(x1);
+              r[4 * i + 2] = __float_as_uint(x2); r[4 * i + 3] = __float_as_uint(x3);
+            }
           }
           tmem_st32(trow + c * 32, r);
         }
@@ -411,9 +455,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
 #pragma unroll 1
         for (int c = 0; c < CH; ++c) {
           tmem_ld32(trow + c * 32, r);
+          {
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + cb + c * 32);
+            const float4* e4 = reinterpret_cast<const float4*>(s_beta + cb + c * 32);
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            v[i] = (__uint_as_float(r[i]) - mean) * rstd * s_gamma[cb + c * 32 + i] + s_beta[cb + c * 32 + i];
+            for (int i = 0; i < 8; ++i) {
+              const float4 gg = g4[i], bb = e4[i];
+              v[4 * i + 0] = fmaf((__uint_as_float(r[4 * i + 0]) - mean) * rstd, gg.x, bb.x);
+              v[4 * i + 1] = fmaf((__uint_as_float(r[4 * i + 1]) - mean) * rstd, gg.y, bb.y);
+              v[4 * i + 2] = fmaf((__uint_as_float(r[4 * i + 2]) - mean) * rstd, gg.z, bb.z);
+              v[4 * i + 3] = fmaf((__uint_as_float(r[4 * i + 3]) - mean) * rstd, gg.w, bb.w);
+            }
+          }
           if (row_ok) {
             const int64_t o = (int64_t)m * p.ld_out + cb + c * 32;
             store_split_chunk(v, p.out_hi + o, p.out_lo + o);

@@ -17,6 +17,7 @@
 
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -132,6 +133,7 @@ struct TcParams {
   const float* rowvec; int rv_group;
   const float* gamma; const float* beta;
   const float* gamma2; const float* beta2;
+  int dbg;   // timing experiments only (MLDB_TC_DBG): 1 = no global stores, 2 = no epilogue math/loads, 4 = no MMA
 };
 
 constexpr int EPI_WARPS = 8;                         // two warps per TMEM lane quarter
@@ -170,24 +172,6 @@ __device__ __forceinline__ void store_split_chunk(const float (&v)[32], __half* 
   }
 }
 
-__device__ __forceinline__ void load_split_chunk(const __half* hi, const __half* lo, float (&v)[32]) {
-  const uint4* sh = reinterpret_cast<const uint4*>(hi);
-  const uint4* sl = reinterpret_cast<const uint4*>(lo);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint4 a = sh[i], b = sl[i];
-    const uint32_t ah[4] = {a.x, a.y, a.z, a.w}, bl[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __half2 h2 = *reinterpret_cast<const __half2*>(&ah[j]);
-      const __half2 l2 = *reinterpret_cast<const __half2*>(&bl[j]);
-      const float2 hf = __half22float2(h2), lf = __half22float2(l2);
-      v[i * 8 + j * 2] = hf.x + lf.x;
-      v[i * 8 + j * 2 + 1] = hf.y + lf.y;
-    }
-  }
-}
-
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -214,7 +198,7 @@ __device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the TMA/MMA main loop of tile i + 1.
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(200)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
           const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
@@ -313,9 +297,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
             const uint32_t off = kk * 32;   // 16 halves = 32 bytes inside the 128B swizzle row
             const uint64_t ah = make_desc(sAh + off), al = make_desc(sAl + off);
             const uint64_t wh = make_desc(sWh + off), wl = make_desc(sWl + off);
-            umma(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
-            umma(tacc, ah, wl, idesc, 1u);
-            umma(tacc, ah, wh, idesc, 1u);
+            if (!(p.dbg & 4)) {
+              umma(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
+              umma(tacc, ah, wl, idesc, 1u);
+              umma(tacc, ah, wh, idesc, 1u);
+            }
           }
           umma_commit(smem_u32(&bar_empty[s]));      // frees the stage when these MMAs retire
         }
@@ -337,9 +323,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       const int m = m0 + row;
       const bool row_ok = m < p.M;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + hf * (BN / 2));
-      mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
-      tc_fence_after();
       if (!p.ln) {
+        mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
         int seq = 0, pos = m;
         if (row_ok && p.in_group < p.M) { seq = m / p.in_group; pos = m - seq * p.in_group; }
         const int64_t orow = (int64_t)seq * p.out_group + p.out_off + pos;
@@ -352,7 +338,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         __half* const olo = p.out_lo;
         const int64_t obase = orow * p.ld_out + p.out_col0;
 #pragma unroll 1
-        for (int c = 0; c < CH; ++c) {
+        for (int c = 0; c < ((p.dbg & 2) ? 0 : CH); ++c) {
           tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
           const int nb = n0 + hf * (BN / 2) + c * 32;
           if (row_ok && nb < N) {
@@ -364,7 +350,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
                 case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, s_bias + nb, inv_scale); break;
                 default:       epi_chunk_fast<ACT_SILU>(r, v, s_bias + nb, inv_scale); break;
               }
-              store_split_chunk(v, ohi + obase + nb, olo + obase + nb);
+              if (!(p.dbg & 1)) store_split_chunk(v, ohi + obase + nb, olo + obase + nb);
             } else {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
@@ -399,59 +385,68 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           __syncwarp();
         }
       } else {
-        // x = acc*s + bias + residual (+ rowvec); y = LayerNorm(x) over the 256-wide row (two-pass
-        // statistics, eps 1e-5).  Two warps share a row (column halves) and exchange partial sums
-        // through shared memory; the pre-norm row is parked in TMEM between the passes.
+        // x = acc*s + bias + residual (+ rowvec); y = LayerNorm(x) over the 256-wide row, eps 1e-5.
+        // Two warps share a row (column halves) and exchange partial sums through shared memory; the
+        // pre-norm row is parked in TMEM between the statistics pass and the normalise pass.
+        // Statistics in one pass with a per-row shift K (the row's first residual value) so that
+        // var = E[(x-K)^2] - E[x-K]^2 does not cancel.  The residual chunk c+1 is fetched while
+        // chunk c is processed (the loop is fully unrolled), chunk 0 before the accumulator is ready.
         const float* rv = (row_ok && p.rowvec) ? p.rowvec + (int64_t)(m / p.rv_group) * BN : nullptr;
         const int cb = hf * (BN / 2);
-        float sum = 0.0f;
-#pragma unroll 1
+        const bool has_res = row_ok && p.res_hi != nullptr;
+        const __half* rbh = p.res_hi + (int64_t)m * p.ld_res;
+        const __half* rbl = p.res_lo + (int64_t)m * p.ld_res;
+        const float shiftK = has_res ? join_f32(rbh[0], rbl[0]) : 0.0f;
+        uint4 rawh[2][4], rawl[2][4];            // residual chunk double buffer (hi / lo planes)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          rawh[0][i] = has_res ? reinterpret_cast<const uint4*>(rbh + cb)[i] : make_uint4(0, 0, 0, 0);
+          rawl[0][i] = has_res ? reinterpret_cast<const uint4*>(rbl + cb)[i] : make_uint4(0, 0, 0, 0);
+        }
+        mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
+        float s1 = 0.0f, s2 = 0.0f;
+        const float sc = p.inv_scale;
+#pragma unroll
         for (int c = 0; c < CH; ++c) {
-          tmem_ld32(trow + c * 32, r);
-          if (row_ok && p.res_hi) {
-            const int64_t o = (int64_t)m * p.ld_res + cb + c * 32;
-            load_split_chunk(p.res_hi + o, p.res_lo + o, v);
-          } else {
+          if (c + 1 < CH) {                       // fetch the next residual chunk under this one
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.0f;
+            for (int i = 0; i < 4; ++i) {
+              rawh[(c + 1) & 1][i] = has_res ? reinterpret_cast<const uint4*>(rbh + cb + (c + 1) * 32)[i] : make_uint4(0, 0, 0, 0);
+              rawl[(c + 1) & 1][i] = has_res ? reinterpret_cast<const uint4*>(rbl + cb + (c + 1) * 32)[i] : make_uint4(0, 0, 0, 0);
+            }
           }
-          {
-            const float4* b4 = reinterpret_cast<const float4*>(s_bias + cb + c * 32);
-            const float sc = p.inv_scale;
+          tmem_ld32(trow + c * 32, r);
+          const float4* b4 = reinterpret_cast<const float4*>(s_bias + cb + c * 32);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = b4[i];
-              float x0 = fmaf(__uint_as_float(r[4 * i + 0]), sc, b.x) + v[4 * i + 0];
-              float x1 = fmaf(__uint_as_float(r[4 * i + 1]), sc, b.y) + v[4 * i + 1];
-              float x2 = fmaf(__uint_as_float(r[4 * i + 2]), sc, b.z) + v[4 * i + 2];
-              float x3 = fmaf(__uint_as_float(r[4 * i + 3]), sc, b.w) + v[4 * i + 3];
-              if (rv) {
-                const float4 q4 = *reinterpret_cast<const float4*>(rv + cb + c * 32 + 4 * i);
-                x0 += q4.x; x1 += q4.y; x2 += q4.z; x3 += q4.w;
-              }
-              sum += (x0 + x1) + (x2 + x3);
-              r[4 * i + 0] = __float_as_uint(x0); r[4 * i + 1] = __float_as_uint(x1);
-              r[4 * i + 2] = __float_as_uint(x2); r[4 * i + 3] = __float_as_uint(x3);
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t ah[4] = {rawh[c & 1][i].x, rawh[c & 1][i].y, rawh[c & 1][i].z, rawh[c & 1][i].w};
+            const uint32_t al[4] = {rawl[c & 1][i].x, rawl[c & 1][i].y, rawl[c & 1][i].z, rawl[c & 1][i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&ah[j]));
+              const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&al[j]));
+              const int e = i * 8 + j * 2;
+              const float bia0 = reinterpret_cast<const float*>(b4)[e], bia1 = reinterpret_cast<const float*>(b4)[e + 1];
+              float x0 = fmaf(__uint_as_float(r[e]), sc, bia0) + (hf2.x + lf2.x);
+              float x1 = fmaf(__uint_as_float(r[e + 1]), sc, bia1) + (hf2.y + lf2.y);
+              if (rv) { x0 += rv[cb + c * 32 + e]; x1 += rv[cb + c * 32 + e + 1]; }
+              const float d0 = x0 - shiftK, d1 = x1 - shiftK;
+              s1 += d0 + d1;
+              s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+              r[e] = __float_as_uint(x0);
+              r[e + 1] = __float_as_uint(x1);
             }
           }
           tmem_st32(trow + c * 32, r);
         }
-        s_part[hf * 128 + row] = sum;
+        s_part[hf * 128 + row] = s1;
+        s_part[256 + hf * 128 + row] = s2;
         epi_bar_sync();
-        const float mean = (s_part[row] + s_part[128 + row]) * (1.0f / BN);
-        float sq = 0.0f;
-#pragma unroll 1
-        for (int c = 0; c < CH; ++c) {
-          tmem_ld32(trow + c * 32, r);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float dlt = __uint_as_float(r[i]) - mean;
-            sq += dlt * dlt;
-          }
-        }
-        s_part[256 + hf * 128 + row] = sq;
-        epi_bar_sync();
-        const float rstd = rsqrtf((s_part[256 + row] + s_part[256 + 128 + row]) * (1.0f / BN) + 1e-5f);
+        const float e1 = (s_part[row] + s_part[128 + row]) * (1.0f / BN);
+        const float e2 = (s_part[256 + row] + s_part[256 + 128 + row]) * (1.0f / BN);
+        const float mean = shiftK + e1;
+        const float rstd = rsqrtf(fmaxf(e2 - e1 * e1, 0.0f) + 1e-5f);
 #pragma unroll 1
         for (int c = 0; c < CH; ++c) {
           tmem_ld32(trow + c * 32, r);
@@ -473,6 +468,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           }
           __syncwarp();
         }
+        // the partial sums of this tile may be overwritten only after everyone has read them
+        epi_bar_sync();
       }
       // this warp is done reading the accumulator stage: hand it back to the MMA warp
       tc_fence_before();
@@ -497,6 +494,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapFloatOOBfill);
 
 struct TcCtx {
+  int dbg = 0;
   int device = 0;
   int sm_count = 148;
   PFN_tmapEncodeTiled encode = nullptr;
@@ -515,6 +513,7 @@ TcCtx* tc_create(int device) {
     return nullptr;
   }
   c->encode = (PFN_tmapEncodeTiled)fn;
+  if (const char* e = getenv("MLDB_TC_DBG")) c->dbg = atoi(e);
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   e = cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::SMEM_BYTES);
   if (e == cudaSuccess)
@@ -589,6 +588,7 @@ void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
     p.out_hi = g.out.hi; p.out_lo = g.out.hi ? g.out.lo() : nullptr; p.ld_out = g.out.cols; p.out_col0 = g.out_col0;
     p.out_f32 = g.out_f32; p.ldc = g.ldc;
   }
+  p.dbg = c->dbg;
   p.m_tiles = (g.M + BM - 1) / BM;
   p.n_tiles = (g.w.N + bn - 1) / bn;
   const int ntiles = p.m_tiles * p.n_tiles;

@@ -13,4 +13,4 @@ eng.finalize()
 eng.set_timesteps(2)
 ops = sys.argv[1:] or ["qkv", "attn", "outproj_ln", "ffn1", "ffn2_ln"]
 for op in ops:
-    print(op, eng.profile_op(op, 256, 77, 1), "ms")
+    print(op, eng.profile_op(op, 256, 77, int(__import__("os").environ.get("PROF_ITERS", "10"))), "ms")

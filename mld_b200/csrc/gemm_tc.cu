@@ -198,7 +198,7 @@ __device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the TMA/MMA main loop of tile i + 1.
 template <int BN>
-__global__ void __maxnreg__(200)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
           const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,

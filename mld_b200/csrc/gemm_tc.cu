@@ -148,7 +148,8 @@ struct TileCfg {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator
   // bias[MAX_N] + gamma[256] + beta[256] + LN partials [2][2][128] + barriers
-  static constexpr int AUX_BYTES = MAX_N * 4 + 2 * 256 * 4 + 4 * 128 * 4 + 256;
+  static constexpr int STG_BYTES = EPI_WARPS * 2048;   // per-warp 32 rows x 64 B transpose buffer
+  static constexpr int AUX_BYTES = MAX_N * 4 + 2 * 256 * 4 + 4 * 128 * 4 + 256 + STG_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;   // + alignment slack
 };
 
@@ -169,6 +170,59 @@ __device__ __forceinline__ void store_split_chunk(const float (&v)[32], __half* 
   for (int i = 0; i < 4; ++i) {
     dh[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
     dl[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
+  }
+}
+
+// ---- warp-level transpose through shared memory so that global accesses are row-contiguous.
+// A thread owns one tile row (TMEM lane); a 32-column fp16 chunk of that row is 64 B = 4 x 16 B
+// slots.  Staging tile: 32 rows x 64 B, slot index XOR-swizzled with (row >> 1) & 3 (conflict-free
+// for both the row-owner pattern and the coalesced pattern: lane -> row i*8 + lane/4, slot lane%4).
+__device__ __forceinline__ uint32_t stg_off(int row, int slot) {
+  return (uint32_t)(row * 64 + ((slot ^ ((row >> 1) & 3)) << 4));
+}
+// registers (row-owner layout) -> global, 64-byte row segments written by 4 adjacent lanes
+__device__ __forceinline__ void store_plane_coalesced(uint8_t* stg, const uint32_t (&pk)[16], __half* gbase,
+                                                      int64_t ld, int rows_valid, int lane) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(stg + stg_off(lane, j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2), qq = lane & 3;
+    const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(rr, qq));
+    if (rr < rows_valid) *reinterpret_cast<uint4*>(gbase + (int64_t)rr * ld + qq * 8) = val;
+  }
+  __syncwarp();
+}
+// global (coalesced pattern, issued earlier into g[4]) -> registers in row-owner layout
+__device__ __forceinline__ void load_plane_issue(const __half* gbase, int64_t ld, int rows_valid, int lane, uint4 (&g)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2), qq = lane & 3;
+    g[i] = (rr < rows_valid) ? *reinterpret_cast<const uint4*>(gbase + (int64_t)rr * ld + qq * 8) : make_uint4(0, 0, 0, 0);
+  }
+}
+__device__ __forceinline__ void plane_to_rows(uint8_t* stg, const uint4 (&g)[4], int lane, uint4 (&rowv)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2), qq = lane & 3;
+    *reinterpret_cast<uint4*>(stg + stg_off(rr, qq)) = g[i];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rowv[j] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
+  __syncwarp();
+}
+// fp32 x32 -> packed split16 words (hi and lo planes)
+__device__ __forceinline__ void pack_split(const float (&v)[32], uint32_t (&ph)[16], uint32_t (&pl)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
   }
 }
 
@@ -212,7 +266,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   float* s_gamma = s_bias + MAX_N;                            // [256]
   float* s_beta = s_gamma + 256;                              // [256]
   float* s_part = s_beta + 256;                               // [2 passes][2 halves][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 4 * 128);
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_part + 4 * 128);   // [EPI_WARPS][2048], 16B aligned
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + Cfg::STG_BYTES);
   // bars: full[S], empty[S], tmem_full[2], tmem_empty[2]
   uint64_t* bar_full = bars;
   uint64_t* bar_empty = bars + STAGES;
@@ -323,6 +378,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       const int m = m0 + row;
       const bool row_ok = m < p.M;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + hf * (BN / 2));
+      uint8_t* const stg = s_stage + (warp - 2) * 2048;
+      const int wrow0 = m0 + q * 32;                         // first tile row owned by this warp
+      const int rows_valid = min(32, p.M - wrow0);           // <= 0: nothing to write
       if (!p.ln) {
         mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
         tc_fence_after();
@@ -331,7 +389,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         const int64_t orow = (int64_t)seq * p.out_group + p.out_off + pos;
         const bool zero = row_ok && p.zero_lengths != nullptr && pos >= p.zero_lengths[seq];
         const float* tab = p.addtab ? p.addtab + (int64_t)(p.out_off + pos) * p.N : nullptr;
-        const bool fast = tab == nullptr && !zero && p.out_hi != nullptr && p.out_f32 == nullptr;
+        // fast path: identity row mapping, split16 output, no table / masking (warp-uniform)
+        const bool fast = p.addtab == nullptr && p.zero_lengths == nullptr && p.out_hi != nullptr &&
+                          p.out_f32 == nullptr && p.in_group >= p.M && p.out_group == 0 && p.out_off == 0;
         const float inv_scale = p.inv_scale;
         const int act = p.act, N = p.N;
         __half* const ohi = p.out_hi;
@@ -341,17 +401,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         for (int c = 0; c < ((p.dbg & 2) ? 0 : CH); ++c) {
           tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
           const int nb = n0 + hf * (BN / 2) + c * 32;
-          if (row_ok && nb < N) {
+          if (fast && nb + 32 <= N) {               // warp-uniform branch: all lanes take part
+            switch (act) {                          // once per chunk
+              case ACT_NONE: epi_chunk_fast<ACT_NONE>(r, v, s_bias + nb, inv_scale); break;
+              case ACT_GELU: epi_chunk_fast<ACT_GELU>(r, v, s_bias + nb, inv_scale); break;
+              case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, s_bias + nb, inv_scale); break;
+              default:       epi_chunk_fast<ACT_SILU>(r, v, s_bias + nb, inv_scale); break;
+            }
+            uint32_t ph[16], pl[16];
+            pack_split(v, ph, pl);
+            if (!(p.dbg & 1)) {
+              const int64_t o = (int64_t)wrow0 * p.ld_out + p.out_col0 + nb;
+              store_plane_coalesced(stg, ph, ohi + o, p.ld_out, rows_valid, lane);
+              store_plane_coalesced(stg, pl, olo + o, p.ld_out, rows_valid, lane);
+            }
+          } else if (row_ok && nb < N) {
             const bool full = nb + 32 <= N;
-            if (fast && full) {
-              switch (act) {                          // warp-uniform, once per chunk
-                case ACT_NONE: epi_chunk_fast<ACT_NONE>(r, v, s_bias + nb, inv_scale); break;
-                case ACT_GELU: epi_chunk_fast<ACT_GELU>(r, v, s_bias + nb, inv_scale); break;
-                case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, s_bias + nb, inv_scale); break;
-                default:       epi_chunk_fast<ACT_SILU>(r, v, s_bias + nb, inv_scale); break;
-              }
-              if (!(p.dbg & 1)) store_split_chunk(v, ohi + obase + nb, olo + obase + nb);
-            } else {
+            {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 float x = __uint_as_float(r[i]) * inv_scale + s_bias[min(nb + i, MAX_N - 1)];
@@ -393,15 +459,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         // chunk c is processed (the loop is fully unrolled), chunk 0 before the accumulator is ready.
         const float* rv = (row_ok && p.rowvec) ? p.rowvec + (int64_t)(m / p.rv_group) * BN : nullptr;
         const int cb = hf * (BN / 2);
-        const bool has_res = row_ok && p.res_hi != nullptr;
-        const __half* rbh = p.res_hi + (int64_t)m * p.ld_res;
-        const __half* rbl = p.res_lo + (int64_t)m * p.ld_res;
-        const float shiftK = has_res ? join_f32(rbh[0], rbl[0]) : 0.0f;
-        uint4 rawh[2][4], rawl[2][4];            // residual chunk double buffer (hi / lo planes)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          rawh[0][i] = has_res ? reinterpret_cast<const uint4*>(rbh + cb)[i] : make_uint4(0, 0, 0, 0);
-          rawl[0][i] = has_res ? reinterpret_cast<const uint4*>(rbl + cb)[i] : make_uint4(0, 0, 0, 0);
+        const bool has_res = p.res_hi != nullptr;                       // warp-uniform
+        const float shiftK = (has_res && row_ok) ? join_f32(p.res_hi[(int64_t)m * p.ld_res], p.res_lo[(int64_t)m * p.ld_res]) : 0.0f;
+        const __half* rbh = p.res_hi + (int64_t)wrow0 * p.ld_res + cb;   // this warp's 32 rows, its column half
+        const __half* rbl = p.res_lo + (int64_t)wrow0 * p.ld_res + cb;
+        uint4 gh[4], gl[4];                       // residual chunk in the coalesced (4 lanes per row) pattern
+        if (has_res) {
+          load_plane_issue(rbh, p.ld_res, rows_valid, lane, gh);
+          load_plane_issue(rbl, p.ld_res, rows_valid, lane, gl);
         }
         mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
         tc_fence_after();
@@ -409,27 +474,33 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         const float sc = p.inv_scale;
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
-          if (c + 1 < CH) {                       // fetch the next residual chunk under this one
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              rawh[(c + 1) & 1][i] = has_res ? reinterpret_cast<const uint4*>(rbh + cb + (c + 1) * 32)[i] : make_uint4(0, 0, 0, 0);
-              rawl[(c + 1) & 1][i] = has_res ? reinterpret_cast<const uint4*>(rbl + cb + (c + 1) * 32)[i] : make_uint4(0, 0, 0, 0);
+          uint4 rh[4], rl[4];                     // the same chunk, row-owner layout
+          if (has_res) {
+            plane_to_rows(stg, gh, lane, rh);
+            plane_to_rows(stg, gl, lane, rl);
+            if (c + 1 < CH) {                     // fetch the next chunk under this one's math
+              load_plane_issue(rbh + (c + 1) * 32, p.ld_res, rows_valid, lane, gh);
+              load_plane_issue(rbl + (c + 1) * 32, p.ld_res, rows_valid, lane, gl);
             }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
           }
           tmem_ld32(trow + c * 32, r);
-          const float4* b4 = reinterpret_cast<const float4*>(s_bias + cb + c * 32);
+          const float* bch = s_bias + cb + c * 32;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const uint32_t ah[4] = {rawh[c & 1][i].x, rawh[c & 1][i].y, rawh[c & 1][i].z, rawh[c & 1][i].w};
-            const uint32_t al[4] = {rawl[c & 1][i].x, rawl[c & 1][i].y, rawl[c & 1][i].z, rawl[c & 1][i].w};
+            const uint32_t ah[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
+            const uint32_t al[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
+            const float4 b0 = reinterpret_cast<const float4*>(bch)[2 * i], b1 = reinterpret_cast<const float4*>(bch)[2 * i + 1];
+            const float bia[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&ah[j]));
               const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&al[j]));
               const int e = i * 8 + j * 2;
-              const float bia0 = reinterpret_cast<const float*>(b4)[e], bia1 = reinterpret_cast<const float*>(b4)[e + 1];
-              float x0 = fmaf(__uint_as_float(r[e]), sc, bia0) + (hf2.x + lf2.x);
-              float x1 = fmaf(__uint_as_float(r[e + 1]), sc, bia1) + (hf2.y + lf2.y);
+              float x0 = fmaf(__uint_as_float(r[e]), sc, bia[2 * j]) + (hf2.x + lf2.x);
+              float x1 = fmaf(__uint_as_float(r[e + 1]), sc, bia[2 * j + 1]) + (hf2.y + lf2.y);
               if (rv) { x0 += rv[cb + c * 32 + e]; x1 += rv[cb + c * 32 + e + 1]; }
               const float d0 = x0 - shiftK, d1 = x1 - shiftK;
               s1 += d0 + d1;
@@ -462,11 +533,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
               v[4 * i + 3] = fmaf((__uint_as_float(r[4 * i + 3]) - mean) * rstd, gg.w, bb.w);
             }
           }
-          if (row_ok) {
-            const int64_t o = (int64_t)m * p.ld_out + cb + c * 32;
-            store_split_chunk(v, p.out_hi + o, p.out_lo + o);
-          }
-          __syncwarp();
+          uint32_t ph[16], pl[16];
+          pack_split(v, ph, pl);
+          const int64_t o = (int64_t)wrow0 * p.ld_out + cb + c * 32;
+          store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
+          store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
         }
         // the partial sums of this tile may be overwritten only after everyone has read them
         epi_bar_sync();

@@ -497,6 +497,8 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   if (!h->tc) { delete h; return MLDB_ERR_CUDA; }
   const char* env = getenv("MLDB_GEMM");
   if (env && !strcmp(env, "simt")) h->use_tc = false;
+  env = getenv("MLDB_CHUNK");
+  if (env) h->chunk_seqs = atoi(env);
   env = getenv("MLDB_GRAPH");
   if (env && !strcmp(env, "0")) h->use_graph = false;
   *out = h;
@@ -523,6 +525,8 @@ extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* val
     if (!strcmp(value, "tc")) h->use_tc = true;
     else if (!strcmp(value, "simt")) h->use_tc = false;
     else FAIL(MLDB_ERR_INVALID, "gemm must be tc|simt");
+  } else if (!strcmp(name, "chunk")) {
+    h->chunk_seqs = atoi(value);
   } else if (!strcmp(name, "graph")) {
     h->use_graph = strcmp(value, "0") != 0;
   } else {
@@ -830,11 +834,23 @@ static void denoiser_pass(mldb_handle* h, Plan* p, const float* latents, int lat
       p->ws.x0, p->Ntok, p->Bx, lat_mod, c.n_lat, d, latents, h->query_pe, tt);
   count_launch(h);
   SeqInfo si;
-  ActBuf x = run_stack(h, h->den, p->ws.x0, ActBuf{}, p->ws, si, st);
-  // encoder.norm on the latent tokens only (cross_attention.py:62-63, mld_denoiser.py:206)
-  LnArgs l; l.res = x; l.gamma = h->den.norm.g; l.beta = h->den.norm.b; l.M = p->Bx * c.n_lat; l.d = d;
-  l.sel_group = c.n_lat; l.in_group = p->Ntok; l.out_f32 = eps_out; l.ld_out = d;
-  op_ln(h, l, st);
+  // Sequences are independent, so the stack runs over chunks of `chunk_seqs` sequences that reuse
+  // the SAME workspace rows: a chunk's activations (qkv, FFN hidden, ...) then stay resident in the
+  // 126 MB L2 from the kernel that writes them to the kernel that reads them instead of streaming
+  // through HBM (~870 MB per layer for the whole 40 448-token batch).
+  const int cs = (h->chunk_seqs > 0 && h->chunk_seqs < p->Bx) ? h->chunk_seqs : p->Bx;
+  for (int s0 = 0; s0 < p->Bx; s0 += cs) {
+    const int n = std::min(cs, p->Bx - s0);
+    StackWs w = p->ws;
+    w.nseq = n; w.M = n * p->Ntok;
+    ActBuf x0v = p->ws.x0;
+    x0v.hi += (int64_t)s0 * p->Ntok * x0v.cols; x0v.rows = w.M;
+    ActBuf x = run_stack(h, h->den, x0v, ActBuf{}, w, si, st);
+    // encoder.norm on the latent tokens only (cross_attention.py:62-63, mld_denoiser.py:206)
+    LnArgs l; l.res = x; l.gamma = h->den.norm.g; l.beta = h->den.norm.b; l.M = n * c.n_lat; l.d = d;
+    l.sel_group = c.n_lat; l.in_group = p->Ntok; l.out_f32 = eps_out + (size_t)s0 * c.n_lat * d; l.ld_out = d;
+    op_ln(h, l, st);
+  }
 }
 
 // ----------------------------------------------------------------------------- denoiser (trans_dec)

@@ -6,16 +6,13 @@
 // [N, K] (PyTorch's [out, in] layout is already the K-major B operand), also split into hi/lo
 // planes.  Three kind::f16 MMAs per K-step reproduce the reference's fp32 GEMM to ~1e-6.
 //
-// Persistent CTAs (one per SM) of 18 warps: warp 0 = TMA producer (one elected lane), warp 1 = TMEM
-// allocator + MMA issuer (one lane), warps 2..17 = epilogue (TMEM lane quarter = warp_id % 4, four
-// warps per quarter each owning a quarter of the tile's columns).  Operands stream through a
+// CTA = 6 warps: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer
+// (one lane), warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Operands stream through a
 // STAGES-deep ring of 128B-swizzled shared-memory tiles (BK = 64 halves = one swizzle row) filled
-// by cp.async.bulk.tensor (TMA) and released by tcgen05.commit; the fp32 accumulator is
-// double-buffered in TMEM so the epilogue of tile i overlaps the main loop of tile i+1, and is read
-// back with tcgen05.ld.  Epilogues: bias (+ positional table) + activation -> split16 / fp32 store,
-// or bias + residual + LayerNorm over the full row (BN == N == 256) -> split16 store with the
-// pre-norm row parked in TMEM between the statistics pass and the normalise pass.  Global stores and
-// residual loads go through a per-warp shared-memory transpose so that they are sector-contiguous.
+// by cp.async.bulk.tensor (TMA) and released by tcgen05.commit; the accumulator is read back with
+// tcgen05.ld.  Epilogues: bias (+ positional table) + activation -> split16 / fp32 store, or
+// bias + residual + LayerNorm over the full row (BN == N == 256) -> split16 store, with the row's
+// pre-norm values parked in TMEM between the statistics passes.
 #include "gemm_tc.h"
 
 #include <cuda.h>
@@ -105,6 +102,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
 // ------------------------------------------------------------------------------ parameters
 struct TcParams {
@@ -119,16 +128,15 @@ struct TcParams {
   int in_group, out_group, out_off;
   const int32_t* zero_lengths;
   // residual + LayerNorm epilogue
+  int ln;
   const __half* res_hi; const __half* res_lo; int ld_res;
   const float* rowvec; int rv_group;
   const float* gamma; const float* beta;
-  int dbg;   // timing experiments only (MLDB_TC_DBG): 1 = no global stores, 2 = no epilogue, 4 = no MMA
+  const float* gamma2; const float* beta2;
+  int dbg;   // timing experiments only (MLDB_TC_DBG): 1 = no global stores, 2 = no epilogue math/loads, 4 = no MMA
 };
 
-// The epilogue is ALU/latency bound (bias, GELU, hi/lo split, LayerNorm), so it gets 16 warps -
-// four per TMEM lane quarter, each owning a quarter of the tile's columns - to keep four warps
-// resident on every SM sub-partition.
-constexpr int EPI_WARPS = 16;
+constexpr int EPI_WARPS = 8;                         // two warps per TMEM lane quarter
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;     // producer warp + MMA warp + epilogue warps
 constexpr int MAX_N = 1024;                          // bias staging capacity
 
@@ -139,90 +147,77 @@ struct TileCfg {
   static constexpr int W_BYTES = BN * BK * 2;          // one plane of the W tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator
-  static constexpr int STG_BYTES = EPI_WARPS * 1024;   // per-warp 32 rows x 32 B transpose buffer
-  // bias[MAX_N] + gamma[256] + beta[256] + LN partials [2][4][128] + staging + barriers
-  static constexpr int AUX_BYTES = MAX_N * 4 + 2 * 256 * 4 + 8 * 128 * 4 + STG_BYTES + 256;
+  // bias[MAX_N] + gamma[256] + beta[256] + LN partials [2][2][128] + barriers
+  static constexpr int STG_BYTES = EPI_WARPS * 2048;   // per-warp 32 rows x 64 B transpose buffer
+  static constexpr int AUX_BYTES = MAX_N * 4 + 2 * 256 * 4 + 4 * 128 * 4 + 256 + STG_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;   // + alignment slack
 };
 
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// direct (row-owner) split16 store of 32 values - generic path only
+// fp32 x32 -> split16 hi/lo planes (64 B each) with packed conversions
 __device__ __forceinline__ void store_split_chunk(const float (&v)[32], __half* hi, __half* lo) {
+  uint32_t ph[16], pl[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 hf = __half22float2(h2);
+    const __half2 l2 = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
+    ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
+    pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
+  }
+  uint4* dh = reinterpret_cast<uint4*>(hi);
+  uint4* dl = reinterpret_cast<uint4*>(lo);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    uint32_t ph[4], pl[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __half2 h2 = __floats2half2_rn(v[8 * i + 2 * j], v[8 * i + 2 * j + 1]);
-      const float2 hf = __half22float2(h2);
-      const __half2 l2 = __floats2half2_rn(v[8 * i + 2 * j] - hf.x, v[8 * i + 2 * j + 1] - hf.y);
-      ph[j] = *reinterpret_cast<const uint32_t*>(&h2);
-      pl[j] = *reinterpret_cast<const uint32_t*>(&l2);
-    }
-    reinterpret_cast<uint4*>(hi)[i] = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-    reinterpret_cast<uint4*>(lo)[i] = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    dh[i] = make_uint4(ph[4 * i], ph[4 * i + 1], ph[4 * i + 2], ph[4 * i + 3]);
+    dl[i] = make_uint4(pl[4 * i], pl[4 * i + 1], pl[4 * i + 2], pl[4 * i + 3]);
   }
 }
 
 // ---- warp-level transpose through shared memory so that global accesses are row-contiguous.
-// A thread owns one tile row (TMEM lane).  Staging tile per warp: 32 rows x 32 B (16 fp16 columns of
-// one plane), the two 16-byte slots XOR-swizzled with (row >> 2) & 1 (conflict-free for both the
-// row-owner pattern and the coalesced pattern: lane -> row i*16 + lane/2, slot lane%2).
+// A thread owns one tile row (TMEM lane); a 32-column fp16 chunk of that row is 64 B = 4 x 16 B
+// slots.  Staging tile: 32 rows x 64 B, slot index XOR-swizzled with (row >> 1) & 3 (conflict-free
+// for both the row-owner pattern and the coalesced pattern: lane -> row i*8 + lane/4, slot lane%4).
 __device__ __forceinline__ uint32_t stg_off(int row, int slot) {
-  return (uint32_t)(row * 32 + ((slot ^ ((row >> 2) & 1)) << 4));
+  return (uint32_t)(row * 64 + ((slot ^ ((row >> 1) & 3)) << 4));
 }
-// 8 packed words (16 halves of this thread's row) -> global; 32-byte sectors written whole
-__device__ __forceinline__ void store_half_coalesced(uint8_t* stg, const uint32_t* w, __half* gbase, int64_t ld,
-                                                     int rows_valid, int lane) {
-  *reinterpret_cast<uint4*>(stg + stg_off(lane, 0)) = make_uint4(w[0], w[1], w[2], w[3]);
-  *reinterpret_cast<uint4*>(stg + stg_off(lane, 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+// registers (row-owner layout) -> global, 64-byte row segments written by 4 adjacent lanes
+__device__ __forceinline__ void store_plane_coalesced(uint8_t* stg, const uint32_t (&pk)[16], __half* gbase,
+                                                      int64_t ld, int rows_valid, int lane) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    *reinterpret_cast<uint4*>(stg + stg_off(lane, j)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
   __syncwarp();
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int rr = i * 16 + (lane >> 1), qq = lane & 1;
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2), qq = lane & 3;
     const uint4 val = *reinterpret_cast<const uint4*>(stg + stg_off(rr, qq));
     if (rr < rows_valid) *reinterpret_cast<uint4*>(gbase + (int64_t)rr * ld + qq * 8) = val;
   }
   __syncwarp();
 }
-// global (coalesced pattern) -> this thread's row: 16 halves as 2 x uint4
-__device__ __forceinline__ void load_half_rows(uint8_t* stg, const __half* gbase, int64_t ld, int rows_valid,
-                                               int lane, uint4 (&rowv)[2]) {
+// global (coalesced pattern, issued earlier into g[4]) -> registers in row-owner layout
+__device__ __forceinline__ void load_plane_issue(const __half* gbase, int64_t ld, int rows_valid, int lane, uint4 (&g)[4]) {
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int rr = i * 16 + (lane >> 1), qq = lane & 1;
-    const uint4 g = (rr < rows_valid) ? *reinterpret_cast<const uint4*>(gbase + (int64_t)rr * ld + qq * 8)
-                                      : make_uint4(0, 0, 0, 0);
-    *reinterpret_cast<uint4*>(stg + stg_off(rr, qq)) = g;
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2), qq = lane & 3;
+    g[i] = (rr < rows_valid) ? *reinterpret_cast<const uint4*>(gbase + (int64_t)rr * ld + qq * 8) : make_uint4(0, 0, 0, 0);
+  }
+}
+__device__ __forceinline__ void plane_to_rows(uint8_t* stg, const uint4 (&g)[4], int lane, uint4 (&rowv)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2), qq = lane & 3;
+    *reinterpret_cast<uint4*>(stg + stg_off(rr, qq)) = g[i];
   }
   __syncwarp();
-  rowv[0] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, 0));
-  rowv[1] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, 1));
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rowv[j] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
   __syncwarp();
 }
-// fp32 x16 -> packed split16 words (8 hi, 8 lo)
-__device__ __forceinline__ void pack_split16(const float* v, uint32_t (&ph)[8], uint32_t (&pl)[8]) {
+// fp32 x32 -> packed split16 words (hi and lo planes)
+__device__ __forceinline__ void pack_split(const float (&v)[32], uint32_t (&ph)[16], uint32_t (&pl)[16]) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < 16; ++i) {
     const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
     const float2 hf = __half22float2(h2);
     const __half2 l2 = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
@@ -255,8 +250,8 @@ __device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&
 // ------------------------------------------------------------------------------ the kernel
 // Persistent: CTA c walks tiles c, c + gridDim.x, ...; tile t -> (m = t / n_tiles, n = t % n_tiles).
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
-// the TMA/MMA main loop of tile i + 1.  LN = residual + LayerNorm epilogue (BN == N == 256).
-template <int BN, bool LN>
+// the TMA/MMA main loop of tile i + 1.
+template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
@@ -270,8 +265,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   float* s_bias = reinterpret_cast<float*>(aux);              // [MAX_N]
   float* s_gamma = s_bias + MAX_N;                            // [256]
   float* s_beta = s_gamma + 256;                              // [256]
-  float* s_part = s_beta + 256;                               // [2 stats][4 column quarters][128 rows]
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_part + 8 * 128);   // [EPI_WARPS][1024]
+  float* s_part = s_beta + 256;                               // [2 passes][2 halves][128 rows]
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_part + 4 * 128);   // [EPI_WARPS][2048], 16B aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + Cfg::STG_BYTES);
   // bars: full[S], empty[S], tmem_full[2], tmem_empty[2]
   uint64_t* bar_full = bars;
@@ -301,7 +296,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   }
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.0f;
-    if (LN)
+    if (p.ln)
       for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) { s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
   }
   tc_fence_before();
@@ -369,26 +364,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..17)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int qj = (warp - 2) >> 2;                  // which quarter of the tile's columns
+    const int hf = (warp - 2) >> 2;                  // which half of the tile's columns
     const int row = q * 32 + lane;
-    constexpr int QC = BN / 4;                       // columns per warp (64 or 32)
-    uint8_t* const stg = s_stage + (warp - 2) * 1024;
+    constexpr int CH = BN / 64;                      // 32-column chunks per warp
+    uint32_t r[32];
+    float v[32];
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
       const int m = m0 + row;
       const bool row_ok = m < p.M;
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + qj * QC);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + hf * (BN / 2));
+      uint8_t* const stg = s_stage + (warp - 2) * 2048;
       const int wrow0 = m0 + q * 32;                         // first tile row owned by this warp
       const int rows_valid = min(32, p.M - wrow0);           // <= 0: nothing to write
-      mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
-      tc_fence_after();
-      if (!LN) {
-        uint32_t r[32];
-        float v[32];
+      if (!p.ln) {
+        mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
         int seq = 0, pos = m;
         if (row_ok && p.in_group < p.M) { seq = m / p.in_group; pos = m - seq * p.in_group; }
         const int64_t orow = (int64_t)seq * p.out_group + p.out_off + pos;
@@ -403,9 +398,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         __half* const olo = p.out_lo;
         const int64_t obase = orow * p.ld_out + p.out_col0;
 #pragma unroll 1
-        for (int c = 0; c < ((p.dbg & 2) ? 0 : QC / 32); ++c) {
+        for (int c = 0; c < ((p.dbg & 2) ? 0 : CH); ++c) {
           tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
-          const int nb = n0 + qj * QC + c * 32;
+          const int nb = n0 + hf * (BN / 2) + c * 32;
           if (fast && nb + 32 <= N) {               // warp-uniform branch: all lanes take part
             switch (act) {                          // once per chunk
               case ACT_NONE: epi_chunk_fast<ACT_NONE>(r, v, s_bias + nb, inv_scale); break;
@@ -413,78 +408,88 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
               case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, s_bias + nb, inv_scale); break;
               default:       epi_chunk_fast<ACT_SILU>(r, v, s_bias + nb, inv_scale); break;
             }
+            uint32_t ph[16], pl[16];
+            pack_split(v, ph, pl);
             if (!(p.dbg & 1)) {
               const int64_t o = (int64_t)wrow0 * p.ld_out + p.out_col0 + nb;
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {       // 16 columns at a time through the staging tile
-                uint32_t ph[8], pl[8];
-                pack_split16(v + 16 * hh, ph, pl);
-                store_half_coalesced(stg, ph, ohi + o + 16 * hh, p.ld_out, rows_valid, lane);
-                store_half_coalesced(stg, pl, olo + o + 16 * hh, p.ld_out, rows_valid, lane);
-              }
+              store_plane_coalesced(stg, ph, ohi + o, p.ld_out, rows_valid, lane);
+              store_plane_coalesced(stg, pl, olo + o, p.ld_out, rows_valid, lane);
             }
           } else if (row_ok && nb < N) {
             const bool full = nb + 32 <= N;
+            {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = __uint_as_float(r[i]) * inv_scale + s_bias[min(nb + i, MAX_N - 1)];
-              if (tab && (full || nb + i < N)) x += tab[nb + i];
-              x = apply_act(x, act);
-              v[i] = zero ? 0.0f : x;
-            }
-            if (ohi) {
-              const int64_t o = obase + nb;
-              if (full) {
-                store_split_chunk(v, ohi + o, olo + o);
-              } else {
+              for (int i = 0; i < 32; ++i) {
+                float x = __uint_as_float(r[i]) * inv_scale + s_bias[min(nb + i, MAX_N - 1)];
+                if (tab && (full || nb + i < N)) x += tab[nb + i];
+                x = apply_act(x, act);
+                v[i] = zero ? 0.0f : x;
+              }
+              if (ohi) {
+                const int64_t o = obase + nb;
+                if (full) {
+                  store_split_chunk(v, ohi + o, olo + o);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  if (nb + i < N) {
-                    __half h, l;
-                    split_f32(v[i], h, l);
-                    ohi[o + i] = h; olo[o + i] = l;
+                  for (int i = 0; i < 32; ++i) {
+                    if (nb + i < N) {
+                      __half h, l;
+                      split_f32(v[i], h, l);
+                      ohi[o + i] = h; olo[o + i] = l;
+                    }
                   }
                 }
               }
-            }
-            if (p.out_f32) {
-              float* dst = p.out_f32 + orow * p.ldc + nb;
+              if (p.out_f32) {
+                float* dst = p.out_f32 + orow * p.ldc + nb;
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (full || nb + i < N) dst[i] = v[i];
+                for (int i = 0; i < 32; ++i)
+                  if (full || nb + i < N) dst[i] = v[i];
+              }
             }
           }
           __syncwarp();
         }
       } else {
         // x = acc*s + bias + residual (+ rowvec); y = LayerNorm(x) over the 256-wide row, eps 1e-5.
-        // Four warps share a row (column quarters) and exchange partial sums through shared memory;
-        // the pre-norm row is parked in TMEM between the statistics pass and the normalise pass.
-        // One-pass statistics with a per-row shift K (the row's first residual value) so that
-        // var = E[(x-K)^2] - E[x-K]^2 does not cancel.  Work proceeds 16 columns at a time (one
-        // staging tile); latency is hidden by the four epilogue warps per sub-partition.
+        // Two warps share a row (column halves) and exchange partial sums through shared memory; the
+        // pre-norm row is parked in TMEM between the statistics pass and the normalise pass.
+        // Statistics in one pass with a per-row shift K (the row's first residual value) so that
+        // var = E[(x-K)^2] - E[x-K]^2 does not cancel.  The residual chunk c+1 is fetched while
+        // chunk c is processed (the loop is fully unrolled), chunk 0 before the accumulator is ready.
         const float* rv = (row_ok && p.rowvec) ? p.rowvec + (int64_t)(m / p.rv_group) * BN : nullptr;
-        const int cb = qj * QC;
+        const int cb = hf * (BN / 2);
         const bool has_res = p.res_hi != nullptr;                       // warp-uniform
         const float shiftK = (has_res && row_ok) ? join_f32(p.res_hi[(int64_t)m * p.ld_res], p.res_lo[(int64_t)m * p.ld_res]) : 0.0f;
-        const __half* rbh = p.res_hi + (int64_t)wrow0 * p.ld_res + cb;   // this warp's 32 rows, its column quarter
+        const __half* rbh = p.res_hi + (int64_t)wrow0 * p.ld_res + cb;   // this warp's 32 rows, its column half
         const __half* rbl = p.res_lo + (int64_t)wrow0 * p.ld_res + cb;
+        uint4 gh[4], gl[4];                       // residual chunk in the coalesced (4 lanes per row) pattern
+        if (has_res) {
+          load_plane_issue(rbh, p.ld_res, rows_valid, lane, gh);
+          load_plane_issue(rbl, p.ld_res, rows_valid, lane, gl);
+        }
+        mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
         float s1 = 0.0f, s2 = 0.0f;
         const float sc = p.inv_scale;
-        uint32_t r[16];
-#pragma unroll 1
-        for (int c = 0; c < QC / 16; ++c) {
-          uint4 rh[2], rl[2];
-          if (has_res) {
-            load_half_rows(stg, rbh + c * 16, p.ld_res, rows_valid, lane, rh);
-            load_half_rows(stg, rbl + c * 16, p.ld_res, rows_valid, lane, rl);
-          } else {
-            rh[0] = rh[1] = rl[0] = rl[1] = make_uint4(0, 0, 0, 0);
-          }
-          tmem_ld16(trow + c * 16, r);
-          const float* bch = s_bias + cb + c * 16;
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
+        for (int c = 0; c < CH; ++c) {
+          uint4 rh[4], rl[4];                     // the same chunk, row-owner layout
+          if (has_res) {
+            plane_to_rows(stg, gh, lane, rh);
+            plane_to_rows(stg, gl, lane, rl);
+            if (c + 1 < CH) {                     // fetch the next chunk under this one's math
+              load_plane_issue(rbh + (c + 1) * 32, p.ld_res, rows_valid, lane, gh);
+              load_plane_issue(rbl + (c + 1) * 32, p.ld_res, rows_valid, lane, gl);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
+          }
+          tmem_ld32(trow + c * 32, r);
+          const float* bch = s_bias + cb + c * 32;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
             const uint32_t ah[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
             const uint32_t al[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
             const float4 b0 = reinterpret_cast<const float4*>(bch)[2 * i], b1 = reinterpret_cast<const float4*>(bch)[2 * i + 1];
@@ -496,7 +501,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
               const int e = i * 8 + j * 2;
               float x0 = fmaf(__uint_as_float(r[e]), sc, bia[2 * j]) + (hf2.x + lf2.x);
               float x1 = fmaf(__uint_as_float(r[e + 1]), sc, bia[2 * j + 1]) + (hf2.y + lf2.y);
-              if (rv) { x0 += rv[cb + c * 16 + e]; x1 += rv[cb + c * 16 + e + 1]; }
+              if (rv) { x0 += rv[cb + c * 32 + e]; x1 += rv[cb + c * 32 + e + 1]; }
               const float d0 = x0 - shiftK, d1 = x1 - shiftK;
               s1 += d0 + d1;
               s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
@@ -504,34 +509,35 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
               r[e + 1] = __float_as_uint(x1);
             }
           }
-          tmem_st16(trow + c * 16, r);
+          tmem_st32(trow + c * 32, r);
         }
-        s_part[qj * 128 + row] = s1;
-        s_part[512 + qj * 128 + row] = s2;
+        s_part[hf * 128 + row] = s1;
+        s_part[256 + hf * 128 + row] = s2;
         epi_bar_sync();
-        const float e1 = ((s_part[row] + s_part[128 + row]) + (s_part[256 + row] + s_part[384 + row])) * (1.0f / BN);
-        const float e2 = ((s_part[512 + row] + s_part[640 + row]) + (s_part[768 + row] + s_part[896 + row])) * (1.0f / BN);
+        const float e1 = (s_part[row] + s_part[128 + row]) * (1.0f / BN);
+        const float e2 = (s_part[256 + row] + s_part[256 + 128 + row]) * (1.0f / BN);
         const float mean = shiftK + e1;
         const float rstd = rsqrtf(fmaxf(e2 - e1 * e1, 0.0f) + 1e-5f);
 #pragma unroll 1
-        for (int c = 0; c < QC / 16; ++c) {
-          tmem_ld16(trow + c * 16, r);
-          float v[16];
-          const float4* g4 = reinterpret_cast<const float4*>(s_gamma + cb + c * 16);
-          const float4* e4 = reinterpret_cast<const float4*>(s_beta + cb + c * 16);
+        for (int c = 0; c < CH; ++c) {
+          tmem_ld32(trow + c * 32, r);
+          {
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + cb + c * 32);
+            const float4* e4 = reinterpret_cast<const float4*>(s_beta + cb + c * 32);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 gg = g4[i], bb = e4[i];
-            v[4 * i + 0] = fmaf((__uint_as_float(r[4 * i + 0]) - mean) * rstd, gg.x, bb.x);
-            v[4 * i + 1] = fmaf((__uint_as_float(r[4 * i + 1]) - mean) * rstd, gg.y, bb.y);
-            v[4 * i + 2] = fmaf((__uint_as_float(r[4 * i + 2]) - mean) * rstd, gg.z, bb.z);
-            v[4 * i + 3] = fmaf((__uint_as_float(r[4 * i + 3]) - mean) * rstd, gg.w, bb.w);
+            for (int i = 0; i < 8; ++i) {
+              const float4 gg = g4[i], bb = e4[i];
+              v[4 * i + 0] = fmaf((__uint_as_float(r[4 * i + 0]) - mean) * rstd, gg.x, bb.x);
+              v[4 * i + 1] = fmaf((__uint_as_float(r[4 * i + 1]) - mean) * rstd, gg.y, bb.y);
+              v[4 * i + 2] = fmaf((__uint_as_float(r[4 * i + 2]) - mean) * rstd, gg.z, bb.z);
+              v[4 * i + 3] = fmaf((__uint_as_float(r[4 * i + 3]) - mean) * rstd, gg.w, bb.w);
+            }
           }
-          uint32_t ph[8], pl[8];
-          pack_split16(v, ph, pl);
-          const int64_t o = (int64_t)wrow0 * p.ld_out + cb + c * 16;
-          store_half_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
-          store_half_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
+          uint32_t ph[16], pl[16];
+          pack_split(v, ph, pl);
+          const int64_t o = (int64_t)wrow0 * p.ld_out + cb + c * 32;
+          store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
+          store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
         }
         // the partial sums of this tile may be overwritten only after everyone has read them
         epi_bar_sync();
@@ -580,11 +586,9 @@ TcCtx* tc_create(int device) {
   c->encode = (PFN_tmapEncodeTiled)fn;
   if (const char* e = getenv("MLDB_TC_DBG")) c->dbg = atoi(e);
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-  e = cudaFuncSetAttribute(k_gemm_tc<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::SMEM_BYTES);
+  e = cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::SMEM_BYTES);
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_gemm_tc<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_gemm_tc<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::SMEM_BYTES);
+    e = cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::SMEM_BYTES);
   if (e != cudaSuccess) {
     mldb_set_err(std::string("cudaFuncSetAttribute(k_gemm_tc): ") + cudaGetErrorString(e));
     delete c;
@@ -646,10 +650,11 @@ void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   p.inv_scale = g.w.inv_scale; p.bias = g.w.bias; p.addtab = g.addtab; p.act = g.act;
   p.in_group = g.in_group; p.out_group = g.out_group; p.out_off = g.out_off; p.zero_lengths = g.zero_lengths;
   if (ln) {
+    p.ln = 1;
     p.out_hi = ln->out.hi; p.out_lo = ln->out.lo(); p.ld_out = ln->out.cols; p.out_col0 = 0;
     p.res_hi = ln->res.hi; p.res_lo = ln->res.hi ? ln->res.lo() : nullptr; p.ld_res = ln->res.cols;
     p.rowvec = ln->rowvec; p.rv_group = ln->rv_group > 0 ? ln->rv_group : 1;
-    p.gamma = ln->gamma; p.beta = ln->beta;
+    p.gamma = ln->gamma; p.beta = ln->beta; p.gamma2 = ln->gamma2; p.beta2 = ln->beta2;
   } else {
     p.out_hi = g.out.hi; p.out_lo = g.out.hi ? g.out.lo() : nullptr; p.ld_out = g.out.cols; p.out_col0 = g.out_col0;
     p.out_f32 = g.out_f32; p.ldc = g.ldc;
@@ -659,10 +664,8 @@ void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   p.n_tiles = (g.w.N + bn - 1) / bn;
   const int ntiles = p.m_tiles * p.n_tiles;
   dim3 grid(ntiles < c->sm_count ? ntiles : c->sm_count);
-  if (ln)
-    k_gemm_tc<256, true><<<grid, NUM_THREADS, TileCfg<256>::SMEM_BYTES, st>>>(mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
-  else if (bn == 256)
-    k_gemm_tc<256, false><<<grid, NUM_THREADS, TileCfg<256>::SMEM_BYTES, st>>>(mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
+  if (bn == 256)
+    k_gemm_tc<256><<<grid, NUM_THREADS, TileCfg<256>::SMEM_BYTES, st>>>(mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
   else
-    k_gemm_tc<128, false><<<grid, NUM_THREADS, TileCfg<128>::SMEM_BYTES, st>>>(mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
+    k_gemm_tc<128><<<grid, NUM_THREADS, TileCfg<128>::SMEM_BYTES, st>>>(mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
 }

@@ -31,6 +31,9 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) {
   __half2 h = __halves2half2(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -55,34 +58,37 @@ __global__ void __launch_bounds__(AW_MAX * 32) k_attn_mma(const AttnArgs a) {
   __half* Vl = Vh + (size_t)LkP * PITCH;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nthreads = blockDim.x, AW = blockDim.x >> 5;
+  pdl_trigger();
+  pdl_wait();
 
-  // ---- stage the head slices (16-byte vectors; rows beyond L are zero)
-  constexpr int VPR = HD / 8;                // uint4 per row
-  for (int i = tid; i < LqP * VPR; i += nthreads) {
-    const int r = i / VPR, c = i - r * VPR;
-    uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
-    if (r < Lq) {
-      const int64_t o = ((int64_t)s * Lq + r) * a.q.cols + a.q_col0 + h * HD + c * 8;
-      vh = *reinterpret_cast<const uint4*>(a.q.hi + o);
-      vl = *reinterpret_cast<const uint4*>(a.q.lo() + o);
+  // ---- stage the head slices with cp.async (16-byte LDGSTS, no register staging): every copy of
+  // the CTA is in flight at once, so the whole 46-69 KB working set costs about one L2 round trip.
+  // Rows beyond L are zero-filled (src-size 0).
+  constexpr int VPR = HD / 8;                // 16-byte vectors per row
+  {
+    const uint32_t sQh = (uint32_t)__cvta_generic_to_shared(Qh), sQl = (uint32_t)__cvta_generic_to_shared(Ql);
+    for (int i = tid; i < LqP * VPR; i += nthreads) {
+      const int r = i / VPR, c = i - r * VPR;
+      const int rc = r < Lq ? r : Lq - 1;
+      const int64_t o = ((int64_t)s * Lq + rc) * a.q.cols + a.q_col0 + h * HD + c * 8;
+      const uint32_t so = (uint32_t)(r * PITCH + c * 8) * 2, nb = r < Lq ? 16u : 0u;
+      cp_async16(sQh + so, a.q.hi + o, nb);
+      cp_async16(sQl + so, a.q.lo() + o, nb);
     }
-    *reinterpret_cast<uint4*>(Qh + (size_t)r * PITCH + c * 8) = vh;
-    *reinterpret_cast<uint4*>(Ql + (size_t)r * PITCH + c * 8) = vl;
-  }
-  for (int i = tid; i < LkP * VPR; i += nthreads) {
-    const int r = i / VPR, c = i - r * VPR;
-    uint4 kh = make_uint4(0, 0, 0, 0), kl = kh, vh = kh, vl = kh;
-    if (r < Lk) {
-      const int64_t base = ((int64_t)s * Lk + r) * a.kv.cols + h * HD + c * 8;
-      kh = *reinterpret_cast<const uint4*>(a.kv.hi + base + a.k_col0);
-      kl = *reinterpret_cast<const uint4*>(a.kv.lo() + base + a.k_col0);
-      vh = *reinterpret_cast<const uint4*>(a.kv.hi + base + a.v_col0);
-      vl = *reinterpret_cast<const uint4*>(a.kv.lo() + base + a.v_col0);
+    const uint32_t sKh = (uint32_t)__cvta_generic_to_shared(Kh), sKl = (uint32_t)__cvta_generic_to_shared(Kl);
+    const uint32_t sVh = (uint32_t)__cvta_generic_to_shared(Vh), sVl = (uint32_t)__cvta_generic_to_shared(Vl);
+    for (int i = tid; i < LkP * VPR; i += nthreads) {
+      const int r = i / VPR, c = i - r * VPR;
+      const int rc = r < Lk ? r : Lk - 1;
+      const int64_t base = ((int64_t)s * Lk + rc) * a.kv.cols + h * HD + c * 8;
+      const uint32_t so = (uint32_t)(r * PITCH + c * 8) * 2, nb = r < Lk ? 16u : 0u;
+      cp_async16(sKh + so, a.kv.hi + base + a.k_col0, nb);
+      cp_async16(sKl + so, a.kv.lo() + base + a.k_col0, nb);
+      cp_async16(sVh + so, a.kv.hi + base + a.v_col0, nb);
+      cp_async16(sVl + so, a.kv.lo() + base + a.v_col0, nb);
     }
-    *reinterpret_cast<uint4*>(Kh + (size_t)r * PITCH + c * 8) = kh;
-    *reinterpret_cast<uint4*>(Kl + (size_t)r * PITCH + c * 8) = kl;
-    *reinterpret_cast<uint4*>(Vh + (size_t)r * PITCH + c * 8) = vh;
-    *reinterpret_cast<uint4*>(Vl + (size_t)r * PITCH + c * 8) = vl;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
 
@@ -251,6 +257,6 @@ void mma_attention_init() {
 void mma_attention(const AttnArgs& a, cudaStream_t st) {
   const int qtiles = (a.Lq + 15) / 16;
   const int nw = qtiles < AW_MAX ? qtiles : AW_MAX;     // L = 79 -> 5 warps, one tile each
-  if (a.hd == 64) k_attn_mma<64><<<a.nseq * a.heads, nw * 32, attn_smem<64>(a), st>>>(a);
-  else k_attn_mma<128><<<a.nseq * a.heads, nw * 32, attn_smem<128>(a), st>>>(a);
+  if (a.hd == 64) launch_pdl(k_attn_mma<64>, dim3(a.nseq * a.heads), dim3(nw * 32), attn_smem<64>(a), st, a);
+  else launch_pdl(k_attn_mma<128>, dim3(a.nseq * a.heads), dim3(nw * 32), attn_smem<128>(a), st, a);
 }

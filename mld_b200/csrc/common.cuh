@@ -49,6 +49,27 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization
+// attribute may begin (prologue: barrier init, TMEM alloc, weight staging) while its predecessor
+// drains; it must execute pdl_wait() before touching anything the predecessor produced or reads.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+#ifdef __CUDACC__
+extern int g_mldb_pdl;   // 1 = launch the step-loop kernels with the PDL attribute (MLDB_PDL=0 disables)
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_mldb_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 enum ActKind { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2, ACT_SILU = 3 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {

@@ -830,8 +830,8 @@ static void denoiser_pass(mldb_handle* h, Plan* p, const float* latents, int lat
                           float* eps_out, cudaStream_t st) {
   const mldb_config& c = h->cfg;
   const int d = c.latent_dim;
-  k_assemble_tokens<<<nblk((int64_t)p->Bx * (c.n_lat + 1) * d), 256, 0, st>>>(
-      p->ws.x0, p->Ntok, p->Bx, lat_mod, c.n_lat, d, latents, h->query_pe, tt);
+  launch_pdl(k_assemble_tokens, dim3(nblk((int64_t)p->Bx * (c.n_lat + 1) * d)), dim3(256), 0, st,
+             p->ws.x0, p->Ntok, p->Bx, lat_mod, c.n_lat, d, latents, (const float*)h->query_pe, tt);
   count_launch(h);
   SeqInfo si;
   // Sequences are independent, so the stack runs over chunks of `chunk_seqs` sequences that reuse
@@ -1030,8 +1030,9 @@ static int run_reverse(mldb_handle* h, const void* cond, const float* init_noise
   TRY(run_graphed(h, p, st, [&](cudaStream_t s) {
     for (int i = 0; i < nsteps; ++i) {                                           // mld.py:323
       denoiser_pass(h, p, p->latents, B, h->d_tt + (size_t)i * d, p->eps, s);
-      k_cfg_sched<<<nblk(B * per), 256, 0, s>>>(p->eps, p->latents, nullptr, B * per, cfg_on ? 1 : 0,
-                                               c.guidance_scale, h->d_coefs, i);
+      launch_pdl(k_cfg_sched, dim3(nblk(B * per)), dim3(256), 0, s, (const float*)p->eps, p->latents,
+                 (const float*)nullptr, (int64_t)(B * per), cfg_on ? 1 : 0, c.guidance_scale,
+                 (const StepCoef*)h->d_coefs, i);
       count_launch(h);
     }
   }));

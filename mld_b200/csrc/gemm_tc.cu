@@ -299,10 +299,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     if (p.ln)
       for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) { s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
   }
+  pdl_trigger();               // let the next kernel's prologue overlap our tail
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                  // everything below touches activations of the previous kernel
 
   if (warp == 0) {
     if (lane == 0) {
@@ -665,7 +667,7 @@ void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   const int ntiles = p.m_tiles * p.n_tiles;
   dim3 grid(ntiles < c->sm_count ? ntiles : c->sm_count);
   if (bn == 256)
-    k_gemm_tc<256><<<grid, NUM_THREADS, TileCfg<256>::SMEM_BYTES, st>>>(mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
+    launch_pdl(k_gemm_tc<256>, grid, dim3(NUM_THREADS), TileCfg<256>::SMEM_BYTES, st, mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
   else
-    k_gemm_tc<128><<<grid, NUM_THREADS, TileCfg<128>::SMEM_BYTES, st>>>(mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
+    launch_pdl(k_gemm_tc<128>, grid, dim3(NUM_THREADS), TileCfg<128>::SMEM_BYTES, st, mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
 }

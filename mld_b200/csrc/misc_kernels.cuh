@@ -28,6 +28,8 @@ __global__ void k_timestep_features(const int64_t* __restrict__ ts, int64_t t_sc
 __global__ void k_assemble_tokens(ActBuf X, int Ntok, int Bx, int lat_mod, int n_lat, int d,
                                   const float* __restrict__ latents, const float* __restrict__ pe,
                                   const float* __restrict__ tt) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)Bx * (n_lat + 1) * d;
   if (idx >= total) return;
@@ -101,6 +103,8 @@ __device__ __forceinline__ float sched_update(const StepCoef& k, float x, float 
 __global__ void k_cfg_sched(const float* __restrict__ eps, float* __restrict__ latents,
                             const float* __restrict__ noise, int64_t n_per_half, int cfg_on,
                             float guidance, const StepCoef* __restrict__ coefs, int step) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_per_half) return;
   float e = eps[i];

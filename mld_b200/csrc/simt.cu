@@ -3,6 +3,8 @@
 // shapes do not fit a tensor-core tile (odd K such as 263/150 motion features, tiny M).
 #include "ops.cuh"
 
+#include <stdlib.h>
+
 // ------------------------------------------------------------------------------------ GEMM
 namespace {
 
@@ -98,6 +100,8 @@ __global__ void __launch_bounds__(256) k_gemm_simt(const GemmArgs a) {
 // ------------------------------------------------------------------------------- LayerNorm
 template <int VPL>
 __global__ void __launch_bounds__(256) k_ln(const LnArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= a.M) return;
   const int r = warp;
@@ -252,16 +256,19 @@ void simt_gemm(const GemmArgs& a, cudaStream_t st) {
 void simt_ln(const LnArgs& a, cudaStream_t st) {
   const int rows_per_block = 8;
   dim3 grid((a.M + rows_per_block - 1) / rows_per_block);
-  if (a.d <= 256) k_ln<8><<<grid, 256, 0, st>>>(a);
-  else if (a.d <= 512) k_ln<16><<<grid, 256, 0, st>>>(a);
-  else k_ln<32><<<grid, 256, 0, st>>>(a);
+  if (a.d <= 256) launch_pdl(k_ln<8>, grid, dim3(256), 0, st, a);
+  else if (a.d <= 512) launch_pdl(k_ln<16>, grid, dim3(256), 0, st, a);
+  else launch_pdl(k_ln<32>, grid, dim3(256), 0, st, a);
 }
 
 size_t simt_attention_smem(const AttnArgs& a) {
   return ((size_t)a.Lk * (2 * a.hd + 1) + (size_t)ATT_WARPS * (a.hd + a.Lk)) * sizeof(float);
 }
 
+int g_mldb_pdl = 1;
+
 void simt_init() {
+  if (const char* e = getenv("MLDB_PDL")) g_mldb_pdl = atoi(e) != 0;
   // opt in to the full 227 KB once (not during stream capture)
   cudaFuncSetAttribute(k_attn_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }

@@ -245,6 +245,12 @@ static int pack_skip_stack(mldb_handle* h, const std::string& p, int d, int ff, 
     if (dec) { s->dec.emplace_back(); TRY(pack_dec_layer(h, n, d, &s->dec.back())); }
     else     { s->enc.emplace_back(); TRY(pack_enc_layer(h, n, d, &s->enc.back())); }
   }
+  if (!dec) {   // the last block only has to produce the first few tokens of every sequence
+    const std::string& n = names.back();
+    EncW& w = s->enc.back();
+    TRY(pack_named(h, n + "self_attn.in_proj_weight", n + "self_attn.in_proj_bias", &w.q_only, 0, d));
+    TRY(pack_named(h, n + "self_attn.in_proj_weight", n + "self_attn.in_proj_bias", &w.kv_only, d, 2 * d));
+  }
   for (int i = 0; i < nb; ++i) {
     s->skip.emplace_back();
     const std::string lp = p + "linear_blocks." + std::to_string(i) + ".";
@@ -320,6 +326,8 @@ static StepCoef make_coef(const mldb_handle* h, int64_t t, int n_inference) {
   return k;
 }
 
+static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
 // ----------------------------------------------------------------------------- op dispatch
 static void op_gemm(mldb_handle* h, const GemmArgs& g, cudaStream_t st) {
   if (h->use_tc && tc_gemm_supported(h->tc, g)) tc_gemm(h->tc, g, nullptr, st);
@@ -355,7 +363,8 @@ static int alloc_act(mldb_handle* h, int rows, int cols, ActBuf* out) {
   out->hi = p; out->plane_stride = rp * cols; out->rows = rows; out->cols = cols;
   return MLDB_OK;
 }
-static int alloc_stack_ws(mldb_handle* h, const StackW& sw, int nseq, int L, int Lmem, StackWs* ws) {
+static int alloc_stack_ws(mldb_handle* h, const StackW& sw, int nseq, int L, int Lmem, StackWs* ws,
+                          int n_sel = 0) {
   ws->nseq = nseq; ws->L = L; ws->M = nseq * L; ws->d = sw.d; ws->ff = sw.ff; ws->Lmem = Lmem;
   const int M = ws->M, d = sw.d;
   TRY(alloc_act(h, M, d, &ws->x0));
@@ -377,6 +386,16 @@ static int alloc_stack_ws(mldb_handle* h, const StackW& sw, int nseq, int L, int
     for (int i = 0; i < nb; ++i) TRY(alloc_act(h, M, d, &ws->ys[i]));
   }
   TRY(dev_alloc(h, (void**)&ws->cf32, (size_t)M * d * sizeof(float)));
+  if (sw.kind == STACK_SKIP_ENC && n_sel > 0) {
+    ws->n_sel = n_sel;
+    const int R = nseq * n_sel;
+    TRY(alloc_act(h, R, d, &ws->sx));
+    TRY(alloc_act(h, R, d, &ws->sq));
+    TRY(alloc_act(h, R, d, &ws->satt));
+    TRY(alloc_act(h, R, d, &ws->sx1));
+    TRY(alloc_act(h, R, sw.ff, &ws->sh));
+    TRY(alloc_act(h, R, d, &ws->sout));
+  }
   return MLDB_OK;
 }
 
@@ -437,6 +456,50 @@ static void any_layer(mldb_handle* h, const StackW& sw, int li, ActBuf xin, ActB
   if (sw.kind == STACK_SKIP_ENC) enc_layer(h, sw, sw.enc[li], xin, xout, ws, si, st);
   else dec_layer(h, sw, sw.dec[li], xin, xout, mem, ws, si, st);
 }
+// rows (s, j < n_sel) of a [nseq, L] token buffer -> compact [nseq * n_sel] rows
+__global__ void k_gather_rows(ActBuf src, ActBuf dst, int L, int n_sel, int nrows_out, int d) {
+  pdl_trigger();
+  pdl_wait();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)nrows_out * (d / 8)) return;
+  const int c = (int)(idx % (d / 8));
+  const int r = (int)(idx / (d / 8));
+  const int64_t srow = (int64_t)(r / n_sel) * L + r % n_sel;
+  const uint4* sh = reinterpret_cast<const uint4*>(src.hi + srow * src.cols) + c;
+  const uint4* sl = reinterpret_cast<const uint4*>(src.lo() + srow * src.cols) + c;
+  reinterpret_cast<uint4*>(dst.hi + (int64_t)r * dst.cols)[c] = *sh;
+  reinterpret_cast<uint4*>(dst.lo() + (int64_t)r * dst.cols)[c] = *sl;
+}
+
+// Last block of a skip encoder when only the first n_sel tokens of every sequence are consumed
+// downstream (the denoiser returns tokens[:n_lat], mld_denoiser.py:206; MldVae.encode keeps the
+// distribution tokens, mld_vae.py:161).  Keys and values still come from every token, but queries,
+// the out-projection, both LayerNorms and the whole FFN run on the selected rows only - exactly
+// the rows the full layer would have produced, since everything after attention is per-token.
+static ActBuf enc_layer_selected(mldb_handle* h, const StackW& sw, const EncW& w, ActBuf xin, StackWs& ws,
+                                 const SeqInfo& si, cudaStream_t st) {
+  const int d = ws.d, R = ws.nseq * ws.n_sel;
+  GemmArgs gk; gk.a1 = xin; gk.K1 = d; gk.M = ws.M; gk.w = w.kv_only; gk.out = ws.qkv;   // K | V in cols [0, 2d)
+  op_gemm(h, gk, st);
+  launch_pdl(k_gather_rows, dim3(nblk((int64_t)R * (d / 8))), dim3(256), 0, st, xin, ws.sx, ws.L, ws.n_sel, R, d);
+  count_launch(h);
+  GemmArgs gq; gq.a1 = ws.sx; gq.K1 = d; gq.M = R; gq.w = w.q_only; gq.out = ws.sq;
+  op_gemm(h, gq, st);
+  AttnArgs a; a.q = ws.sq; a.q_col0 = 0; a.Lq = ws.n_sel; a.kv = ws.qkv; a.k_col0 = 0; a.v_col0 = d;
+  a.Lk = ws.L; a.nseq = ws.nseq; a.heads = sw.heads; a.hd = d / sw.heads; a.lengths = si.lengths;
+  a.kv_prefix = si.kv_prefix; a.len_mod = si.len_mod; a.out = ws.satt;
+  op_attn(h, a, st);
+  GemmArgs go; go.a1 = ws.satt; go.K1 = d; go.M = R; go.w = w.out_proj;
+  LnArgs l1; l1.res = ws.sx; l1.gamma = w.n1.g; l1.beta = w.n1.b; l1.M = R; l1.d = d; l1.out = ws.sx1;
+  op_gemm_ln(h, go, l1, ws.cf32, st);
+  GemmArgs g1; g1.a1 = ws.sx1; g1.K1 = d; g1.M = R; g1.w = w.l1; g1.act = ACT_GELU; g1.out = ws.sh;
+  op_gemm(h, g1, st);
+  GemmArgs g2; g2.a1 = ws.sh; g2.K1 = ws.ff; g2.M = R; g2.w = w.l2;
+  LnArgs l2; l2.res = ws.sx1; l2.gamma = w.n2.g; l2.beta = w.n2.b; l2.M = R; l2.d = d; l2.out = ws.sout;
+  op_gemm_ln(h, g2, l2, ws.cf32, st);
+  return ws.sout;
+}
+
 // SkipTransformerEncoder/Decoder.forward (cross_attention.py:41-64, 89-125) and the plain
 // decoder stacks (cross_attention.py:204-233; torch nn.TransformerDecoder for ActorVae).
 // Returns the buffer holding the last layer's output (before the stack's final norm).
@@ -462,6 +525,8 @@ static ActBuf run_stack(mldb_handle* h, const StackW& sw, ActBuf x0, ActBuf mem,
     GemmArgs g; g.a1 = x; g.K1 = sw.d; g.a2 = ws.ys[nb - 1 - i]; g.K2 = sw.d; g.M = ws.M;
     g.w = sw.skip[i]; g.out = ws.cat;
     op_gemm(h, g, st);
+    if (i == nb - 1 && sw.kind == STACK_SKIP_ENC && ws.n_sel > 0)
+      return enc_layer_selected(h, sw, sw.enc[nb + 1 + i], ws.cat, ws, si, st);   // compact rows
     any_layer(h, sw, nb + 1 + i, ws.cat, ws.cur[(i + 1) & 1], mem, ws, si, st);
     x = ws.cur[(i + 1) & 1];
   }
@@ -753,7 +818,6 @@ static int run_graphed(mldb_handle* h, Plan* p, cudaStream_t st, F record) {
   return MLDB_OK;
 }
 
-static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
 // ----------------------------------------------------------------------------- denoiser (trans_enc)
 // Gather + place the action tokens (EmbedAction.forward, mld_denoiser.py:250-262): rows of the
@@ -787,7 +851,7 @@ static int enc_plan(mldb_handle* h, int kind, int B, int Bx, int S, Plan** out) 
     const int Sc = c.cond_kind == MLDB_COND_TEXT ? S : 1;
     p->Ntok = c.n_lat + 1 + Sc;
     if (p->Ntok > 500) FAIL(MLDB_ERR_INVALID, "sequence of %d tokens exceeds the learned PE table (500)", p->Ntok);
-    TRY(alloc_stack_ws(h, h->den, Bx, p->Ntok, 0, &p->ws));
+    TRY(alloc_stack_ws(h, h->den, Bx, p->Ntok, 0, &p->ws, h->den.layers >= 3 ? c.n_lat : 0));
     const size_t per = (size_t)c.n_lat * c.latent_dim;
     TRY(dev_alloc(h, (void**)&p->latents, (size_t)B * per * sizeof(float)));
     TRY(dev_alloc(h, (void**)&p->eps, (size_t)Bx * per * sizeof(float)));
@@ -848,7 +912,8 @@ static void denoiser_pass(mldb_handle* h, Plan* p, const float* latents, int lat
     ActBuf x = run_stack(h, h->den, x0v, ActBuf{}, w, si, st);
     // encoder.norm on the latent tokens only (cross_attention.py:62-63, mld_denoiser.py:206)
     LnArgs l; l.res = x; l.gamma = h->den.norm.g; l.beta = h->den.norm.b; l.M = n * c.n_lat; l.d = d;
-    l.sel_group = c.n_lat; l.in_group = p->Ntok; l.out_f32 = eps_out + (size_t)s0 * c.n_lat * d; l.ld_out = d;
+    if (w.n_sel == 0) { l.sel_group = c.n_lat; l.in_group = p->Ntok; }   // else x is already compact
+    l.out_f32 = eps_out + (size_t)s0 * c.n_lat * d; l.ld_out = d;
     op_ln(h, l, st);
   }
 }
@@ -1154,7 +1219,7 @@ extern "C" int mldb_vae_encode(mldb_handle* h, const float* feats, const int32_t
   Plan* p = find_plan(h, 2, B, 0, T);
   if (!p) {
     p = add_plan(h, 2, B, 0, T);
-    TRY(alloc_stack_ws(h, h->venc, B, L, 0, &p->ws));
+    TRY(alloc_stack_ws(h, h->venc, B, L, 0, &p->ws, h->venc.layers >= 3 ? G : 0));
     TRY(dev_alloc(h, (void**)&p->lengths, (size_t)B * sizeof(int32_t)));
     TRY(dev_alloc(h, (void**)&p->stage_f32, (size_t)B * G * d * sizeof(float)));
   }
@@ -1169,7 +1234,8 @@ extern "C" int mldb_vae_encode(mldb_handle* h, const float* feats, const int32_t
   SeqInfo si; si.lengths = p->lengths; si.kv_prefix = G;
   ActBuf x = run_stack(h, h->venc, p->ws.x0, ActBuf{}, p->ws, si, st);
   LnArgs l; l.res = x; l.gamma = h->venc.norm.g; l.beta = h->venc.norm.b; l.M = B * G; l.d = d;
-  l.sel_group = G; l.in_group = L; l.out_f32 = p->stage_f32; l.ld_out = d;
+  if (p->ws.n_sel == 0) { l.sel_group = G; l.in_group = L; }
+  l.out_f32 = p->stage_f32; l.ld_out = d;
   op_ln(h, l, st);
   k_rows_out_permuted<<<nblk((int64_t)B * G * d), 256, 0, st>>>(p->stage_f32, mu, logvar, B, c.n_lat, d);
   count_launch(h);

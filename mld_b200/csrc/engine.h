@@ -16,6 +16,7 @@ struct LnW { float* g = nullptr; float* b = nullptr; };
 struct EncW {  // TransformerEncoderLayer (cross_attention.py:236-257)
   LinW in_proj, out_proj, l1, l2;
   LnW n1, n2;
+  LinW q_only, kv_only;   // row slices [0:d) / [d:3d) of in_proj, packed for the stack's last layer
 };
 struct DecW {  // TransformerDecoderLayer (cross_attention.py:297-321)
   LinW sa_in, sa_out, ca_q, ca_kv, ca_out, l1, l2;
@@ -41,6 +42,9 @@ struct RawTensor {
 struct StackWs {
   int nseq = 0, L = 0, M = 0, d = 0, ff = 0, Lmem = 0;
   ActBuf x0, cur[2], x1, x2, att, qkv, qc, kvm, h, cat;
+  // compact buffers for the trimmed last layer (rows = nseq * n_sel)
+  int n_sel = 0;
+  ActBuf sx, sq, satt, sx1, sh, sout;
   std::vector<ActBuf> ys;
   float* cf32 = nullptr;  // [M, d] GEMM result staging for the unfused (SIMT) LN path
 };

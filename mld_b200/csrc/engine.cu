@@ -224,6 +224,7 @@ static int pack_dec_layer(mldb_handle* h, const std::string& p, int d, DecW* w) 
   // packed in_proj rows are [Wq; Wk; Wv] (nn.MultiheadAttention): q part and kv part
   TRY(pack_named(h, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", &w->ca_q, 0, d));
   TRY(pack_named(h, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", &w->ca_kv, d, 2 * d));
+  TRY(pack_named(h, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", &w->ca_v, 2 * d, d));
   TRY(pack_named(h, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", &w->ca_out));
   TRY(pack_named(h, p + "linear1.weight", p + "linear1.bias", &w->l1));
   TRY(pack_named(h, p + "linear2.weight", p + "linear2.bias", &w->l2));
@@ -378,6 +379,8 @@ static int alloc_stack_ws(mldb_handle* h, const StackW& sw, int nseq, int L, int
     TRY(alloc_act(h, M, d, &ws->x2));
     TRY(alloc_act(h, M, d, &ws->qc));
     TRY(alloc_act(h, nseq * Lmem, 2 * d, &ws->kvm));
+    TRY(alloc_act(h, nseq, d, &ws->vrow));
+    TRY(dev_alloc(h, (void**)&ws->cvec, (size_t)nseq * d * sizeof(float)));
   }
   if (sw.kind != STACK_PLAIN_DEC) {
     TRY(alloc_act(h, M, d, &ws->cat));
@@ -438,6 +441,20 @@ static void dec_layer(mldb_handle* h, const StackW& sw, const DecW& w, ActBuf xi
                       ActBuf mem, StackWs& ws, const SeqInfo& si, cudaStream_t st) {
   const int d = ws.d;
   self_attn_block(h, w.sa_in, w.sa_out, w.n1, xin, ws.x1, ws, si, sw.heads, st);
+  if (ws.Lmem == 1) {
+    // One memory token: softmax over a single key is exactly 1, so the cross-attention output of
+    // every query row of sequence b is out_proj(W_v z_b + b_v) + b_o - a per-sequence vector added
+    // before norm2 (no q projection, no attention kernel, no [M,d] out-projection).
+    GemmArgs gv; gv.a1 = mem; gv.K1 = d; gv.M = ws.nseq; gv.w = w.ca_v; gv.out = ws.vrow;
+    op_gemm(h, gv, st);
+    GemmArgs gc; gc.a1 = ws.vrow; gc.K1 = d; gc.M = ws.nseq; gc.w = w.ca_out; gc.out_f32 = ws.cvec; gc.ldc = d;
+    op_gemm(h, gc, st);
+    LnArgs lc; lc.res = ws.x1; lc.rowvec = ws.cvec; lc.rv_group = ws.L; lc.gamma = w.n2.g; lc.beta = w.n2.b;
+    lc.M = ws.M; lc.d = d; lc.out = ws.x2;
+    op_ln(h, lc, st);
+    ffn_block(h, w.l1, w.l2, w.n3, ws.x2, xout, ws, ACT_GELU, st);
+    return;
+  }
   // cross attention: query = tgt, key = value = memory, no memory mask
   GemmArgs gq; gq.a1 = ws.x1; gq.K1 = d; gq.M = ws.M; gq.w = w.ca_q; gq.out = ws.qc;
   op_gemm(h, gq, st);
@@ -856,6 +873,8 @@ static int enc_plan(mldb_handle* h, int kind, int B, int Bx, int S, Plan** out) 
     TRY(dev_alloc(h, (void**)&p->latents, (size_t)B * per * sizeof(float)));
     TRY(dev_alloc(h, (void**)&p->eps, (size_t)Bx * per * sizeof(float)));
     TRY(dev_alloc(h, (void**)&p->tt_single, (size_t)3 * std::max(c.text_dim, c.latent_dim) * sizeof(float) + 64));
+    if (c.cond_kind == MLDB_COND_TEXT && c.text_dim != c.latent_dim)
+      TRY(alloc_act(h, Bx * S, c.text_dim, &p->ctx_split));
   }
   *out = p;
   return MLDB_OK;
@@ -869,9 +888,18 @@ static int place_condition(mldb_handle* h, Plan* p, const void* cond, cudaStream
   if (c.cond_kind == MLDB_COND_TEXT) {
     const int S = p->S;
     if (c.text_dim != d) {
-      GemmArgs g; g.a_kind = A_F32_RELU; g.a_f32 = (const float*)cond; g.lda = c.text_dim;
-      g.M = Bx * S; g.w = h->emb_proj; g.out = p->ws.x0;
+      // emb_proj = ReLU -> Linear (mld_denoiser.py:67-68): ReLU + hi/lo split in one pass over the
+      // CLIP context, then the tensor-core GEMM writes the tokens (+ PE) straight into X0
+      GemmArgs g; g.M = Bx * S; g.w = h->emb_proj; g.out = p->ws.x0;
       g.in_group = S; g.out_group = p->Ntok; g.out_off = c.n_lat + 1; g.addtab = h->query_pe;
+      if (h->use_tc && p->ctx_split.hi && c.text_dim % 64 == 0) {
+        k_rows_to_split<<<nblk((int64_t)Bx * S * c.text_dim), 256, 0, st>>>(p->ctx_split, (const float*)cond, c.text_dim,
+                                                                         Bx * S, c.text_dim, 1 << 30, 0, 0, 0, nullptr, 1);
+        count_launch(h);
+        g.a1 = p->ctx_split; g.K1 = c.text_dim;
+      } else {
+        g.a_kind = A_F32_RELU; g.a_f32 = (const float*)cond; g.lda = c.text_dim;
+      }
       op_gemm(h, g, st);
     } else {
       k_rows_to_split<<<nblk((int64_t)Bx * S * d), 256, 0, st>>>(p->ws.x0, (const float*)cond, d, Bx * S, d, S,

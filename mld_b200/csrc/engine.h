@@ -19,7 +19,7 @@ struct EncW {  // TransformerEncoderLayer (cross_attention.py:236-257)
   LinW q_only, kv_only;   // row slices [0:d) / [d:3d) of in_proj, packed for the stack's last layer
 };
 struct DecW {  // TransformerDecoderLayer (cross_attention.py:297-321)
-  LinW sa_in, sa_out, ca_q, ca_kv, ca_out, l1, l2;
+  LinW sa_in, sa_out, ca_q, ca_kv, ca_v, ca_out, l1, l2;   // ca_v: rows [2d,3d) for the 1-memory-token collapse
   LnW n1, n2, n3;
 };
 enum StackKind { STACK_SKIP_ENC = 0, STACK_SKIP_DEC = 1, STACK_PLAIN_DEC = 2 };
@@ -45,6 +45,9 @@ struct StackWs {
   // compact buffers for the trimmed last layer (rows = nseq * n_sel)
   int n_sel = 0;
   ActBuf sx, sq, satt, sx1, sh, sout;
+  // single-memory-token cross-attention collapse (per-sequence vectors)
+  ActBuf vrow;            // [nseq, d]  V projection of the memory token
+  float* cvec = nullptr;  // [nseq, d]  out_proj(V) + bias
   std::vector<ActBuf> ys;
   float* cf32 = nullptr;  // [M, d] GEMM result staging for the unfused (SIMT) LN path
 };
@@ -61,6 +64,7 @@ struct Plan {
   float* stage_f32 = nullptr; // misc fp32 staging
   float* tt_single = nullptr; // [d] time token for mldb_denoise
   float* feats = nullptr;     // [B, T, F] decode output staging for mldb_sample
+  ActBuf ctx_split;           // relu(ctx) in split16 form, A operand of the emb_proj GEMM
   float* cond_f = nullptr;    // staged condition (host entry point)
   size_t cond_cap = 0;
   int64_t* cond_i = nullptr;

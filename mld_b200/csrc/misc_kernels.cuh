@@ -51,7 +51,7 @@ __global__ void k_assemble_tokens(ActBuf X, int Ntok, int Bx, int lat_mod, int n
 // src_row(r) = r (src_bcast == 0) or r % in_group (broadcast one group to every sequence).
 __global__ void k_rows_to_split(ActBuf X, const float* __restrict__ src, int ld_src, int M, int d,
                                 int in_group, int out_group, int out_off, int src_bcast,
-                                const float* __restrict__ tab) {
+                                const float* __restrict__ tab, int relu = 0) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)M * d) return;
   const int n = (int)(idx % d);
@@ -59,6 +59,7 @@ __global__ void k_rows_to_split(ActBuf X, const float* __restrict__ src, int ld_
   const int seq = r / in_group, pos = r - seq * in_group;
   float v = 0.0f;
   if (src) v = src[(int64_t)(src_bcast ? pos : r) * ld_src + n];
+  if (relu) v = fmaxf(v, 0.0f);
   if (tab) v += tab[(int64_t)(out_off + pos) * d + n];
   __half h, l;
   split_f32(v, h, l);

@@ -566,6 +566,8 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
                                         CUtensorMapFloatOOBfill);
 
+static int g_force_bn = 0;   // MLDB_TC_BN=128: experiment knob (3-stage BN=128 tiles everywhere)
+
 struct TcCtx {
   int dbg = 0;
   int device = 0;
@@ -587,6 +589,7 @@ TcCtx* tc_create(int device) {
   }
   c->encode = (PFN_tmapEncodeTiled)fn;
   if (const char* e = getenv("MLDB_TC_DBG")) c->dbg = atoi(e);
+  if (const char* e = getenv("MLDB_TC_BN")) g_force_bn = atoi(e);
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   e = cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::SMEM_BYTES);
   if (e == cudaSuccess)
@@ -613,7 +616,7 @@ static bool make_map(const TcCtx* c, CUtensorMap* m, const __half* base, int row
   return r == CUDA_SUCCESS;
 }
 
-static int pick_bn(const GemmArgs& g) { return (g.w.N % 256 == 0) ? 256 : 128; }
+static int pick_bn(const GemmArgs& g) { return (g.w.N % 256 == 0 && g_force_bn != 128) ? 256 : 128; }
 
 bool tc_gemm_supported(const TcCtx* c, const GemmArgs& g) {
   if (!c || !c->ok) return false;

@@ -249,8 +249,16 @@ def main():
         dom = max(times, key=times.get)
         peak = peaks.get("bf16_tflops", 1590.0)
         achieved = ops[dom] / (times[dom] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                traffic = json.load(f).get(dom)
+        except Exception:
+            traffic = None
+        roof = {"bound": "tensor", "kernel": f"k_gemm_tc ({dom}: M={M}, {'N=1024,K=256' if dom == 'ffn1' else dom})",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src + " bf16 burst (MEASURED_PEAKS.json)" if peak_src == "measured" else peak_src,
+                "note": "achieved = algorithmic 2*M*N*K per launch / CUDA-event time; the split-fp16 scheme issues 3 "
+                        "tensor-core passes per algorithmic FLOP (tensor-pipe rate = 3x achieved)",
                 "op_ms": {k: round(v, 4) for k, v in times.items()}, "layer_ms": round(layer_ms, 4),
                 "path_tflops": FLOP_PER_MOTION * value / 1e12,
                 "path_frac_of_sustained": FLOP_PER_MOTION * value / 1e12 / peaks.get("bf16_tflops_sustained", 1400.0)}

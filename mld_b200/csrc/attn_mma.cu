@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(AW_MAX * 32) k_attn_mma(const AttnArgs a) {
   const int Lq = a.Lq, Lk = a.Lk;
   const int LqP = (Lq + 15) & ~15, LkP = (Lk + 15) & ~15;
   int nk = Lk;
-  if (a.lengths) nk = min(Lk, a.kv_prefix + a.lengths[a.len_mod > 0 ? s % a.len_mod : s]);
+  if (a.lengths) nk = min(Lk, a.kv_prefix + a.lengths[a.len_mod > 0 ? (a.seq0 + s) % a.len_mod : s]);
   __half* Qh = reinterpret_cast<__half*>(sm_raw);
   __half* Ql = Qh + (size_t)LqP * PITCH;
   __half* Kh = Ql + (size_t)LqP * PITCH;

@@ -408,27 +408,51 @@ struct SeqInfo {
   int len_mod = 0;
 };
 
+static inline ActBuf rows_of(ActBuf b, int64_t row0, int rows) {
+  b.hi += row0 * b.cols; b.rows = rows; return b;
+}
+// Producer -> consumer pairs whose intermediate is larger than L2 at full batch (qkv: 124 MB,
+// FFN hidden: 166 MB) run over row chunks that REUSE one chunk-sized intermediate buffer: the
+// consumer kernel then reads it from L2 and the dirty lines are overwritten in place by the next
+// chunk instead of being written back, which removes most of the path's HBM traffic.  Chunks are
+// sized in whole waves of GEMM tiles (sm_count x 128 rows) so no tile rounds are lost.
 static void self_attn_block(mldb_handle* h, const LinW& in_proj, const LinW& out_proj, const LnW& n,
                             ActBuf xin, ActBuf xout, StackWs& ws, const SeqInfo& si, int heads,
                             cudaStream_t st) {
   const int d = ws.d;
-  GemmArgs g; g.a1 = xin; g.K1 = d; g.M = ws.M; g.w = in_proj; g.out = ws.qkv;
-  op_gemm(h, g, st);
-  AttnArgs a; a.q = ws.qkv; a.q_col0 = 0; a.Lq = ws.L; a.kv = ws.qkv; a.k_col0 = d; a.v_col0 = 2 * d;
-  a.Lk = ws.L; a.nseq = ws.nseq; a.heads = heads; a.hd = d / heads; a.lengths = si.lengths;
-  a.kv_prefix = si.kv_prefix; a.len_mod = si.len_mod; a.out = ws.att;
-  op_attn(h, a, st);
+  int cseq = ws.nseq;
+  if (h->pair_chunk && h->use_tc) cseq = std::max(1, (h->sm_count * 128 - 127) / ws.L);   // <= one wave of m-tiles
+  for (int s0 = 0; s0 < ws.nseq; s0 += cseq) {
+    const int ns = std::min(cseq, ws.nseq - s0);
+    const int64_t r0 = (int64_t)s0 * ws.L;
+    const int rows = ns * ws.L;
+    ActBuf qkv = rows_of(ws.qkv, 0, rows);                 // the same rows for every chunk
+    GemmArgs g; g.a1 = rows_of(xin, r0, rows); g.K1 = d; g.M = rows; g.w = in_proj; g.out = qkv;
+    op_gemm(h, g, st);
+    AttnArgs a; a.q = qkv; a.q_col0 = 0; a.Lq = ws.L; a.kv = qkv; a.k_col0 = d; a.v_col0 = 2 * d;
+    a.Lk = ws.L; a.nseq = ns; a.heads = heads; a.hd = d / heads;
+    a.lengths = si.lengths ? si.lengths + (si.len_mod > 0 ? 0 : s0) : nullptr;
+    a.kv_prefix = si.kv_prefix; a.len_mod = si.len_mod; a.seq0 = s0; a.out = rows_of(ws.att, r0, rows);
+    op_attn(h, a, st);
+  }
   GemmArgs g2; g2.a1 = ws.att; g2.K1 = d; g2.M = ws.M; g2.w = out_proj;
   LnArgs l; l.res = xin; l.gamma = n.g; l.beta = n.b; l.M = ws.M; l.d = d; l.out = xout;
   op_gemm_ln(h, g2, l, ws.cf32, st);
 }
 static void ffn_block(mldb_handle* h, const LinW& l1, const LinW& l2, const LnW& n, ActBuf xin,
                       ActBuf xout, StackWs& ws, int act, cudaStream_t st) {
-  GemmArgs g; g.a1 = xin; g.K1 = ws.d; g.M = ws.M; g.w = l1; g.act = act; g.out = ws.h;
-  op_gemm(h, g, st);
-  GemmArgs g2; g2.a1 = ws.h; g2.K1 = ws.ff; g2.M = ws.M; g2.w = l2;
-  LnArgs l; l.res = xin; l.gamma = n.g; l.beta = n.b; l.M = ws.M; l.d = ws.d; l.out = xout;
-  op_gemm_ln(h, g2, l, ws.cf32, st);
+  int crow = ws.M;
+  if (h->pair_chunk && h->use_tc && ws.d == 256) crow = h->sm_count * 128;   // one wave of FFN2 tiles
+  for (int64_t r0 = 0; r0 < ws.M; r0 += crow) {
+    const int rows = (int)std::min<int64_t>(crow, ws.M - r0);
+    ActBuf hb = rows_of(ws.h, 0, rows);                    // the same rows for every chunk
+    GemmArgs g; g.a1 = rows_of(xin, r0, rows); g.K1 = ws.d; g.M = rows; g.w = l1; g.act = act; g.out = hb;
+    op_gemm(h, g, st);
+    GemmArgs g2; g2.a1 = hb; g2.K1 = ws.ff; g2.M = rows; g2.w = l2;
+    LnArgs l; l.res = rows_of(xin, r0, rows); l.gamma = n.g; l.beta = n.b; l.M = rows; l.d = ws.d;
+    l.out = rows_of(xout, r0, rows);
+    op_gemm_ln(h, g2, l, ws.cf32, st);
+  }
 }
 // TransformerEncoderLayer.forward_post (cross_attention.py:259-272)
 static void enc_layer(mldb_handle* h, const StackW& sw, const EncW& w, ActBuf xin, ActBuf xout,
@@ -579,6 +603,8 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   if (!h->tc) { delete h; return MLDB_ERR_CUDA; }
   const char* env = getenv("MLDB_GEMM");
   if (env && !strcmp(env, "simt")) h->use_tc = false;
+  env = getenv("MLDB_PAIR_CHUNK");
+  if (env) h->pair_chunk = atoi(env) != 0;
   env = getenv("MLDB_CHUNK");
   if (env) h->chunk_seqs = atoi(env);
   env = getenv("MLDB_GRAPH");
@@ -607,6 +633,8 @@ extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* val
     if (!strcmp(value, "tc")) h->use_tc = true;
     else if (!strcmp(value, "simt")) h->use_tc = false;
     else FAIL(MLDB_ERR_INVALID, "gemm must be tc|simt");
+  } else if (!strcmp(name, "pair_chunk")) {
+    h->pair_chunk = atoi(value) != 0;
   } else if (!strcmp(name, "chunk")) {
     h->chunk_seqs = atoi(value);
   } else if (!strcmp(name, "graph")) {

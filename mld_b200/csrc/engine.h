@@ -111,6 +111,7 @@ struct mldb_handle {
   bool capturing = false;
   bool use_tc = true;        // tcgen05 GEMMs (option gemm=simt switches to the CUDA-core path)
   bool use_graph = true;
+  bool pair_chunk = false;   // chunk qkv->attention and FFN1->FFN2 pairs through one L2-sized buffer
   int chunk_seqs = 0;        // sequences per stack pass (0 = whole batch); see denoiser_pass
   TcCtx* tc = nullptr;
 };

@@ -58,7 +58,8 @@ struct AttnArgs {
   int nseq = 0, heads = 0, hd = 0;
   const int32_t* lengths = nullptr;   // valid keys = min(Lk, kv_prefix + lengths[s]) when set
   int kv_prefix = 0;
-  int len_mod = 0;                    // lengths index = s % len_mod when len_mod > 0
+  int len_mod = 0;                    // lengths index = (seq0 + s) % len_mod when len_mod > 0
+  int seq0 = 0;                       // global index of this launch's first sequence (chunked launches)
   ActBuf out{};                       // [nseq*Lq, heads*hd]
 };
 

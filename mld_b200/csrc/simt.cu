@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) k_attn_simt(const AttnArgs a) 
   const int hd = a.hd, Lk = a.Lk, Lq = a.Lq;
   int nk = Lk;
   if (a.lengths) {
-    const int li = a.len_mod > 0 ? s % a.len_mod : s;
+    const int li = a.len_mod > 0 ? (a.seq0 + s) % a.len_mod : s;
     nk = min(Lk, a.kv_prefix + a.lengths[li]);
   }
   float* Ks = sm;                          // [Lk][hd+1]

@@ -447,10 +447,16 @@ static void ffn_block(mldb_handle* h, const LinW& l1, const LinW& l2, const LnW&
     const int rows = (int)std::min<int64_t>(crow, ws.M - r0);
     ActBuf hb = rows_of(ws.h, 0, rows);                    // the same rows for every chunk
     GemmArgs g; g.a1 = rows_of(xin, r0, rows); g.K1 = ws.d; g.M = rows; g.w = l1; g.act = act; g.out = hb;
-    op_gemm(h, g, st);
     GemmArgs g2; g2.a1 = hb; g2.K1 = ws.ff; g2.M = rows; g2.w = l2;
     LnArgs l; l.res = rows_of(xin, r0, rows); l.gamma = n.g; l.beta = n.b; l.M = rows; l.d = ws.d;
     l.out = rows_of(xout, r0, rows);
+    if (h->use_tc && h->ffn_pair && rows <= 128 * MLDB_PAIR_MAX_TILES && tc_gemm_pair_supported(h->tc, g, g2, l)) {
+      // FFN1 and FFN2 as one persistent launch: the hidden activations are consumed from L2
+      tc_gemm_pair(h->tc, g, g2, l, h->pair_cnt, st);
+      count_launch(h);
+      continue;
+    }
+    op_gemm(h, g, st);
     op_gemm_ln(h, g2, l, ws.cf32, st);
   }
 }
@@ -601,8 +607,12 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   mma_attention_init();
   h->tc = tc_create(device);
   if (!h->tc) { delete h; return MLDB_ERR_CUDA; }
+  if (dev_alloc(h, (void**)&h->pair_cnt, MLDB_PAIR_MAX_TILES * sizeof(int)) != MLDB_OK ||
+      cudaMemset(h->pair_cnt, 0, MLDB_PAIR_MAX_TILES * sizeof(int)) != cudaSuccess) { delete h; return MLDB_ERR_CUDA; }
   const char* env = getenv("MLDB_GEMM");
   if (env && !strcmp(env, "simt")) h->use_tc = false;
+  env = getenv("MLDB_FFN_PAIR");
+  if (env) h->ffn_pair = atoi(env) != 0;
   env = getenv("MLDB_PAIR_CHUNK");
   if (env) h->pair_chunk = atoi(env) != 0;
   env = getenv("MLDB_CHUNK");
@@ -633,6 +643,8 @@ extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* val
     if (!strcmp(value, "tc")) h->use_tc = true;
     else if (!strcmp(value, "simt")) h->use_tc = false;
     else FAIL(MLDB_ERR_INVALID, "gemm must be tc|simt");
+  } else if (!strcmp(name, "ffn_pair")) {
+    h->ffn_pair = atoi(value) != 0;
   } else if (!strcmp(name, "pair_chunk")) {
     h->pair_chunk = atoi(value) != 0;
   } else if (!strcmp(name, "chunk")) {

@@ -11,6 +11,8 @@
 #include "misc_kernels.cuh"
 #include "ops.cuh"
 
+#define MLDB_PAIR_MAX_TILES 65536
+
 struct LnW { float* g = nullptr; float* b = nullptr; };
 
 struct EncW {  // TransformerEncoderLayer (cross_attention.py:236-257)
@@ -111,6 +113,8 @@ struct mldb_handle {
   bool capturing = false;
   bool use_tc = true;        // tcgen05 GEMMs (option gemm=simt switches to the CUDA-core path)
   bool use_graph = true;
+  bool ffn_pair = true;      // FFN1 + FFN2 as one persistent pair launch (gemm_tc.cu pair mode)
+  int* pair_cnt = nullptr;   // per-m-tile arrival counters of the pair launch
   bool pair_chunk = false;   // chunk qkv->attention and FFN1->FFN2 pairs through one L2-sized buffer
   int chunk_seqs = 0;        // sequences per stack pass (0 = whole batch); see denoiser_pass
   TcCtx* tc = nullptr;

@@ -136,6 +136,18 @@ struct TcParams {
   int dbg;   // timing experiments only (MLDB_TC_DBG): 1 = no global stores, 2 = no epilogue math/loads, 4 = no MMA
 };
 
+// Pair mode: one persistent launch runs a producer GEMM (type 0, e.g. FFN1+GELU) and its consumer
+// GEMM (type 1, e.g. FFN2+residual+LayerNorm) as one ordered work list: per block of `mb` m-tiles,
+// the n_tiles producer tiles of every m-tile, then one consumer tile per m-tile.  The consumer
+// tile of m-tile m starts once cnt[m] reaches the number of producer-epilogue arrivals (device
+// scope release/acquire), so the intermediate is read back from L2 right after it was written and
+// one kernel boundary disappears.  mb == 0: ordinary single-GEMM mode.
+struct PairCfg {
+  int mb;        // m-tiles per block (0 = off)
+  int* cnt;      // [m_tiles] arrival counters, zero between launches (the consumer resets them)
+};
+struct WorkItem { int type, m0, n0; };
+
 constexpr int EPI_WARPS = 8;                         // two warps per TMEM lane quarter
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;     // producer warp + MMA warp + epilogue warps
 constexpr int MAX_N = 1024;                          // bias staging capacity
@@ -149,7 +161,8 @@ struct TileCfg {
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator
   // bias[MAX_N] + gamma[256] + beta[256] + LN partials [2][2][128] + barriers
   static constexpr int STG_BYTES = EPI_WARPS * 2048;   // per-warp 32 rows x 64 B transpose buffer
-  static constexpr int AUX_BYTES = MAX_N * 4 + 2 * 256 * 4 + 4 * 128 * 4 + 256 + STG_BYTES;
+  // bias[MAX_N] + bias2[256] + gamma[256] + beta[256] + LN partials + staging + barriers
+  static constexpr int AUX_BYTES = MAX_N * 4 + 3 * 256 * 4 + 4 * 128 * 4 + 256 + STG_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;   // + alignment slack
 };
 
@@ -247,6 +260,22 @@ __device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&
   }
 }
 
+__device__ __forceinline__ WorkItem decode_item(int t, const TcParams& p, int mb, int bn) {
+  WorkItem it;
+  if (mb == 0) { it.type = 0; it.m0 = (t / p.n_tiles) * BM; it.n0 = (t % p.n_tiles) * bn; return it; }
+  const int per = (p.n_tiles + 1) * mb;
+  const int b = t / per, r = t - b * per, mbase = b * mb;
+  const int mc = min(mb, p.m_tiles - mbase);
+  if (r < p.n_tiles * mc) { it.type = 0; it.m0 = (mbase + r / p.n_tiles) * BM; it.n0 = (r % p.n_tiles) * bn; }
+  else { it.type = 1; it.m0 = (mbase + r - p.n_tiles * mc) * BM; it.n0 = 0; }
+  return it;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // ------------------------------------------------------------------------------ the kernel
 // Persistent: CTA c walks tiles c, c + gridDim.x, ...; tile t -> (m = t / n_tiles, n = t % n_tiles).
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
@@ -256,14 +285,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
           const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
-          const TcParams p) {
+          const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
+          const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
+          const TcParams p, const TcParams p2, const PairCfg pc) {
   using Cfg = TileCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
   float* s_bias = reinterpret_cast<float*>(aux);              // [MAX_N]
-  float* s_gamma = s_bias + MAX_N;                            // [256]
+  float* s_bias2 = s_bias + MAX_N;                            // [256] consumer GEMM bias (pair mode)
+  float* s_gamma = s_bias2 + 256;                             // [256]
   float* s_beta = s_gamma + 256;                              // [256]
   float* s_part = s_beta + 256;                               // [2 passes][2 halves][128 rows]
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_part + 4 * 128);   // [EPI_WARPS][2048], 16B aligned
@@ -276,7 +308,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntiles = p.m_tiles * p.n_tiles;
+  const bool pair = pc.mb > 0;
+  const int ntiles = p.m_tiles * (p.n_tiles + (pair ? 1 : 0));
+  const TcParams& pl = pair ? p2 : p;                         // the GEMM whose epilogue is the LayerNorm
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -296,8 +330,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   }
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.0f;
-    if (p.ln)
-      for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) { s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
+    if (pl.ln)
+      for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) {
+        s_gamma[i] = pl.gamma[i]; s_beta[i] = pl.beta[i];
+        s_bias2[i] = (pair && p2.bias) ? p2.bias[i] : 0.0f;
+      }
   }
   pdl_trigger();               // let the next kernel's prologue overlap our tail
   tc_fence_before();
@@ -311,8 +348,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       // ---------------------------------------------------------------- TMA producer
       int kbg = 0;                                   // k-block counter across tiles (ring position)
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
-        for (int kb = 0; kb < p.kblocks; ++kb, ++kbg) {
+        const WorkItem wi = decode_item(tile, p, pc.mb, BN);
+        const TcParams& q = wi.type ? p2 : p;
+        const int m0 = wi.m0, n0 = wi.n0;
+        if (wi.type) {
+          // consumer tile: wait until every producer-epilogue warp of this m-tile has published
+          const int mt = m0 / BM, target = EPI_WARPS * p.n_tiles;
+          long long t0 = 0; unsigned spins = 0;
+          while (ld_acquire_gpu(pc.cnt + mt) < target) {
+            if ((++spins & 255u) == 0) {
+              const long long now = clock64();
+              if (t0 == 0) t0 = now; else if (now - t0 > 4000000000ll) __trap();
+            }
+          }
+          pc.cnt[mt] = 0;                                   // ready for the next launch
+          asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> TMA reads
+        }
+        for (int kb = 0; kb < q.kblocks; ++kb, ++kbg) {
           const int s = kbg % STAGES;
           const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
           mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
@@ -320,15 +372,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           mbar_expect_tx(full, Cfg::STAGE_BYTES);
           const uint32_t sAh = smem_u32(smem + s * Cfg::STAGE_BYTES), sAl = sAh + Cfg::A_BYTES;
           const uint32_t sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
-          if (kb < p.kb1) {
-            tma_load_2d(sAh, &tmA1h, full, kb * BK, m0);
-            tma_load_2d(sAl, &tmA1l, full, kb * BK, m0);
+          if (wi.type) {
+            tma_load_2d(sAh, &tmBh, full, kb * BK, m0);
+            tma_load_2d(sAl, &tmBl, full, kb * BK, m0);
+            tma_load_2d(sWh, &tmVh, full, kb * BK, n0);
+            tma_load_2d(sWl, &tmVl, full, kb * BK, n0);
           } else {
-            tma_load_2d(sAh, &tmA2h, full, (kb - p.kb1) * BK, m0);
-            tma_load_2d(sAl, &tmA2l, full, (kb - p.kb1) * BK, m0);
+            if (kb < q.kb1) {
+              tma_load_2d(sAh, &tmA1h, full, kb * BK, m0);
+              tma_load_2d(sAl, &tmA1l, full, kb * BK, m0);
+            } else {
+              tma_load_2d(sAh, &tmA2h, full, (kb - q.kb1) * BK, m0);
+              tma_load_2d(sAl, &tmA2l, full, (kb - q.kb1) * BK, m0);
+            }
+            tma_load_2d(sWh, &tmWh, full, kb * BK, n0);
+            tma_load_2d(sWl, &tmWl, full, kb * BK, n0);
           }
-          tma_load_2d(sWh, &tmWh, full, kb * BK, n0);
-          tma_load_2d(sWl, &tmWl, full, kb * BK, n0);
         }
       }
     }
@@ -342,7 +401,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         mbar_wait(smem_u32(&bar_tempty[as]), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained it
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
-        for (int kb = 0; kb < p.kblocks; ++kb, ++kbg) {
+        const int nkb = decode_item(tile, p, pc.mb, BN).type ? p2.kblocks : p.kblocks;
+        for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const int s = kbg % STAGES;
           const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
           mbar_wait(smem_u32(&bar_full[s]), ph);
@@ -376,53 +436,56 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
-      const int m0 = (tile / p.n_tiles) * BM, n0 = (tile % p.n_tiles) * BN;
+      const WorkItem wi = decode_item(tile, p, pc.mb, BN);
+      const TcParams& pp = wi.type ? p2 : p;
+      const float* const sb = wi.type ? s_bias2 : s_bias;
+      const int m0 = wi.m0, n0 = wi.n0;
       const int m = m0 + row;
-      const bool row_ok = m < p.M;
+      const bool row_ok = m < pp.M;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + hf * (BN / 2));
       uint8_t* const stg = s_stage + (warp - 2) * 2048;
       const int wrow0 = m0 + q * 32;                         // first tile row owned by this warp
-      const int rows_valid = min(32, p.M - wrow0);           // <= 0: nothing to write
-      if (!p.ln) {
+      const int rows_valid = min(32, pp.M - wrow0);           // <= 0: nothing to write
+      if (!pp.ln) {
         mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
         tc_fence_after();
         int seq = 0, pos = m;
-        if (row_ok && p.in_group < p.M) { seq = m / p.in_group; pos = m - seq * p.in_group; }
-        const int64_t orow = (int64_t)seq * p.out_group + p.out_off + pos;
-        const bool zero = row_ok && p.zero_lengths != nullptr && pos >= p.zero_lengths[seq];
-        const float* tab = p.addtab ? p.addtab + (int64_t)(p.out_off + pos) * p.N : nullptr;
+        if (row_ok && pp.in_group < pp.M) { seq = m / pp.in_group; pos = m - seq * pp.in_group; }
+        const int64_t orow = (int64_t)seq * pp.out_group + pp.out_off + pos;
+        const bool zero = row_ok && pp.zero_lengths != nullptr && pos >= pp.zero_lengths[seq];
+        const float* tab = pp.addtab ? pp.addtab + (int64_t)(pp.out_off + pos) * pp.N : nullptr;
         // fast path: identity row mapping, split16 output, no table / masking (warp-uniform)
-        const bool fast = p.addtab == nullptr && p.zero_lengths == nullptr && p.out_hi != nullptr &&
-                          p.out_f32 == nullptr && p.in_group >= p.M && p.out_group == 0 && p.out_off == 0;
-        const float inv_scale = p.inv_scale;
-        const int act = p.act, N = p.N;
-        __half* const ohi = p.out_hi;
-        __half* const olo = p.out_lo;
-        const int64_t obase = orow * p.ld_out + p.out_col0;
+        const bool fast = pp.addtab == nullptr && pp.zero_lengths == nullptr && pp.out_hi != nullptr &&
+                          pp.out_f32 == nullptr && pp.in_group >= pp.M && pp.out_group == 0 && pp.out_off == 0;
+        const float inv_scale = pp.inv_scale;
+        const int act = pp.act, N = pp.N;
+        __half* const ohi = pp.out_hi;
+        __half* const olo = pp.out_lo;
+        const int64_t obase = orow * pp.ld_out + pp.out_col0;
 #pragma unroll 1
         for (int c = 0; c < ((p.dbg & 2) ? 0 : CH); ++c) {
           tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
           const int nb = n0 + hf * (BN / 2) + c * 32;
           if (fast && nb + 32 <= N) {               // warp-uniform branch: all lanes take part
             switch (act) {                          // once per chunk
-              case ACT_NONE: epi_chunk_fast<ACT_NONE>(r, v, s_bias + nb, inv_scale); break;
-              case ACT_GELU: epi_chunk_fast<ACT_GELU>(r, v, s_bias + nb, inv_scale); break;
-              case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, s_bias + nb, inv_scale); break;
-              default:       epi_chunk_fast<ACT_SILU>(r, v, s_bias + nb, inv_scale); break;
+              case ACT_NONE: epi_chunk_fast<ACT_NONE>(r, v, sb + nb, inv_scale); break;
+              case ACT_GELU: epi_chunk_fast<ACT_GELU>(r, v, sb + nb, inv_scale); break;
+              case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, sb + nb, inv_scale); break;
+              default:       epi_chunk_fast<ACT_SILU>(r, v, sb + nb, inv_scale); break;
             }
             uint32_t ph[16], pl[16];
             pack_split(v, ph, pl);
             if (!(p.dbg & 1)) {
-              const int64_t o = (int64_t)wrow0 * p.ld_out + p.out_col0 + nb;
-              store_plane_coalesced(stg, ph, ohi + o, p.ld_out, rows_valid, lane);
-              store_plane_coalesced(stg, pl, olo + o, p.ld_out, rows_valid, lane);
+              const int64_t o = (int64_t)wrow0 * pp.ld_out + pp.out_col0 + nb;
+              store_plane_coalesced(stg, ph, ohi + o, pp.ld_out, rows_valid, lane);
+              store_plane_coalesced(stg, pl, olo + o, pp.ld_out, rows_valid, lane);
             }
           } else if (row_ok && nb < N) {
             const bool full = nb + 32 <= N;
             {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
-                float x = __uint_as_float(r[i]) * inv_scale + s_bias[min(nb + i, MAX_N - 1)];
+                float x = __uint_as_float(r[i]) * inv_scale + sb[min(nb + i, MAX_N - 1)];
                 if (tab && (full || nb + i < N)) x += tab[nb + i];
                 x = apply_act(x, act);
                 v[i] = zero ? 0.0f : x;
@@ -442,8 +505,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
                   }
                 }
               }
-              if (p.out_f32) {
-                float* dst = p.out_f32 + orow * p.ldc + nb;
+              if (pp.out_f32) {
+                float* dst = pp.out_f32 + orow * pp.ldc + nb;
 #pragma unroll
                 for (int i = 0; i < 32; ++i)
                   if (full || nb + i < N) dst[i] = v[i];
@@ -452,6 +515,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           }
           __syncwarp();
         }
+        if (pair && wi.type == 0) {              // publish this warp's part of the intermediate tile
+          __threadfence();
+          __syncwarp();
+          if (lane == 0) atomicAdd(pc.cnt + m0 / BM, 1);
+        }
       } else {
         // x = acc*s + bias + residual (+ rowvec); y = LayerNorm(x) over the 256-wide row, eps 1e-5.
         // Two warps share a row (column halves) and exchange partial sums through shared memory; the
@@ -459,21 +527,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         // Statistics in one pass with a per-row shift K (the row's first residual value) so that
         // var = E[(x-K)^2] - E[x-K]^2 does not cancel.  The residual chunk c+1 is fetched while
         // chunk c is processed (the loop is fully unrolled), chunk 0 before the accumulator is ready.
-        const float* rv = (row_ok && p.rowvec) ? p.rowvec + (int64_t)(m / p.rv_group) * BN : nullptr;
+        const float* rv = (row_ok && pp.rowvec) ? pp.rowvec + (int64_t)(m / pp.rv_group) * BN : nullptr;
         const int cb = hf * (BN / 2);
-        const bool has_res = p.res_hi != nullptr;                       // warp-uniform
-        const float shiftK = (has_res && row_ok) ? join_f32(p.res_hi[(int64_t)m * p.ld_res], p.res_lo[(int64_t)m * p.ld_res]) : 0.0f;
-        const __half* rbh = p.res_hi + (int64_t)wrow0 * p.ld_res + cb;   // this warp's 32 rows, its column half
-        const __half* rbl = p.res_lo + (int64_t)wrow0 * p.ld_res + cb;
+        const bool has_res = pp.res_hi != nullptr;                       // warp-uniform
+        const float shiftK = (has_res && row_ok) ? join_f32(pp.res_hi[(int64_t)m * pp.ld_res], pp.res_lo[(int64_t)m * pp.ld_res]) : 0.0f;
+        const __half* rbh = pp.res_hi + (int64_t)wrow0 * pp.ld_res + cb;   // this warp's 32 rows, its column half
+        const __half* rbl = pp.res_lo + (int64_t)wrow0 * pp.ld_res + cb;
         uint4 gh[4], gl[4];                       // residual chunk in the coalesced (4 lanes per row) pattern
         if (has_res) {
-          load_plane_issue(rbh, p.ld_res, rows_valid, lane, gh);
-          load_plane_issue(rbl, p.ld_res, rows_valid, lane, gl);
+          load_plane_issue(rbh, pp.ld_res, rows_valid, lane, gh);
+          load_plane_issue(rbl, pp.ld_res, rows_valid, lane, gl);
         }
         mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
         tc_fence_after();
         float s1 = 0.0f, s2 = 0.0f;
-        const float sc = p.inv_scale;
+        const float sc = pp.inv_scale;
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           uint4 rh[4], rl[4];                     // the same chunk, row-owner layout
@@ -481,15 +549,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
             plane_to_rows(stg, gh, lane, rh);
             plane_to_rows(stg, gl, lane, rl);
             if (c + 1 < CH) {                     // fetch the next chunk under this one's math
-              load_plane_issue(rbh + (c + 1) * 32, p.ld_res, rows_valid, lane, gh);
-              load_plane_issue(rbl + (c + 1) * 32, p.ld_res, rows_valid, lane, gl);
+              load_plane_issue(rbh + (c + 1) * 32, pp.ld_res, rows_valid, lane, gh);
+              load_plane_issue(rbl + (c + 1) * 32, pp.ld_res, rows_valid, lane, gl);
             }
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
           }
           tmem_ld32(trow + c * 32, r);
-          const float* bch = s_bias + cb + c * 32;
+          const float* bch = sb + cb + c * 32;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t ah[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
@@ -537,9 +605,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           }
           uint32_t ph[16], pl[16];
           pack_split(v, ph, pl);
-          const int64_t o = (int64_t)wrow0 * p.ld_out + cb + c * 32;
-          store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
-          store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
+          const int64_t o = (int64_t)wrow0 * pp.ld_out + cb + c * 32;
+          store_plane_coalesced(stg, ph, pp.out_hi + o, pp.ld_out, rows_valid, lane);
+          store_plane_coalesced(stg, pl, pp.out_lo + o, pp.ld_out, rows_valid, lane);
         }
         // the partial sums of this tile may be overwritten only after everyone has read them
         epi_bar_sync();
@@ -638,18 +706,7 @@ bool tc_gemm_ln_supported(const TcCtx* c, const GemmArgs& g, const LnArgs& l) {
   return true;
 }
 
-void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
-  CUtensorMap mA1h, mA1l, mA2h, mA2l, mWh, mWl;
-  const int bn = ln ? 256 : pick_bn(g);
-  bool ok = make_map(c, &mA1h, g.a1.hi, g.M, g.K1, BM) && make_map(c, &mA1l, g.a1.lo(), g.M, g.K1, BM);
-  if (g.K2 > 0) ok = ok && make_map(c, &mA2h, g.a2.hi, g.M, g.K2, BM) && make_map(c, &mA2l, g.a2.lo(), g.M, g.K2, BM);
-  else { mA2h = mA1h; mA2l = mA1l; }
-  ok = ok && make_map(c, &mWh, g.w.w, g.w.N, g.w.K, bn) && make_map(c, &mWl, g.w.w + g.w.plane_stride, g.w.N, g.w.K, bn);
-  if (!ok) {
-    fprintf(stderr, "libmldb200: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)\n", g.M, g.w.N, g.w.K);
-    c->ok = false;
-    return;
-  }
+static void fill_params(const TcCtx* c, const GemmArgs& g, const LnArgs* ln, int bn, TcParams* out) {
   TcParams p{};
   p.M = g.M; p.N = g.w.N; p.kblocks = g.w.K / BK; p.kb1 = g.K1 / BK;
   p.inv_scale = g.w.inv_scale; p.bias = g.w.bias; p.addtab = g.addtab; p.act = g.act;
@@ -667,10 +724,64 @@ void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   p.dbg = c->dbg;
   p.m_tiles = (g.M + BM - 1) / BM;
   p.n_tiles = (g.w.N + bn - 1) / bn;
+  *out = p;
+}
+
+void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
+  CUtensorMap mA1h, mA1l, mA2h, mA2l, mWh, mWl;
+  const int bn = ln ? 256 : pick_bn(g);
+  bool ok = make_map(c, &mA1h, g.a1.hi, g.M, g.K1, BM) && make_map(c, &mA1l, g.a1.lo(), g.M, g.K1, BM);
+  if (g.K2 > 0) ok = ok && make_map(c, &mA2h, g.a2.hi, g.M, g.K2, BM) && make_map(c, &mA2l, g.a2.lo(), g.M, g.K2, BM);
+  else { mA2h = mA1h; mA2l = mA1l; }
+  ok = ok && make_map(c, &mWh, g.w.w, g.w.N, g.w.K, bn) && make_map(c, &mWl, g.w.w + g.w.plane_stride, g.w.N, g.w.K, bn);
+  if (!ok) {
+    fprintf(stderr, "libmldb200: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)\n", g.M, g.w.N, g.w.K);
+    c->ok = false;
+    return;
+  }
+  TcParams p, p2{};
+  fill_params(c, g, ln, bn, &p);
+  const PairCfg pc{0, nullptr};
   const int ntiles = p.m_tiles * p.n_tiles;
   dim3 grid(ntiles < c->sm_count ? ntiles : c->sm_count);
   if (bn == 256)
-    launch_pdl(k_gemm_tc<256>, grid, dim3(NUM_THREADS), TileCfg<256>::SMEM_BYTES, st, mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
+    launch_pdl(k_gemm_tc<256>, grid, dim3(NUM_THREADS), TileCfg<256>::SMEM_BYTES, st, mA1h, mA1l, mA2h, mA2l, mWh, mWl,
+               mA1h, mA1l, mWh, mWl, p, p2, pc);
   else
-    launch_pdl(k_gemm_tc<128>, grid, dim3(NUM_THREADS), TileCfg<128>::SMEM_BYTES, st, mA1h, mA1l, mA2h, mA2l, mWh, mWl, p);
+    launch_pdl(k_gemm_tc<128>, grid, dim3(NUM_THREADS), TileCfg<128>::SMEM_BYTES, st, mA1h, mA1l, mA2h, mA2l, mWh, mWl,
+               mA1h, mA1l, mWh, mWl, p, p2, pc);
+}
+
+// Producer GEMM g1 (plain epilogue, N a multiple of 256, e.g. FFN1+GELU) and consumer GEMM g2
+// (+ residual + LayerNorm, A operand == g1's output) in ONE persistent launch (pair mode).
+bool tc_gemm_pair_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2) {
+  if (!tc_gemm_supported(c, g1) || !tc_gemm_ln_supported(c, g2, l2)) return false;
+  if (g1.w.N % 256 || g1.K2 > 0 || g2.K2 > 0 || g1.M != g2.M) return false;
+  if (!g1.out.hi || g1.out.hi != g2.a1.hi || g1.out_col0 != 0 || g1.out_f32) return false;
+  if (g1.addtab || g1.zero_lengths || g1.in_group < g1.M || g1.out_group != 0 || g1.out_off != 0) return false;
+  return true;
+}
+
+void tc_gemm_pair(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, int* counters,
+                  cudaStream_t st) {
+  CUtensorMap mAh, mAl, mWh, mWl, mBh, mBl, mVh, mVl;
+  bool ok = make_map(c, &mAh, g1.a1.hi, g1.M, g1.K1, BM) && make_map(c, &mAl, g1.a1.lo(), g1.M, g1.K1, BM) &&
+            make_map(c, &mWh, g1.w.w, g1.w.N, g1.w.K, 256) && make_map(c, &mWl, g1.w.w + g1.w.plane_stride, g1.w.N, g1.w.K, 256) &&
+            make_map(c, &mBh, g2.a1.hi, g2.M, g2.K1, BM) && make_map(c, &mBl, g2.a1.lo(), g2.M, g2.K1, BM) &&
+            make_map(c, &mVh, g2.w.w, g2.w.N, g2.w.K, 256) && make_map(c, &mVl, g2.w.w + g2.w.plane_stride, g2.w.N, g2.w.K, 256);
+  if (!ok) {
+    fprintf(stderr, "libmldb200: cuTensorMapEncodeTiled failed (pair M=%d)\n", g1.M);
+    c->ok = false;
+    return;
+  }
+  TcParams p, p2;
+  fill_params(c, g1, nullptr, 256, &p);
+  fill_params(c, g2, &l2, 256, &p2);
+  // one wave of producer tiles per block: mb m-tiles x n_tiles == sm_count (at least 1)
+  const int mb = c->sm_count / p.n_tiles > 0 ? c->sm_count / p.n_tiles : 1;
+  const PairCfg pc{mb, counters};
+  const int ntiles = p.m_tiles * (p.n_tiles + 1);
+  dim3 grid(ntiles < c->sm_count ? ntiles : c->sm_count);
+  launch_pdl(k_gemm_tc<256>, grid, dim3(NUM_THREADS), TileCfg<256>::SMEM_BYTES, st, mAh, mAl, mAh, mAl, mWh, mWl,
+             mBh, mBl, mVh, mVl, p, p2, pc);
 }

@@ -11,3 +11,6 @@ bool tc_gemm_supported(const TcCtx* c, const GemmArgs& g);
 bool tc_gemm_ln_supported(const TcCtx* c, const GemmArgs& g, const LnArgs& l);
 // enqueue; ln == nullptr for the plain epilogue
 void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st);
+// producer GEMM + consumer GEMM(+LN) as one persistent launch; counters: int[m_tiles], zeroed once
+bool tc_gemm_pair_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2);
+void tc_gemm_pair(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, int* counters, cudaStream_t st);

@@ -137,16 +137,17 @@ struct TcParams {
 };
 
 // Pair mode: one persistent launch runs a producer GEMM (type 0, e.g. FFN1+GELU) and its consumer
-// GEMM (type 1, e.g. FFN2+residual+LayerNorm) as one ordered work list: per block of `mb` m-tiles,
-// the n_tiles producer tiles of every m-tile, then one consumer tile per m-tile.  The consumer
-// tile of m-tile m starts once cnt[m] reaches the number of producer-epilogue arrivals (device
-// scope release/acquire), so the intermediate is read back from L2 right after it was written and
-// one kernel boundary disappears.  mb == 0: ordinary single-GEMM mode.
+// GEMM (type 1, e.g. FFN2+residual+LayerNorm).  CTA c owns m-tiles c, c+G, c+2G, ... and for each
+// of them runs the n_tiles producer tiles and then the consumer tile, so every dependency is
+// CTA-local: the producer epilogue writes the intermediate tile into this CTA's private 128-row
+// slot of a small scratch buffer (G x 128 rows - it lives in L2 and never travels to HBM), the TMA
+// warp waits on a per-CTA arrival counter (release/acquire + async-proxy fence) before loading the
+// slot as the consumer's A operand, and one kernel boundary disappears.  on == 0: single-GEMM mode.
 struct PairCfg {
-  int mb;        // m-tiles per block (0 = off)
-  int* cnt;      // [m_tiles] arrival counters, zero between launches (the consumer resets them)
+  int on;
+  int* cnt;      // [gridDim.x] arrival counters, zero between launches (the consumer resets them)
 };
-struct WorkItem { int type, m0, n0; };
+struct WorkItem { int type, m0, n0, s0; };   // s0: first row of this CTA's scratch slot
 
 constexpr int EPI_WARPS = 8;                         // two warps per TMEM lane quarter
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;     // producer warp + MMA warp + epilogue warps
@@ -260,14 +261,19 @@ __device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&
   }
 }
 
-__device__ __forceinline__ WorkItem decode_item(int t, const TcParams& p, int mb, int bn) {
+// j-th work item of this CTA
+__device__ __forceinline__ WorkItem decode_item(int j, const TcParams& p, int pair, int bn) {
   WorkItem it;
-  if (mb == 0) { it.type = 0; it.m0 = (t / p.n_tiles) * BM; it.n0 = (t % p.n_tiles) * bn; return it; }
-  const int per = (p.n_tiles + 1) * mb;
-  const int b = t / per, r = t - b * per, mbase = b * mb;
-  const int mc = min(mb, p.m_tiles - mbase);
-  if (r < p.n_tiles * mc) { it.type = 0; it.m0 = (mbase + r / p.n_tiles) * BM; it.n0 = (r % p.n_tiles) * bn; }
-  else { it.type = 1; it.m0 = (mbase + r - p.n_tiles * mc) * BM; it.n0 = 0; }
+  it.s0 = blockIdx.x * BM;
+  if (!pair) {
+    const int t = blockIdx.x + j * gridDim.x;
+    it.type = 0; it.m0 = (t / p.n_tiles) * BM; it.n0 = (t % p.n_tiles) * bn;
+    return it;
+  }
+  const int per = p.n_tiles + 1;
+  const int k = j / per, r = j - k * per;
+  it.m0 = (blockIdx.x + k * gridDim.x) * BM;
+  if (r < p.n_tiles) { it.type = 0; it.n0 = r * bn; } else { it.type = 1; it.n0 = 0; }
   return it;
 }
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
@@ -308,8 +314,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool pair = pc.mb > 0;
-  const int ntiles = p.m_tiles * (p.n_tiles + (pair ? 1 : 0));
+  const bool pair = pc.on != 0;
+  // number of work items of this CTA
+  const int nlocal = pair ? ((p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (p.n_tiles + 1)
+                          : (p.m_tiles * p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const TcParams& pl = pair ? p2 : p;                         // the GEMM whose epilogue is the LayerNorm
 
   if (threadIdx.x == 0) {
@@ -347,13 +355,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     if (lane == 0) {
       // ---------------------------------------------------------------- TMA producer
       int kbg = 0;                                   // k-block counter across tiles (ring position)
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const WorkItem wi = decode_item(tile, p, pc.mb, BN);
+      for (int j = 0; j < nlocal; ++j) {
+        const WorkItem wi = decode_item(j, p, pair, BN);
         const TcParams& q = wi.type ? p2 : p;
         const int m0 = wi.m0, n0 = wi.n0;
         if (wi.type) {
-          // consumer tile: wait until every producer-epilogue warp of this m-tile has published
-          const int mt = m0 / BM, target = EPI_WARPS * p.n_tiles;
+          // consumer tile: wait until every producer-epilogue warp has published its part of the slot
+          const int mt = blockIdx.x, target = EPI_WARPS * p.n_tiles;
           long long t0 = 0; unsigned spins = 0;
           while (ld_acquire_gpu(pc.cnt + mt) < target) {
             if ((++spins & 255u) == 0) {
@@ -373,8 +381,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           const uint32_t sAh = smem_u32(smem + s * Cfg::STAGE_BYTES), sAl = sAh + Cfg::A_BYTES;
           const uint32_t sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
           if (wi.type) {
-            tma_load_2d(sAh, &tmBh, full, kb * BK, m0);
-            tma_load_2d(sAl, &tmBl, full, kb * BK, m0);
+            tma_load_2d(sAh, &tmBh, full, kb * BK, wi.s0);
+            tma_load_2d(sAl, &tmBl, full, kb * BK, wi.s0);
             tma_load_2d(sWh, &tmVh, full, kb * BK, n0);
             tma_load_2d(sWl, &tmVl, full, kb * BK, n0);
           } else {
@@ -396,12 +404,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       // ---------------------------------------------------------------- MMA issuer
       constexpr uint32_t idesc = make_idesc(BN);
       int kbg = 0, it = 0;
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (; it < nlocal; ++it) {
         const int as = it & 1;
         mbar_wait(smem_u32(&bar_tempty[as]), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained it
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
-        const int nkb = decode_item(tile, p, pc.mb, BN).type ? p2.kblocks : p.kblocks;
+        const int nkb = decode_item(it, p, pair, BN).type ? p2.kblocks : p.kblocks;
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const int s = kbg % STAGES;
           const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
@@ -434,9 +442,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     uint32_t r[32];
     float v[32];
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (; it < nlocal; ++it) {
       const int as = it & 1;
-      const WorkItem wi = decode_item(tile, p, pc.mb, BN);
+      const WorkItem wi = decode_item(it, p, pair, BN);
       const TcParams& pp = wi.type ? p2 : p;
       const float* const sb = wi.type ? s_bias2 : s_bias;
       const int m0 = wi.m0, n0 = wi.n0;
@@ -444,8 +452,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       const bool row_ok = m < pp.M;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + hf * (BN / 2));
       uint8_t* const stg = s_stage + (warp - 2) * 2048;
-      const int wrow0 = m0 + q * 32;                         // first tile row owned by this warp
-      const int rows_valid = min(32, pp.M - wrow0);           // <= 0: nothing to write
+      const bool to_slot = pair && wi.type == 0;             // producer tile: write into the CTA's slot
+      const int wrow0 = (to_slot ? wi.s0 : m0) + q * 32;     // first output row owned by this warp
+      const int rows_valid = to_slot ? 32 : min(32, pp.M - wrow0);   // <= 0: nothing to write
       if (!pp.ln) {
         mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
         tc_fence_after();
@@ -518,7 +527,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         if (pair && wi.type == 0) {              // publish this warp's part of the intermediate tile
           __threadfence();
           __syncwarp();
-          if (lane == 0) atomicAdd(pc.cnt + m0 / BM, 1);
+          if (lane == 0) atomicAdd(pc.cnt + blockIdx.x, 1);
         }
       } else {
         // x = acc*s + bias + residual (+ rowvec); y = LayerNorm(x) over the 256-wide row, eps 1e-5.
@@ -758,6 +767,7 @@ bool tc_gemm_pair_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& 
   if (!tc_gemm_supported(c, g1) || !tc_gemm_ln_supported(c, g2, l2)) return false;
   if (g1.w.N % 256 || g1.K2 > 0 || g2.K2 > 0 || g1.M != g2.M) return false;
   if (!g1.out.hi || g1.out.hi != g2.a1.hi || g1.out_col0 != 0 || g1.out_f32) return false;
+  if (g1.out.rows < (g1.M < c->sm_count * BM ? ((g1.M + BM - 1) / BM) * BM : c->sm_count * BM) && g1.out.rows < g1.M) return false;
   if (g1.addtab || g1.zero_lengths || g1.in_group < g1.M || g1.out_group != 0 || g1.out_off != 0) return false;
   return true;
 }
@@ -765,9 +775,12 @@ bool tc_gemm_pair_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& 
 void tc_gemm_pair(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, int* counters,
                   cudaStream_t st) {
   CUtensorMap mAh, mAl, mWh, mWl, mBh, mBl, mVh, mVl;
+  const int m_tiles = (g1.M + BM - 1) / BM;
+  const int grid = m_tiles < c->sm_count ? m_tiles : c->sm_count;
+  // the intermediate (g1.out == g2.a1) is used as grid x 128 scratch rows
   bool ok = make_map(c, &mAh, g1.a1.hi, g1.M, g1.K1, BM) && make_map(c, &mAl, g1.a1.lo(), g1.M, g1.K1, BM) &&
             make_map(c, &mWh, g1.w.w, g1.w.N, g1.w.K, 256) && make_map(c, &mWl, g1.w.w + g1.w.plane_stride, g1.w.N, g1.w.K, 256) &&
-            make_map(c, &mBh, g2.a1.hi, g2.M, g2.K1, BM) && make_map(c, &mBl, g2.a1.lo(), g2.M, g2.K1, BM) &&
+            make_map(c, &mBh, g2.a1.hi, grid * BM, g2.K1, BM) && make_map(c, &mBl, g2.a1.lo(), grid * BM, g2.K1, BM) &&
             make_map(c, &mVh, g2.w.w, g2.w.N, g2.w.K, 256) && make_map(c, &mVl, g2.w.w + g2.w.plane_stride, g2.w.N, g2.w.K, 256);
   if (!ok) {
     fprintf(stderr, "libmldb200: cuTensorMapEncodeTiled failed (pair M=%d)\n", g1.M);
@@ -777,11 +790,7 @@ void tc_gemm_pair(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs
   TcParams p, p2;
   fill_params(c, g1, nullptr, 256, &p);
   fill_params(c, g2, &l2, 256, &p2);
-  // one wave of producer tiles per block: mb m-tiles x n_tiles == sm_count (at least 1)
-  const int mb = c->sm_count / p.n_tiles > 0 ? c->sm_count / p.n_tiles : 1;
-  const PairCfg pc{mb, counters};
-  const int ntiles = p.m_tiles * (p.n_tiles + 1);
-  dim3 grid(ntiles < c->sm_count ? ntiles : c->sm_count);
-  launch_pdl(k_gemm_tc<256>, grid, dim3(NUM_THREADS), TileCfg<256>::SMEM_BYTES, st, mAh, mAl, mAh, mAl, mWh, mWl,
+  const PairCfg pc{1, counters};
+  launch_pdl(k_gemm_tc<256>, dim3(grid), dim3(NUM_THREADS), TileCfg<256>::SMEM_BYTES, st, mAh, mAl, mAh, mAl, mWh, mWl,
              mBh, mBl, mVh, mVl, p, p2, pc);
 }

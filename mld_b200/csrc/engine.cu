@@ -443,6 +443,11 @@ static void ffn_block(mldb_handle* h, const LinW& l1, const LinW& l2, const LnW&
                       ActBuf xout, StackWs& ws, int act, cudaStream_t st) {
   int crow = ws.M;
   if (h->pair_chunk && h->use_tc && ws.d == 256) crow = h->sm_count * 128;   // one wave of FFN2 tiles
+  // Pair launch on whole waves of m-tiles only (every CTA runs the same number of FFN1->FFN2 chains);
+  // the ragged remainder goes through the two plain launches so that it spreads over all SMs.
+  const int wave_rows = h->sm_count * 128;
+  if (h->ffn_pair && h->use_tc && !h->pair_chunk && ws.M > wave_rows && ws.M % wave_rows != 0)
+    crow = (ws.M / wave_rows) * wave_rows;
   for (int64_t r0 = 0; r0 < ws.M; r0 += crow) {
     const int rows = (int)std::min<int64_t>(crow, ws.M - r0);
     ActBuf hb = rows_of(ws.h, 0, rows);                    // the same rows for every chunk
@@ -450,7 +455,8 @@ static void ffn_block(mldb_handle* h, const LinW& l1, const LinW& l2, const LnW&
     GemmArgs g2; g2.a1 = hb; g2.K1 = ws.ff; g2.M = rows; g2.w = l2;
     LnArgs l; l.res = rows_of(xin, r0, rows); l.gamma = n.g; l.beta = n.b; l.M = rows; l.d = ws.d;
     l.out = rows_of(xout, r0, rows);
-    if (h->use_tc && h->ffn_pair && rows <= 128 * MLDB_PAIR_MAX_TILES && tc_gemm_pair_supported(h->tc, g, g2, l)) {
+    if (h->use_tc && h->ffn_pair && (rows % wave_rows == 0 || ws.M <= wave_rows) &&
+        rows <= 128 * MLDB_PAIR_MAX_TILES && tc_gemm_pair_supported(h->tc, g, g2, l)) {
       // FFN1 and FFN2 as one persistent launch: the hidden activations are consumed from L2
       tc_gemm_pair(h->tc, g, g2, l, h->pair_cnt, st);
       count_launch(h);

@@ -1422,6 +1422,8 @@ extern "C" int mldb_profile_op(mldb_handle* h, const char* op, int32_t B, int32_
       GemmArgs g; g.a1 = ws.h; g.K1 = ws.ff; g.M = ws.M; g.w = w.l2;
       LnArgs l; l.res = ws.x1; l.gamma = w.n2.g; l.beta = w.n2.b; l.M = ws.M; l.d = d; l.out = ws.cur[0];
       op_gemm_ln(h, g, l, ws.cf32, st);
+    } else if (!strcmp(op, "ffn")) {             // FFN1 + FFN2 the way the stack runs them (pair mode or not)
+      ffn_block(h, w.l1, w.l2, w.n2, ws.x1, ws.cur[0], ws, ACT_GELU, st);
     } else if (!strcmp(op, "layer")) {
       enc_layer(h, h->den, w, ws.x0, ws.cur[0], ws, si, st);
     } else {

@@ -536,6 +536,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         // Statistics in one pass with a per-row shift K (the row's first residual value) so that
         // var = E[(x-K)^2] - E[x-K]^2 does not cancel.  The residual chunk c+1 is fetched while
         // chunk c is processed (the loop is fully unrolled), chunk 0 before the accumulator is ready.
+        if (p.dbg & 32) {                          // timing experiment: no LayerNorm epilogue work
+          mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
+          tc_fence_after();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
+          continue;
+        }
         const float* rv = (row_ok && pp.rowvec) ? pp.rowvec + (int64_t)(m / pp.rv_group) * BN : nullptr;
         const int cb = hf * (BN / 2);
         const bool has_res = pp.res_hi != nullptr;                       // warp-uniform

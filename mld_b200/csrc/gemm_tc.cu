@@ -291,8 +291,8 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the TMA/MMA main loop of tile i + 1.
 template <int BN>
-// 18 warps x 112 registers x 32 lanes = 64 512 <= 65 536 (register allocation granularity: 512 per warp)
-__global__ void __maxnreg__(112)
+// 18 warps: one SM sub-partition hosts 5 of them, so ptxas caps registers at 16384 / (5 x 32) -> 96
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
           const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,

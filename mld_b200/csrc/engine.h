@@ -113,7 +113,7 @@ struct mldb_handle {
   bool capturing = false;
   bool use_tc = true;        // tcgen05 GEMMs (option gemm=simt switches to the CUDA-core path)
   bool use_graph = true;
-  bool ffn_pair = true;      // FFN1 + FFN2 as one persistent pair launch (gemm_tc.cu pair mode)
+  bool ffn_pair = false;     // FFN1 + FFN2 as one persistent pair launch (gemm_tc.cu pair mode; measured 3% slower, off)
   int* pair_cnt = nullptr;   // per-m-tile arrival counters of the pair launch
   bool pair_chunk = false;   // chunk qkv->attention and FFN1->FFN2 pairs through one L2-sized buffer
   int chunk_seqs = 0;        // sequences per stack pass (0 = whole batch); see denoiser_pass

@@ -149,11 +149,7 @@ struct PairCfg {
 };
 struct WorkItem { int type, m0, n0, s0; };   // s0: first row of this CTA's scratch slot
 
-// The epilogues are ALU/latency bound (bias, GELU, hi/lo split, LayerNorm): 16 epilogue warps - four per
-// TMEM lane quarter, each owning a quarter of the tile's columns - keep four warps on every SM
-// sub-partition.  Bias / LayerNorm affine come through the read-only L1 path so that shared memory is
-// left for the operand ring and the 32 KB of transpose staging.
-constexpr int EPI_WARPS = 16;
+constexpr int EPI_WARPS = 8;                         // two warps per TMEM lane quarter
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;     // producer warp + MMA warp + epilogue warps
 constexpr int MAX_N = 1024;                          // bias staging capacity
 
@@ -166,7 +162,8 @@ struct TileCfg {
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator
   // bias[MAX_N] + gamma[256] + beta[256] + LN partials [2][2][128] + barriers
   static constexpr int STG_BYTES = EPI_WARPS * 2048;   // per-warp 32 rows x 64 B transpose buffer
-  static constexpr int AUX_BYTES = STG_BYTES + 256;    // staging (also LN partial sums) + barriers
+  // bias[MAX_N] + bias2[256] + gamma[256] + beta[256] + LN partials + staging + barriers
+  static constexpr int AUX_BYTES = MAX_N * 4 + 3 * 256 * 4 + 4 * 128 * 4 + 256 + STG_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;   // + alignment slack
 };
 
@@ -248,14 +245,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// x[i] = act(acc[i] * s + bias[i]) for one 32-column chunk; bias comes as float4 broadcast loads
-// through the read-only path (L1 resident).
+// x[i] = act(acc[i] * s + bias[i]) for one 32-column chunk; bias read as float4 broadcasts.
 template <int ACT>
-__device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&v)[32], const float* bias, float s) {
-  const float4* b4 = reinterpret_cast<const float4*>(bias);
+__device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&v)[32], const float* sb, float s) {
+  const float4* b4 = reinterpret_cast<const float4*>(sb);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float4 b = bias ? __ldg(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 b = b4[i];
     float x0 = fmaf(__uint_as_float(r[4 * i + 0]), s, b.x), x1 = fmaf(__uint_as_float(r[4 * i + 1]), s, b.y);
     float x2 = fmaf(__uint_as_float(r[4 * i + 2]), s, b.z), x3 = fmaf(__uint_as_float(r[4 * i + 3]), s, b.w);
     if (ACT == ACT_GELU) { x0 = gelu_fast(x0); x1 = gelu_fast(x1); x2 = gelu_fast(x2); x3 = gelu_fast(x3); }
@@ -291,7 +287,6 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the TMA/MMA main loop of tile i + 1.
 template <int BN>
-// 18 warps: one SM sub-partition hosts 5 of them, so ptxas caps registers at 16384 / (5 x 32) -> 96
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
@@ -304,8 +299,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
-  uint8_t* s_stage = aux;                                     // [EPI_WARPS][2048], 16B aligned
-  float* s_part = reinterpret_cast<float*>(s_stage);          // LN partial sums [2][4][128] alias the staging
+  float* s_bias = reinterpret_cast<float*>(aux);              // [MAX_N]
+  float* s_bias2 = s_bias + MAX_N;                            // [256] consumer GEMM bias (pair mode)
+  float* s_gamma = s_bias2 + 256;                             // [256]
+  float* s_beta = s_gamma + 256;                              // [256]
+  float* s_part = s_beta + 256;                               // [2 passes][2 halves][128 rows]
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_part + 4 * 128);   // [EPI_WARPS][2048], 16B aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + Cfg::STG_BYTES);
   // bars: full[S], empty[S], tmem_full[2], tmem_empty[2]
   uint64_t* bar_full = bars;
@@ -319,6 +318,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   // number of work items of this CTA
   const int nlocal = pair ? ((p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (p.n_tiles + 1)
                           : (p.m_tiles * p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const TcParams& pl = pair ? p2 : p;                         // the GEMM whose epilogue is the LayerNorm
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -335,6 +335,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.0f;
+    if (pl.ln)
+      for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) {
+        s_gamma[i] = pl.gamma[i]; s_beta[i] = pl.beta[i];
+        s_bias2[i] = (pair && p2.bias) ? p2.bias[i] : 0.0f;
+      }
   }
   pdl_trigger();               // let the next kernel's prologue overlap our tail
   tc_fence_before();
@@ -426,13 +434,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..17)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int qj = (warp - 2) >> 2;                  // which quarter of the tile's columns
+    const int hf = (warp - 2) >> 2;                  // which half of the tile's columns
     const int row = q * 32 + lane;
-    constexpr int QC = BN / 4;                       // columns per warp (64 or 32)
-    constexpr int CH = QC / 32;                      // 32-column chunks per warp
-    uint8_t* const stg = s_stage + (warp - 2) * 2048;
+    constexpr int CH = BN / 64;                      // 32-column chunks per warp
     uint32_t r[32];
     float v[32];
     int it = 0;
@@ -440,16 +446,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       const int as = it & 1;
       const WorkItem wi = decode_item(it, p, pair, BN);
       const TcParams& pp = wi.type ? p2 : p;
+      const float* const sb = wi.type ? s_bias2 : s_bias;
       const int m0 = wi.m0, n0 = wi.n0;
       const int m = m0 + row;
       const bool row_ok = m < pp.M;
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + qj * QC);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + hf * (BN / 2));
+      uint8_t* const stg = s_stage + (warp - 2) * 2048;
       const bool to_slot = pair && wi.type == 0;             // producer tile: write into the CTA's slot
       const int wrow0 = (to_slot ? wi.s0 : m0) + q * 32;     // first output row owned by this warp
       const int rows_valid = to_slot ? 32 : min(32, pp.M - wrow0);   // <= 0: nothing to write
-      mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
-      tc_fence_after();
       if (!pp.ln) {
+        mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
         int seq = 0, pos = m;
         if (row_ok && pp.in_group < pp.M) { seq = m / pp.in_group; pos = m - seq * pp.in_group; }
         const int64_t orow = (int64_t)seq * pp.out_group + pp.out_off + pos;
@@ -466,14 +474,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
 #pragma unroll 1
         for (int c = 0; c < ((p.dbg & 2) ? 0 : CH); ++c) {
           tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
-          const int nb = n0 + qj * QC + c * 32;
+          const int nb = n0 + hf * (BN / 2) + c * 32;
           if (fast && nb + 32 <= N) {               // warp-uniform branch: all lanes take part
-            const float* bptr = pp.bias ? pp.bias + nb : nullptr;
             switch (act) {                          // once per chunk
-              case ACT_NONE: epi_chunk_fast<ACT_NONE>(r, v, bptr, inv_scale); break;
-              case ACT_GELU: epi_chunk_fast<ACT_GELU>(r, v, bptr, inv_scale); break;
-              case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, bptr, inv_scale); break;
-              default:       epi_chunk_fast<ACT_SILU>(r, v, bptr, inv_scale); break;
+              case ACT_NONE: epi_chunk_fast<ACT_NONE>(r, v, sb + nb, inv_scale); break;
+              case ACT_GELU: epi_chunk_fast<ACT_GELU>(r, v, sb + nb, inv_scale); break;
+              case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, sb + nb, inv_scale); break;
+              default:       epi_chunk_fast<ACT_SILU>(r, v, sb + nb, inv_scale); break;
             }
             uint32_t ph[16], pl[16];
             pack_split(v, ph, pl);
@@ -484,33 +491,35 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
             }
           } else if (row_ok && nb < N) {
             const bool full = nb + 32 <= N;
+            {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float x = __uint_as_float(r[i]) * inv_scale + (pp.bias ? __ldg(pp.bias + min(nb + i, N - 1)) : 0.0f);
-              if (tab && (full || nb + i < N)) x += tab[nb + i];
-              x = apply_act(x, act);
-              v[i] = zero ? 0.0f : x;
-            }
-            if (ohi) {
-              const int64_t o = obase + nb;
-              if (full) {
-                store_split_chunk(v, ohi + o, olo + o);
-              } else {
+              for (int i = 0; i < 32; ++i) {
+                float x = __uint_as_float(r[i]) * inv_scale + sb[min(nb + i, MAX_N - 1)];
+                if (tab && (full || nb + i < N)) x += tab[nb + i];
+                x = apply_act(x, act);
+                v[i] = zero ? 0.0f : x;
+              }
+              if (ohi) {
+                const int64_t o = obase + nb;
+                if (full) {
+                  store_split_chunk(v, ohi + o, olo + o);
+                } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  if (nb + i < N) {
-                    __half h, l;
-                    split_f32(v[i], h, l);
-                    ohi[o + i] = h; olo[o + i] = l;
+                  for (int i = 0; i < 32; ++i) {
+                    if (nb + i < N) {
+                      __half h, l;
+                      split_f32(v[i], h, l);
+                      ohi[o + i] = h; olo[o + i] = l;
+                    }
                   }
                 }
               }
-            }
-            if (pp.out_f32) {
-              float* dst = pp.out_f32 + orow * pp.ldc + nb;
+              if (pp.out_f32) {
+                float* dst = pp.out_f32 + orow * pp.ldc + nb;
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (full || nb + i < N) dst[i] = v[i];
+                for (int i = 0; i < 32; ++i)
+                  if (full || nb + i < N) dst[i] = v[i];
+              }
             }
           }
           __syncwarp();
@@ -520,43 +529,57 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           __syncwarp();
           if (lane == 0) atomicAdd(pc.cnt + blockIdx.x, 1);
         }
-      } else if (p.dbg & 32) {
-        // timing experiment: no LayerNorm epilogue work
       } else {
         // x = acc*s + bias + residual (+ rowvec); y = LayerNorm(x) over the 256-wide row, eps 1e-5.
-        // Four warps share a row (column quarters) and exchange partial sums through shared memory;
-        // the pre-norm row is parked in TMEM between the statistics pass and the normalise pass.
-        // One-pass statistics with a per-row shift K (the row's first residual value) so that
-        // var = E[(x-K)^2] - E[x-K]^2 does not cancel.
+        // Two warps share a row (column halves) and exchange partial sums through shared memory; the
+        // pre-norm row is parked in TMEM between the statistics pass and the normalise pass.
+        // Statistics in one pass with a per-row shift K (the row's first residual value) so that
+        // var = E[(x-K)^2] - E[x-K]^2 does not cancel.  The residual chunk c+1 is fetched while
+        // chunk c is processed (the loop is fully unrolled), chunk 0 before the accumulator is ready.
+        if (p.dbg & 32) {                          // timing experiment: no LayerNorm epilogue work
+          mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
+          tc_fence_after();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
+          continue;
+        }
         const float* rv = (row_ok && pp.rowvec) ? pp.rowvec + (int64_t)(m / pp.rv_group) * BN : nullptr;
-        const int cb = qj * QC;
+        const int cb = hf * (BN / 2);
         const bool has_res = pp.res_hi != nullptr;                       // warp-uniform
         const float shiftK = (has_res && row_ok) ? join_f32(pp.res_hi[(int64_t)m * pp.ld_res], pp.res_lo[(int64_t)m * pp.ld_res]) : 0.0f;
-        const __half* rbh = pp.res_hi + (int64_t)wrow0 * pp.ld_res + cb;   // this warp's 32 rows, its column quarter
+        const __half* rbh = pp.res_hi + (int64_t)wrow0 * pp.ld_res + cb;   // this warp's 32 rows, its column half
         const __half* rbl = pp.res_lo + (int64_t)wrow0 * pp.ld_res + cb;
+        uint4 gh[4], gl[4];                       // residual chunk in the coalesced (4 lanes per row) pattern
+        if (has_res) {
+          load_plane_issue(rbh, pp.ld_res, rows_valid, lane, gh);
+          load_plane_issue(rbl, pp.ld_res, rows_valid, lane, gl);
+        }
+        mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
+        tc_fence_after();
         float s1 = 0.0f, s2 = 0.0f;
         const float sc = pp.inv_scale;
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < CH; ++c) {
-          uint4 rh[4], rl[4];                     // residual chunk, row-owner layout
+          uint4 rh[4], rl[4];                     // the same chunk, row-owner layout
           if (has_res) {
-            uint4 g4[4];
-            load_plane_issue(rbh + c * 32, pp.ld_res, rows_valid, lane, g4);
-            plane_to_rows(stg, g4, lane, rh);
-            load_plane_issue(rbl + c * 32, pp.ld_res, rows_valid, lane, g4);
-            plane_to_rows(stg, g4, lane, rl);
+            plane_to_rows(stg, gh, lane, rh);
+            plane_to_rows(stg, gl, lane, rl);
+            if (c + 1 < CH) {                     // fetch the next chunk under this one's math
+              load_plane_issue(rbh + (c + 1) * 32, pp.ld_res, rows_valid, lane, gh);
+              load_plane_issue(rbl + (c + 1) * 32, pp.ld_res, rows_valid, lane, gl);
+            }
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
           }
           tmem_ld32(trow + c * 32, r);
-          const float4* bch = reinterpret_cast<const float4*>(pp.bias + cb + c * 32);
+          const float* bch = sb + cb + c * 32;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const uint32_t ah[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
             const uint32_t al[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
-            const float4 b0 = pp.bias ? __ldg(bch + 2 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 b1 = pp.bias ? __ldg(bch + 2 * i + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b0 = reinterpret_cast<const float4*>(bch)[2 * i], b1 = reinterpret_cast<const float4*>(bch)[2 * i + 1];
             const float bia[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -575,24 +598,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           }
           tmem_st32(trow + c * 32, r);
         }
-        epi_bar_sync();                           // every warp is done with its staging tile (pass 1)
-        s_part[qj * 128 + row] = s1;              // the partial sums live in the (now idle) staging area
-        s_part[512 + qj * 128 + row] = s2;
+        s_part[hf * 128 + row] = s1;
+        s_part[256 + hf * 128 + row] = s2;
         epi_bar_sync();
-        const float e1 = ((s_part[row] + s_part[128 + row]) + (s_part[256 + row] + s_part[384 + row])) * (1.0f / BN);
-        const float e2 = ((s_part[512 + row] + s_part[640 + row]) + (s_part[768 + row] + s_part[896 + row])) * (1.0f / BN);
-        epi_bar_sync();                           // all partials read: the staging area may be reused
+        const float e1 = (s_part[row] + s_part[128 + row]) * (1.0f / BN);
+        const float e2 = (s_part[256 + row] + s_part[256 + 128 + row]) * (1.0f / BN);
         const float mean = shiftK + e1;
         const float rstd = rsqrtf(fmaxf(e2 - e1 * e1, 0.0f) + 1e-5f);
 #pragma unroll 1
         for (int c = 0; c < CH; ++c) {
           tmem_ld32(trow + c * 32, r);
           {
-            const float4* g4 = reinterpret_cast<const float4*>(pp.gamma + cb + c * 32);
-            const float4* e4 = reinterpret_cast<const float4*>(pp.beta + cb + c * 32);
+            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + cb + c * 32);
+            const float4* e4 = reinterpret_cast<const float4*>(s_beta + cb + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 gg = __ldg(g4 + i), bb = __ldg(e4 + i);
+              const float4 gg = g4[i], bb = e4[i];
               v[4 * i + 0] = fmaf((__uint_as_float(r[4 * i + 0]) - mean) * rstd, gg.x, bb.x);
               v[4 * i + 1] = fmaf((__uint_as_float(r[4 * i + 1]) - mean) * rstd, gg.y, bb.y);
               v[4 * i + 2] = fmaf((__uint_as_float(r[4 * i + 2]) - mean) * rstd, gg.z, bb.z);
@@ -605,6 +626,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           store_plane_coalesced(stg, ph, pp.out_hi + o, pp.ld_out, rows_valid, lane);
           store_plane_coalesced(stg, pl, pp.out_lo + o, pp.ld_out, rows_valid, lane);
         }
+        // the partial sums of this tile may be overwritten only after everyone has read them
+        epi_bar_sync();
       }
       // this warp is done reading the accumulator stage: hand it back to the MMA warp
       tc_fence_before();

@@ -74,3 +74,26 @@ def test_whole_path_tc_equals_cuda_core_path(built_lib):
     assert _rel(a["latents"], b["latents"]) < 1e-4
     assert _rel(a["joints"], b["joints"]) < 1e-4
     assert l_tc > 0
+
+
+def test_scheduling_options_do_not_change_results(built_lib):
+    """Engine scheduling options only reorder independent work: the fused FFN pair launch (one
+    persistent kernel running FFN1 -> FFN2 chains per CTA), the L2-sized producer/consumer chunking
+    and the sequence chunking must give bit-identical motions."""
+    from mld_b200 import synth
+    from mld_b200.engine import Engine, make_config
+    eng = Engine(make_config(), 0)
+    eng.load_state_dict(synth.denoiser_state_dict(1234), "denoiser.")
+    eng.load_state_dict(synth.mld_vae_state_dict(4321), "vae.")
+    eng.finalize()
+    eng.set_mean_std(*synth.mean_std())
+    eng.set_timesteps(4)
+    B = 300                                   # 600 sequences x 79 tokens = 371 m-tiles: > 2 waves + ragged tail
+    ctx, noise = synth.text_context(B, 77, seed=15), synth.init_noise(B, seed=16)
+    lengths = [196] * B
+    base = eng.sample(ctx, noise, lengths, want=("latents",))["latents"].clone()
+    for name, value in (("ffn_pair", "1"), ("pair_chunk", "1"), ("chunk", "96")):
+        eng.set_option(name, value)
+        out = eng.sample(ctx, noise, lengths, want=("latents",))["latents"]
+        assert torch.equal(out, base), f"option {name}={value} changed the result"
+        eng.set_option(name, "0")

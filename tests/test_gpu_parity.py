@@ -273,3 +273,31 @@ def test_novae_ddpm_loop_vs_oracle(novae):
     zo = O.diffusion_reverse(nsd, cfg, O.DDPMScheduler(), steps, ctx, x0, lengths, step_noise=nz)
     assert z.shape == (T, B, 263)
     assert _rel(z, zo) < 1e-3
+
+
+# ------------------------------------------------------------------ action-to-motion (BASELINE configs[3] shape)
+def test_action_to_motion_loop_vs_oracle(built_lib):
+    """15-layer action-conditioned denoiser (EmbedAction, uncond half zeroed) + ActorVae decoder,
+    50 guided DDIM steps, against the oracle."""
+    from mld_b200.engine import Engine, make_config
+    asd = synth.denoiser_state_dict(seed=2345, condition="action", num_layers=15, nclasses=12, nfeats=150)
+    avsd = synth.actor_vae_state_dict(seed=777)
+    eng = Engine(make_config(condition="action", num_layers=15, nclasses=12, nfeats=150, vae="actor",
+                             vae_layers=6, vae_nfeats=150), 0)
+    eng.load_state_dict(asd, "denoiser.")
+    eng.load_state_dict(avsd, "vae.")
+    eng.finalize()
+    eng.set_timesteps(50)
+    B, lengths = 5, [60, 60, 44, 60, 20]
+    g = torch.Generator().manual_seed(91)
+    actions = torch.randint(0, 12, (B, 1), generator=g)
+    cond = torch.cat([torch.zeros_like(actions), actions])            # mld.py:716-717
+    noise = synth.init_noise(B, seed=92)
+    out = eng.sample(cond, noise, lengths, want=("latents", "feats"))
+    acfg = O.DenoiserCfg(condition="action", num_layers=15, nclasses=12, nfeats=150)
+    zo = O.diffusion_reverse(asd, acfg, O.DDIMScheduler(), 50, cond, noise, lengths)
+    fo = O.vae_decode(avsd, O.VaeCfg(kind="actor", nfeats=150, num_layers=6), zo, lengths)
+    assert out["feats"].shape == (B, 60, 150)
+    assert _rel(out["latents"], zo) < 1e-3
+    assert _rel(out["feats"], fo) < 1e-3
+    assert float(out["feats"][4, 20:].abs().max()) == 0.0

@@ -58,15 +58,29 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 #ifdef __CUDACC__
 extern int g_mldb_pdl;   // 1 = launch the step-loop kernels with the PDL attribute (MLDB_PDL=0 disables)
 template <typename... KArgs, typename... Args>
-static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                              Args&&... args) {
+static inline void launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      int cluster, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = g_mldb_pdl ? 1 : 0;
+  cudaLaunchAttribute at[2];
+  int n = 0;
+  if (g_mldb_pdl) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = (unsigned)cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
   cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  launch_pdl_cluster(kernel, grid, block, smem, st, 1, static_cast<Args&&>(args)...);
 }
 #endif
 

@@ -60,6 +60,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset of every CTA in `mask` and
+// completes `bytes` on the mbarrier at the same offset of each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -88,6 +107,11 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// commit that arrives on the mbarrier at the same offset of every CTA in `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -261,13 +285,15 @@ __device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&
   }
 }
 
-// j-th work item of this CTA
-__device__ __forceinline__ WorkItem decode_item(int j, const TcParams& p, int pair, int bn) {
+// j-th work item of this CTA.  Single-GEMM mode: clusters of `cl` CTAs walk (m-group, n) items in
+// lockstep - CTA rank r of a cluster takes m-tile mg*cl + r - so that the W tile of an item is
+// fetched once per cluster (TMA multicast) instead of once per CTA.
+__device__ __forceinline__ WorkItem decode_item(int j, const TcParams& p, int pair, int bn, int cl, int rank) {
   WorkItem it;
   it.s0 = blockIdx.x * BM;
   if (!pair) {
-    const int t = blockIdx.x + j * gridDim.x;
-    it.type = 0; it.m0 = (t / p.n_tiles) * BM; it.n0 = (t % p.n_tiles) * bn;
+    const int t = (int)blockIdx.x / cl + j * ((int)gridDim.x / cl);
+    it.type = 0; it.m0 = ((t / p.n_tiles) * cl + rank) * BM; it.n0 = (t % p.n_tiles) * bn;
     return it;
   }
   const int per = p.n_tiles + 1;
@@ -286,7 +312,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 // Persistent: CTA c walks tiles c, c + gridDim.x, ...; tile t -> (m = t / n_tiles, n = t % n_tiles).
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the TMA/MMA main loop of tile i + 1.
-template <int BN>
+template <int BN, int CL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
@@ -316,14 +342,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool pair = pc.on != 0;
   // number of work items of this CTA
+  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
+  const int ncl = (int)gridDim.x / CL, cid = (int)blockIdx.x / CL;          // clusters, this CTA's cluster
+  const int ngroups = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;               // (m-group, n) items
   const int nlocal = pair ? ((p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (p.n_tiles + 1)
-                          : (p.m_tiles * p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+                          : (ngroups - cid + ncl - 1) / ncl;
   const TcParams& pl = pair ? p2 : p;                         // the GEMM whose epilogue is the LayerNorm
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), CL);              // one MMA-commit arrival per CTA of the cluster
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tfull[s]), 1);
@@ -347,6 +377,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   pdl_trigger();               // let the next kernel's prologue overlap our tail
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                  // everything below touches activations of the previous kernel
@@ -356,7 +387,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       // ---------------------------------------------------------------- TMA producer
       int kbg = 0;                                   // k-block counter across tiles (ring position)
       for (int j = 0; j < nlocal; ++j) {
-        const WorkItem wi = decode_item(j, p, pair, BN);
+        const WorkItem wi = decode_item(j, p, pair, BN, CL, rank);
         const TcParams& q = wi.type ? p2 : p;
         const int m0 = wi.m0, n0 = wi.n0;
         if (wi.type) {
@@ -393,8 +424,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
               tma_load_2d(sAh, &tmA2h, full, (kb - q.kb1) * BK, m0);
               tma_load_2d(sAl, &tmA2l, full, (kb - q.kb1) * BK, m0);
             }
-            tma_load_2d(sWh, &tmWh, full, kb * BK, n0);
-            tma_load_2d(sWl, &tmWl, full, kb * BK, n0);
+            if (CL == 1) {
+              tma_load_2d(sWh, &tmWh, full, kb * BK, n0);
+              tma_load_2d(sWl, &tmWl, full, kb * BK, n0);
+            } else {
+              // this CTA fetches rows [rank*BN/CL, (rank+1)*BN/CL) of the W tile for the whole cluster
+              constexpr int SL = BN / CL;
+              tma_load_2d_mc(sWh + rank * SL * 128, &tmWh, full, kb * BK, n0 + rank * SL, MC_MASK);
+              tma_load_2d_mc(sWl + rank * SL * 128, &tmWl, full, kb * BK, n0 + rank * SL, MC_MASK);
+            }
           }
         }
       }
@@ -409,7 +447,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         mbar_wait(smem_u32(&bar_tempty[as]), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained it
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
-        const int nkb = decode_item(it, p, pair, BN).type ? p2.kblocks : p.kblocks;
+        const int nkb = decode_item(it, p, pair, BN, CL, rank).type ? p2.kblocks : p.kblocks;
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
           const int s = kbg % STAGES;
           const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
@@ -428,7 +466,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
               umma(tacc, ah, wh, idesc, 1u);
             }
           }
-          umma_commit(smem_u32(&bar_empty[s]));      // frees the stage when these MMAs retire
+          if (CL == 1) umma_commit(smem_u32(&bar_empty[s]));      // frees the stage when these MMAs retire
+          else umma_commit_mc(smem_u32(&bar_empty[s]), MC_MASK);  // ... in every CTA of the cluster
         }
         umma_commit(smem_u32(&bar_tfull[as]));       // accumulator complete
       }
@@ -444,7 +483,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     int it = 0;
     for (; it < nlocal; ++it) {
       const int as = it & 1;
-      const WorkItem wi = decode_item(it, p, pair, BN);
+      const WorkItem wi = decode_item(it, p, pair, BN, CL, rank);
       const TcParams& pp = wi.type ? p2 : p;
       const float* const sb = wi.type ? s_bias2 : s_bias;
       const int m0 = wi.m0, n0 = wi.n0;
@@ -637,6 +676,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // nobody exits while a peer may still signal its barriers / write its smem
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
@@ -654,6 +694,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 static int g_force_bn = 0;   // MLDB_TC_BN=128: experiment knob (3-stage BN=128 tiles everywhere)
 
 struct TcCtx {
+  int cluster = 1;   // CTAs per cluster sharing one multicast W tile (1, 2 or 4)
   int dbg = 0;
   int device = 0;
   int sm_count = 148;
@@ -675,10 +716,15 @@ TcCtx* tc_create(int device) {
   c->encode = (PFN_tmapEncodeTiled)fn;
   if (const char* e = getenv("MLDB_TC_DBG")) c->dbg = atoi(e);
   if (const char* e = getenv("MLDB_TC_BN")) g_force_bn = atoi(e);
+  if (const char* e = getenv("MLDB_TC_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->cluster = v; }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
-  e = cudaFuncSetAttribute(k_gemm_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<256>::SMEM_BYTES);
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(k_gemm_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<128>::SMEM_BYTES);
+  e = cudaSuccess;
+  auto opt_in = [&](auto kernel, int bytes) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  };
+  opt_in(k_gemm_tc<256, 1>, TileCfg<256>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1>, TileCfg<128>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 2>, TileCfg<256>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2>, TileCfg<128>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 4>, TileCfg<256>::SMEM_BYTES); opt_in(k_gemm_tc<128, 4>, TileCfg<128>::SMEM_BYTES);
   if (e != cudaSuccess) {
     mldb_set_err(std::string("cudaFuncSetAttribute(k_gemm_tc): ") + cudaGetErrorString(e));
     delete c;
@@ -750,7 +796,11 @@ void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   bool ok = make_map(c, &mA1h, g.a1.hi, g.M, g.K1, BM) && make_map(c, &mA1l, g.a1.lo(), g.M, g.K1, BM);
   if (g.K2 > 0) ok = ok && make_map(c, &mA2h, g.a2.hi, g.M, g.K2, BM) && make_map(c, &mA2l, g.a2.lo(), g.M, g.K2, BM);
   else { mA2h = mA1h; mA2l = mA1l; }
-  ok = ok && make_map(c, &mWh, g.w.w, g.w.N, g.w.K, bn) && make_map(c, &mWl, g.w.w + g.w.plane_stride, g.w.N, g.w.K, bn);
+  const int m_tiles_ = (g.M + BM - 1) / BM;
+  int cl = c->cluster;
+  while (cl > 1 && (m_tiles_ < 2 * cl || c->sm_count % cl)) cl >>= 1;     // small problems: no cluster
+  ok = ok && make_map(c, &mWh, g.w.w, g.w.N, g.w.K, bn / cl) &&
+       make_map(c, &mWl, g.w.w + g.w.plane_stride, g.w.N, g.w.K, bn / cl);
   if (!ok) {
     fprintf(stderr, "libmldb200: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)\n", g.M, g.w.N, g.w.K);
     c->ok = false;
@@ -759,14 +809,15 @@ void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   TcParams p, p2{};
   fill_params(c, g, ln, bn, &p);
   const PairCfg pc{0, nullptr};
-  const int ntiles = p.m_tiles * p.n_tiles;
-  dim3 grid(ntiles < c->sm_count ? ntiles : c->sm_count);
-  if (bn == 256)
-    launch_pdl(k_gemm_tc<256>, grid, dim3(NUM_THREADS), TileCfg<256>::SMEM_BYTES, st, mA1h, mA1l, mA2h, mA2l, mWh, mWl,
-               mA1h, mA1l, mWh, mWl, p, p2, pc);
-  else
-    launch_pdl(k_gemm_tc<128>, grid, dim3(NUM_THREADS), TileCfg<128>::SMEM_BYTES, st, mA1h, mA1l, mA2h, mA2l, mWh, mWl,
-               mA1h, mA1l, mWh, mWl, p, p2, pc);
+  const int ngroups = ((p.m_tiles + cl - 1) / cl) * p.n_tiles;
+  const int ncl = ngroups < c->sm_count / cl ? ngroups : c->sm_count / cl;
+  dim3 grid(ncl * cl);
+#define MLDB_LAUNCH(BN_, CL_)                                                                              \
+  launch_pdl_cluster(k_gemm_tc<BN_, CL_>, grid, dim3(NUM_THREADS), TileCfg<BN_>::SMEM_BYTES, st, CL_, mA1h, \
+                     mA1l, mA2h, mA2l, mWh, mWl, mA1h, mA1l, mWh, mWl, p, p2, pc)
+  if (bn == 256) { if (cl == 4) MLDB_LAUNCH(256, 4); else if (cl == 2) MLDB_LAUNCH(256, 2); else MLDB_LAUNCH(256, 1); }
+  else           { if (cl == 4) MLDB_LAUNCH(128, 4); else if (cl == 2) MLDB_LAUNCH(128, 2); else MLDB_LAUNCH(128, 1); }
+#undef MLDB_LAUNCH
 }
 
 // Producer GEMM g1 (plain epilogue, N a multiple of 256, e.g. FFN1+GELU) and consumer GEMM g2
@@ -799,6 +850,6 @@ void tc_gemm_pair(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs
   fill_params(c, g1, nullptr, 256, &p);
   fill_params(c, g2, &l2, 256, &p2);
   const PairCfg pc{1, counters};
-  launch_pdl(k_gemm_tc<256>, dim3(grid), dim3(NUM_THREADS), TileCfg<256>::SMEM_BYTES, st, mAh, mAl, mAh, mAl, mWh, mWl,
+  launch_pdl(k_gemm_tc<256, 1>, dim3(grid), dim3(NUM_THREADS), TileCfg<256>::SMEM_BYTES, st, mAh, mAl, mAh, mAl, mWh, mWl,
              mBh, mBl, mVh, mVl, p, p2, pc);
 }

@@ -30,6 +30,8 @@ CASES = [
     (392, 263, 256, 0, 0, False),       # final layer: N not a tile multiple (TMA zero fill)
     (129, 512, 256, 0, 2, False),       # kv projection, ReLU epilogue variant
     (4096, 1024, 256, 0, 3, False),     # many tiles, SiLU
+    (1300, 256, 1024, 0, 0, True),      # 11 m-tiles: cluster groups with an out-of-range m-tile, LN epilogue
+    (1100, 263, 512, 256, 0, False),    # clusters + ragged N + two A sources
 ]
 
 

@@ -203,6 +203,14 @@ int mldb_debug_gemm(mldb_handle* h, const float* A, const float* W, const float*
                     const float* beta, const float* R, int32_t M, int32_t N, int32_t K, int32_t K1,
                     int32_t act, int32_t use_tc, float* out, void* stream);
 
+/* Debug aid: one post-norm FFN block y = LayerNorm(x + W2 gelu(W1 x + b1) + b2) through the engine's
+ * operators (cross_attention.py:266-271).  mode 0 = CUDA-core kernels, 1 = tcgen05 GEMMs as two
+ * launches, 2 = the fused tcgen05 FFN kernel.  X, out [M,d]: fp32 DEVICE; W1 [ff,d], W2 [d,ff],
+ * b1 [ff], b2/gamma/beta [d]: fp32 HOST.  Synchronous. */
+int mldb_debug_ffn(mldb_handle* h, const float* X, const float* W1, const float* b1, const float* W2,
+                   const float* b2, const float* gamma, const float* beta, int32_t M, int32_t d, int32_t ff,
+                   int32_t mode, float* out, void* stream);
+
 /* Introspection */
 const char* mldb_last_error(void);
 int mldb_abi_version(void);

@@ -411,6 +411,22 @@ struct SeqInfo {
 static inline ActBuf rows_of(ActBuf b, int64_t row0, int rows) {
   b.hi += row0 * b.cols; b.rows = rows; return b;
 }
+// the workspace rows of sequences [s0, s0 + n): a self-contained workspace for that sub-batch
+static StackWs ws_slice(const StackWs& ws, int s0, int n) {
+  StackWs w = ws;
+  w.nseq = n; w.M = n * ws.L;
+  auto tok = [&](ActBuf b) { return b.hi ? rows_of(b, (int64_t)s0 * ws.L, n * ws.L) : b; };
+  auto sel = [&](ActBuf b) { return b.hi ? rows_of(b, (int64_t)s0 * ws.n_sel, n * ws.n_sel) : b; };
+  w.x0 = tok(ws.x0); w.cur[0] = tok(ws.cur[0]); w.cur[1] = tok(ws.cur[1]); w.x1 = tok(ws.x1); w.x2 = tok(ws.x2);
+  w.att = tok(ws.att); w.qkv = tok(ws.qkv); w.qc = tok(ws.qc); w.h = tok(ws.h); w.cat = tok(ws.cat);
+  for (auto& y : w.ys) y = tok(y);
+  if (ws.kvm.hi) w.kvm = rows_of(ws.kvm, (int64_t)s0 * ws.Lmem, n * ws.Lmem);
+  if (ws.vrow.hi) w.vrow = rows_of(ws.vrow, s0, n);
+  if (ws.cvec) w.cvec = ws.cvec + (size_t)s0 * ws.d;
+  if (ws.cf32) w.cf32 = ws.cf32 + (size_t)s0 * ws.L * ws.d;
+  w.sx = sel(ws.sx); w.sq = sel(ws.sq); w.satt = sel(ws.satt); w.sx1 = sel(ws.sx1); w.sh = sel(ws.sh); w.sout = sel(ws.sout);
+  return w;
+}
 // Producer -> consumer pairs whose intermediate is larger than L2 at full batch (qkv: 124 MB,
 // FFN hidden: 166 MB) run over row chunks that REUSE one chunk-sized intermediate buffer: the
 // consumer kernel then reads it from L2 and the dirty lines are overwritten in place by the next
@@ -455,6 +471,12 @@ static void ffn_block(mldb_handle* h, const LinW& l1, const LinW& l2, const LnW&
     GemmArgs g2; g2.a1 = hb; g2.K1 = ws.ff; g2.M = rows; g2.w = l2;
     LnArgs l; l.res = rows_of(xin, r0, rows); l.gamma = n.g; l.beta = n.b; l.M = rows; l.d = ws.d;
     l.out = rows_of(xout, r0, rows);
+    if (h->use_tc && tc_ffn_supported(h->tc, g, g2, l)) {
+      // one launch: the hidden activations stay in shared memory / TMEM (gemm_tc.cu k_ffn_tc)
+      tc_ffn(h->tc, g, g2, l, st);
+      count_launch(h);
+      continue;
+    }
     if (h->use_tc && h->ffn_pair && (rows % wave_rows == 0 || ws.M <= wave_rows) &&
         rows <= 128 * MLDB_PAIR_MAX_TILES && tc_gemm_pair_supported(h->tc, g, g2, l)) {
       // FFN1 and FFN2 as one persistent launch: the hidden activations are consumed from L2
@@ -546,9 +568,14 @@ static ActBuf enc_layer_selected(mldb_handle* h, const StackW& sw, const EncW& w
   LnArgs l1; l1.res = ws.sx; l1.gamma = w.n1.g; l1.beta = w.n1.b; l1.M = R; l1.d = d; l1.out = ws.sx1;
   op_gemm_ln(h, go, l1, ws.cf32, st);
   GemmArgs g1; g1.a1 = ws.sx1; g1.K1 = d; g1.M = R; g1.w = w.l1; g1.act = ACT_GELU; g1.out = ws.sh;
-  op_gemm(h, g1, st);
   GemmArgs g2; g2.a1 = ws.sh; g2.K1 = ws.ff; g2.M = R; g2.w = w.l2;
   LnArgs l2; l2.res = ws.sx1; l2.gamma = w.n2.g; l2.beta = w.n2.b; l2.M = R; l2.d = d; l2.out = ws.sout;
+  if (h->use_tc && tc_ffn_supported(h->tc, g1, g2, l2)) {
+    tc_ffn(h->tc, g1, g2, l2, st);
+    count_launch(h);
+    return ws.sout;
+  }
+  op_gemm(h, g1, st);
   op_gemm_ln(h, g2, l2, ws.cf32, st);
   return ws.sout;
 }
@@ -625,6 +652,14 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   if (env) h->chunk_seqs = atoi(env);
   env = getenv("MLDB_GRAPH");
   if (env && !strcmp(env, "0")) h->use_graph = false;
+  env = getenv("MLDB_BRANCHES");
+  if (env) h->branches = std::min(std::max(atoi(env), 1), (int)mldb_handle::MAX_BRANCHES);
+  e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+  for (int i = 0; i < mldb_handle::MAX_BRANCHES - 1 && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&h->br_stream[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) { mldb_destroy(h); FAIL(MLDB_ERR_CUDA, "branch streams: %s", cudaGetErrorString(e)); }
   *out = h;
   return MLDB_OK;
 }
@@ -639,6 +674,11 @@ extern "C" void mldb_destroy(mldb_handle* h) {
   }
   for (void* p : h->allocs) cudaFree(p);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  for (int i = 0; i < mldb_handle::MAX_BRANCHES - 1; ++i) {
+    if (h->br_stream[i]) cudaStreamDestroy(h->br_stream[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   tc_destroy(h->tc);
   delete h;
 }
@@ -649,12 +689,16 @@ extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* val
     if (!strcmp(value, "tc")) h->use_tc = true;
     else if (!strcmp(value, "simt")) h->use_tc = false;
     else FAIL(MLDB_ERR_INVALID, "gemm must be tc|simt");
+  } else if (!strcmp(name, "ffn_fused")) {
+    tc_set_ffn_fused(h->tc, atoi(value) != 0);
   } else if (!strcmp(name, "ffn_pair")) {
     h->ffn_pair = atoi(value) != 0;
   } else if (!strcmp(name, "pair_chunk")) {
     h->pair_chunk = atoi(value) != 0;
   } else if (!strcmp(name, "chunk")) {
     h->chunk_seqs = atoi(value);
+  } else if (!strcmp(name, "branches")) {
+    h->branches = std::min(std::max(atoi(value), 1), (int)mldb_handle::MAX_BRANCHES);
   } else if (!strcmp(name, "graph")) {
     h->use_graph = strcmp(value, "0") != 0;
   } else {
@@ -977,18 +1021,35 @@ static void denoiser_pass(mldb_handle* h, Plan* p, const float* latents, int lat
   // 126 MB L2 from the kernel that writes them to the kernel that reads them instead of streaming
   // through HBM (~870 MB per layer for the whole 40 448-token batch).
   const int cs = (h->chunk_seqs > 0 && h->chunk_seqs < p->Bx) ? h->chunk_seqs : p->Bx;
-  for (int s0 = 0; s0 < p->Bx; s0 += cs) {
-    const int n = std::min(cs, p->Bx - s0);
-    StackWs w = p->ws;
-    w.nseq = n; w.M = n * p->Ntok;
-    ActBuf x0v = p->ws.x0;
-    x0v.hi += (int64_t)s0 * p->Ntok * x0v.cols; x0v.rows = w.M;
-    ActBuf x = run_stack(h, h->den, x0v, ActBuf{}, w, si, st);
+  auto run_range = [&](const StackWs& wsv, int s0, int n, cudaStream_t s) {
+    StackWs w = wsv;
+    ActBuf x = run_stack(h, h->den, w.x0, ActBuf{}, w, si, s);
     // encoder.norm on the latent tokens only (cross_attention.py:62-63, mld_denoiser.py:206)
     LnArgs l; l.res = x; l.gamma = h->den.norm.g; l.beta = h->den.norm.b; l.M = n * c.n_lat; l.d = d;
     if (w.n_sel == 0) { l.sel_group = c.n_lat; l.in_group = p->Ntok; }   // else x is already compact
     l.out_f32 = eps_out + (size_t)s0 * c.n_lat * d; l.ld_out = d;
-    op_ln(h, l, st);
+    op_ln(h, l, s);
+  };
+  const int nbr = (cs == p->Bx && h->branches > 1 && p->Bx * p->Ntok >= 2 * 128 * h->branches) ? h->branches : 1;
+  if (nbr > 1) {
+    // fork: every range waits for the token assembly; join: the caller's stream waits for every range
+    cudaEventRecord(h->ev_fork, st);
+    for (int k = 0; k < nbr; ++k) {
+      cudaStream_t s = k == 0 ? st : h->br_stream[k - 1];
+      if (k) cudaStreamWaitEvent(s, h->ev_fork, 0);
+      const int s0 = (int)((int64_t)p->Bx * k / nbr), s1 = (int)((int64_t)p->Bx * (k + 1) / nbr);
+      run_range(ws_slice(p->ws, s0, s1 - s0), s0, s1 - s0, s);
+      if (k) cudaEventRecord(h->ev_join[k - 1], s);
+    }
+    for (int k = 1; k < nbr; ++k) cudaStreamWaitEvent(st, h->ev_join[k - 1], 0);
+    return;
+  }
+  for (int s0 = 0; s0 < p->Bx; s0 += cs) {
+    const int n = std::min(cs, p->Bx - s0);
+    StackWs w = p->ws;                                   // every chunk reuses the first rows
+    w.nseq = n; w.M = n * p->Ntok;
+    w.x0 = rows_of(p->ws.x0, (int64_t)s0 * p->Ntok, w.M);
+    run_range(w, s0, n, st);
   }
 }
 
@@ -1501,4 +1562,40 @@ extern "C" int mldb_debug_gemm(mldb_handle* h, const float* A, const float* W, c
   while (h->allocs.size() > n_alloc0) { cudaFree(h->allocs.back()); h->allocs.pop_back(); }
   if (e != cudaSuccess) FAIL(MLDB_ERR_CUDA, "debug gemm: %s", cudaGetErrorString(e));
   return rc;
+}
+
+extern "C" int mldb_debug_ffn(mldb_handle* h, const float* X, const float* W1, const float* b1, const float* W2,
+                              const float* b2, const float* gamma, const float* beta, int32_t M, int32_t d,
+                              int32_t ff, int32_t mode, float* out, void* stream) {
+  if (!h || !X || !W1 || !W2 || !gamma || !beta || !out || M <= 0 || d <= 0 || ff <= 0)
+    FAIL(MLDB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_alloc0 = h->allocs.size();
+  LinW l1, l2;
+  LnW n;
+  TRY(pack_linear(h, W1, ff, d, b1, &l1));
+  TRY(pack_linear(h, W2, d, ff, b2, &l2));
+  TRY(upload_f32(h, gamma, d, &n.g));
+  TRY(upload_f32(h, beta, d, &n.b));
+  StackWs ws;
+  ws.M = M; ws.d = d; ws.ff = ff;
+  ActBuf x, o;
+  TRY(alloc_act(h, M, d, &x));
+  TRY(alloc_act(h, M, d, &o));
+  TRY(alloc_act(h, M, ff, &ws.h));
+  TRY(dev_alloc(h, (void**)&ws.cf32, (size_t)M * d * sizeof(float)));
+  k_rows_to_split<<<nblk((int64_t)M * d), 256, 0, st>>>(x, X, d, M, d, 1 << 30, 0, 0, 0, nullptr);
+  const bool saved = h->use_tc;
+  h->use_tc = mode != 0;
+  const int saved_fused = tc_set_ffn_fused(h->tc, mode == 2);
+  ffn_block(h, l1, l2, n, x, o, ws, ACT_GELU, st);
+  h->use_tc = saved;
+  tc_set_ffn_fused(h->tc, saved_fused);
+  k_split_to_f32<<<nblk((int64_t)M * d), 256, 0, st>>>(o, out, (int64_t)M * d);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  while (h->allocs.size() > n_alloc0) { cudaFree(h->allocs.back()); h->allocs.pop_back(); }
+  if (e != cudaSuccess) FAIL(MLDB_ERR_CUDA, "debug ffn: %s", cudaGetErrorString(e));
+  return MLDB_OK;
 }

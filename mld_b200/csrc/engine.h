@@ -117,6 +117,14 @@ struct mldb_handle {
   int* pair_cnt = nullptr;   // per-m-tile arrival counters of the pair launch
   bool pair_chunk = false;   // chunk qkv->attention and FFN1->FFN2 pairs through one L2-sized buffer
   int chunk_seqs = 0;        // sequences per stack pass (0 = whole batch); see denoiser_pass
+  // Concurrent sub-batches: the denoiser stack runs as `branches` independent sequence ranges on
+  // parallel streams (parallel chains inside the captured graph), each with its own workspace rows,
+  // so one range's kernel tails (316 m-tiles on 148 SMs = 2.13 rounds) and kernel boundaries are
+  // filled by the other range's kernels.  1 = off.
+  int branches = 2;
+  static constexpr int MAX_BRANCHES = 4;
+  cudaStream_t br_stream[MAX_BRANCHES - 1] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_BRANCHES - 1] = {};
   TcCtx* tc = nullptr;
 };
 

@@ -683,6 +683,337 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   }
 }
 
+// ------------------------------------------------------------------------------ fused FFN
+// y = LayerNorm(res + W2 gelu(W1 x + b1) + b2) for d = 256 as ONE persistent launch in which the
+// hidden activations never leave the SM (the unfused pair writes and re-reads 2 x 4 x ff bytes per
+// row through HBM, which is what bounds it).  A CTA owns 128-row m-tiles; per tile it walks the
+// hidden dimension in 128-column chunks:
+//   F1(c): acc1[c&1] (TMEM, 128 cols)  = x[128 x 256] . W1[c*128.., :]^T        (4 k-blocks)
+//   E1(c): acc1 -> *s1 + b1 -> GELU -> split16 -> Hs (shared memory, UMMA K-major SWIZZLE_128B)
+//   F2(c): acc2 (TMEM, 256 cols)      += Hs[128 x 128] . W2[:, c*128..]^T        (2 k-blocks)
+// and finishes with the residual + LayerNorm epilogue on acc2.  The MMA warp issues
+// F1(0) F1(1) F2(0) F1(2) F2(1) ... so E1(c) runs under F1(c+1); the TMA warp streams the x / W1 /
+// W2 k-blocks through one 2 x 64 KB ring in exactly that order.
+struct FfnParams {
+  int M, m_tiles, n_chunks;
+  float inv_s1, inv_s2;
+  const float* b1; const float* b2; const float* gamma; const float* beta;
+  const __half* res_hi; const __half* res_lo; int ld_res;
+  __half* out_hi; __half* out_lo; int ld_out;
+};
+struct FfnCfg {
+  static constexpr int CHUNK = 128;                      // hidden columns per chunk
+  static constexpr int STAGES = 2, STAGE_BYTES = 65536;  // F1: xh|xl|w1h|w1l (16 KB each); F2: w2h|w2l (32 KB each)
+  static constexpr int HS_BYTES = 65536;                 // [plane][k-block][128 rows x 128 B]
+  static constexpr int TMEM_COLS = 512;                  // acc1 x 2 (128 cols each) + acc2 (256 cols)
+  static constexpr int STG_BYTES = EPI_WARPS * 2048;
+  static constexpr int AUX_BYTES = MAX_N * 4 + 3 * 256 * 4 + 4 * 128 * 4 + 256 + STG_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + HS_BYTES + AUX_BYTES + 1024;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
+         const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW1l,
+         const __grid_constant__ CUtensorMap tmW2h, const __grid_constant__ CUtensorMap tmW2l, const FfnParams p) {
+  using Cfg = FfnCfg;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* hs = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* aux = hs + Cfg::HS_BYTES;
+  float* s_b1 = reinterpret_cast<float*>(aux);                // [MAX_N]
+  float* s_b2 = s_b1 + MAX_N;                                 // [256]
+  float* s_gamma = s_b2 + 256;
+  float* s_beta = s_gamma + 256;
+  float* s_part = s_beta + 256;                               // [2][2][128]
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_part + 4 * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + Cfg::STG_BYTES);
+  uint64_t* bar_full = bars;                  // [2] ring stage filled (TMA tx)
+  uint64_t* bar_empty = bars + 2;             // [2] ring stage consumed (MMA commit)
+  uint64_t* bar_a1full = bars + 4;            // [2] F1 chunk accumulated
+  uint64_t* bar_a1empty = bars + 6;           // [2] ... and drained by the epilogue warps
+  uint64_t* bar_hfull = bars + 8;             // Hs written (epilogue warps)
+  uint64_t* bar_hempty = bars + 9;            // Hs consumed (MMA commit)
+  uint64_t* bar_a2full = bars + 10;           // tile's acc2 complete
+  uint64_t* bar_a2empty = bars + 11;          // ... and drained by the LayerNorm epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NC = p.n_chunks;
+  const int nlocal = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_full[s]), 1);
+      mbar_init(smem_u32(&bar_empty[s]), 1);
+      mbar_init(smem_u32(&bar_a1full[s]), 1);
+      mbar_init(smem_u32(&bar_a1empty[s]), EPI_WARPS);
+    }
+    mbar_init(smem_u32(bar_hfull), EPI_WARPS);
+    mbar_init(smem_u32(bar_hempty), 1);
+    mbar_init(smem_u32(bar_a2full), 1);
+    mbar_init(smem_u32(bar_a2empty), EPI_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    tma_prefetch_desc(&tmXh); tma_prefetch_desc(&tmXl); tma_prefetch_desc(&tmW1h);
+    tma_prefetch_desc(&tmW1l); tma_prefetch_desc(&tmW2h); tma_prefetch_desc(&tmW2l);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_b1[i] = (p.b1 && i < NC * Cfg::CHUNK) ? p.b1[i] : 0.0f;
+    for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) {
+      s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; s_b2[i] = p.b2 ? p.b2[i] : 0.0f;
+    }
+  }
+  pdl_trigger();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      int kbg = 0;
+      auto acquire = [&]() -> uint32_t {           // next ring stage: wait until free, arm its barrier
+        const int s = kbg % STAGES;
+        mbar_wait(smem_u32(&bar_empty[s]), (((uint32_t)(kbg / STAGES)) & 1u) ^ 1u);
+        mbar_expect_tx(smem_u32(&bar_full[s]), Cfg::STAGE_BYTES);
+        ++kbg;
+        return (uint32_t)s;
+      };
+      for (int j = 0; j < nlocal; ++j) {
+        const int m0 = ((int)blockIdx.x + j * (int)gridDim.x) * BM;
+        for (int i = 0; i <= NC; ++i) {
+          if (i < NC) {
+            for (int kb = 0; kb < 4; ++kb) {
+              const uint32_t s = acquire();
+              const uint32_t full = smem_u32(&bar_full[s]), dst = smem_u32(smem + s * Cfg::STAGE_BYTES);
+              tma_load_2d(dst, &tmXh, full, kb * BK, m0);
+              tma_load_2d(dst + 16384, &tmXl, full, kb * BK, m0);
+              tma_load_2d(dst + 32768, &tmW1h, full, kb * BK, i * Cfg::CHUNK);
+              tma_load_2d(dst + 49152, &tmW1l, full, kb * BK, i * Cfg::CHUNK);
+            }
+          }
+          if (i >= 1) {
+            for (int kb = 0; kb < 2; ++kb) {
+              const uint32_t s = acquire();
+              const uint32_t full = smem_u32(&bar_full[s]), dst = smem_u32(smem + s * Cfg::STAGE_BYTES);
+              tma_load_2d(dst, &tmW2h, full, (i - 1) * Cfg::CHUNK + kb * BK, 0);
+              tma_load_2d(dst + 32768, &tmW2l, full, (i - 1) * Cfg::CHUNK + kb * BK, 0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc1 = make_idesc(Cfg::CHUNK), idesc2 = make_idesc(256);
+      const uint32_t hs_u = smem_u32(hs);
+      int kbg = 0, g1 = 0, g2 = 0;                 // ring position, F1 chunks issued, F2 chunks issued
+      for (int j = 0; j < nlocal; ++j) {
+        for (int i = 0; i <= NC; ++i) {
+          if (i < NC) {                            // F1(i)
+            const int b = g1 & 1;
+            mbar_wait(smem_u32(&bar_a1empty[b]), (((uint32_t)g1 >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)(b * Cfg::CHUNK);
+            for (int kb = 0; kb < 4; ++kb, ++kbg) {
+              const int s = kbg % STAGES;
+              mbar_wait(smem_u32(&bar_full[s]), ((uint32_t)(kbg / STAGES)) & 1u);
+              tc_fence_after();
+              const uint32_t sXh = smem_u32(smem + s * Cfg::STAGE_BYTES), sXl = sXh + 16384;
+              const uint32_t sWh = sXh + 32768, sWl = sXh + 49152;
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk) {
+                const uint32_t off = kk * 32;
+                const uint64_t ah = make_desc(sXh + off), al = make_desc(sXl + off);
+                const uint64_t wh = make_desc(sWh + off), wl = make_desc(sWl + off);
+                umma(tacc, al, wh, idesc1, (kb | kk) != 0 ? 1u : 0u);
+                umma(tacc, ah, wl, idesc1, 1u);
+                umma(tacc, ah, wh, idesc1, 1u);
+              }
+              umma_commit(smem_u32(&bar_empty[s]));
+            }
+            umma_commit(smem_u32(&bar_a1full[b]));
+            ++g1;
+          }
+          if (i >= 1) {                            // F2(i - 1)
+            if (i == 1) {                          // the previous tile's LayerNorm epilogue has drained acc2
+              mbar_wait(smem_u32(bar_a2empty), ((uint32_t)j & 1u) ^ 1u);
+              tc_fence_after();
+            }
+            mbar_wait(smem_u32(bar_hfull), (uint32_t)g2 & 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + 2u * Cfg::CHUNK;
+            for (int kb = 0; kb < 2; ++kb, ++kbg) {
+              const int s = kbg % STAGES;
+              mbar_wait(smem_u32(&bar_full[s]), ((uint32_t)(kbg / STAGES)) & 1u);
+              tc_fence_after();
+              const uint32_t sHh = hs_u + kb * 16384, sHl = hs_u + 32768 + kb * 16384;
+              const uint32_t sWh = smem_u32(smem + s * Cfg::STAGE_BYTES), sWl = sWh + 32768;
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk) {
+                const uint32_t off = kk * 32;
+                const uint64_t ah = make_desc(sHh + off), al = make_desc(sHl + off);
+                const uint64_t wh = make_desc(sWh + off), wl = make_desc(sWl + off);
+                umma(tacc, al, wh, idesc2, ((i - 1) | kb | kk) != 0 ? 1u : 0u);
+                umma(tacc, ah, wl, idesc2, 1u);
+                umma(tacc, ah, wh, idesc2, 1u);
+              }
+              umma_commit(smem_u32(&bar_empty[s]));
+            }
+            umma_commit(smem_u32(bar_hempty));
+            ++g2;
+            if (i == NC) umma_commit(smem_u32(bar_a2full));
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue warps 2..9
+    const int q = warp & 3;                          // TMEM lane quarter
+    const int hf = (warp - 2) >> 2;                  // column half of a chunk / of the output row
+    const int row = q * 32 + lane;
+    uint8_t* const stg = s_stage + (warp - 2) * 2048;
+    uint32_t r[32];
+    float v[32];
+    int g = 0;                                       // hidden chunks handled so far
+    for (int j = 0; j < nlocal; ++j) {
+      const int m0 = ((int)blockIdx.x + j * (int)gridDim.x) * BM;
+      // ---- E1: hidden chunks -> Hs
+      for (int c = 0; c < NC; ++c, ++g) {
+        const int b = g & 1;
+        mbar_wait(smem_u32(&bar_a1full[b]), ((uint32_t)g >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * Cfg::CHUNK + hf * 64);
+        uint32_t PH[2][16], PL[2][16];
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          tmem_ld32(tacc + cc * 32, r);
+          epi_chunk_fast<ACT_GELU>(r, v, s_b1 + c * Cfg::CHUNK + hf * 64 + cc * 32, p.inv_s1);
+          pack_split(v, PH[cc], PL[cc]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_a1empty[b]));
+        mbar_wait(smem_u32(bar_hempty), ((uint32_t)g & 1u) ^ 1u);     // F2(g - 1) has read Hs
+        // this thread's row, k-block hf: 128 B per plane = 8 x 16 B, 16-B index XOR (row & 7) (SWIZZLE_128B)
+        uint8_t* const hrow = hs + hf * 16384 + row * 128;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int sl = ((cc * 4 + jj) ^ (row & 7)) << 4;
+            *reinterpret_cast<uint4*>(hrow + sl) = make_uint4(PH[cc][4 * jj], PH[cc][4 * jj + 1], PH[cc][4 * jj + 2], PH[cc][4 * jj + 3]);
+            *reinterpret_cast<uint4*>(hrow + 32768 + sl) = make_uint4(PL[cc][4 * jj], PL[cc][4 * jj + 1], PL[cc][4 * jj + 2], PL[cc][4 * jj + 3]);
+          }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tcgen05.mma reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(bar_hfull));
+      }
+      // ---- residual + LayerNorm on acc2 (same scheme as k_gemm_tc's LN epilogue)
+      const int m = m0 + row;
+      const bool row_ok = m < p.M;
+      const int wrow0 = m0 + q * 32;
+      const int rows_valid = min(32, p.M - wrow0);
+      const int cb = hf * 128;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * Cfg::CHUNK + cb);
+      const bool has_res = p.res_hi != nullptr;
+      const float shiftK = (has_res && row_ok) ? join_f32(p.res_hi[(int64_t)m * p.ld_res], p.res_lo[(int64_t)m * p.ld_res]) : 0.0f;
+      const __half* rbh = p.res_hi + (int64_t)wrow0 * p.ld_res + cb;
+      const __half* rbl = p.res_lo + (int64_t)wrow0 * p.ld_res + cb;
+      uint4 gh[4], gl[4];
+      if (has_res) {
+        load_plane_issue(rbh, p.ld_res, rows_valid, lane, gh);
+        load_plane_issue(rbl, p.ld_res, rows_valid, lane, gl);
+      }
+      mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);
+      tc_fence_after();
+      float s1 = 0.0f, s2 = 0.0f;
+      const float sc = p.inv_s2;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 rh[4], rl[4];
+        if (has_res) {
+          plane_to_rows(stg, gh, lane, rh);
+          plane_to_rows(stg, gl, lane, rl);
+          if (c + 1 < 4) {
+            load_plane_issue(rbh + (c + 1) * 32, p.ld_res, rows_valid, lane, gh);
+            load_plane_issue(rbl + (c + 1) * 32, p.ld_res, rows_valid, lane, gl);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
+        }
+        tmem_ld32(trow + c * 32, r);
+        const float* bch = s_b2 + cb + c * 32;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t ah[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
+          const uint32_t al[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
+          const float4 b0 = reinterpret_cast<const float4*>(bch)[2 * i], b1 = reinterpret_cast<const float4*>(bch)[2 * i + 1];
+          const float bia[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&ah[jj]));
+            const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&al[jj]));
+            const int e = i * 8 + jj * 2;
+            const float x0 = fmaf(__uint_as_float(r[e]), sc, bia[2 * jj]) + (hf2.x + lf2.x);
+            const float x1 = fmaf(__uint_as_float(r[e + 1]), sc, bia[2 * jj + 1]) + (hf2.y + lf2.y);
+            const float d0 = x0 - shiftK, d1 = x1 - shiftK;
+            s1 += d0 + d1;
+            s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+            r[e] = __float_as_uint(x0);
+            r[e + 1] = __float_as_uint(x1);
+          }
+        }
+        tmem_st32(trow + c * 32, r);
+      }
+      s_part[hf * 128 + row] = s1;
+      s_part[256 + hf * 128 + row] = s2;
+      epi_bar_sync();
+      const float e1 = (s_part[row] + s_part[128 + row]) * (1.0f / 256);
+      const float e2 = (s_part[256 + row] + s_part[256 + 128 + row]) * (1.0f / 256);
+      const float mean = shiftK + e1;
+      const float rstd = rsqrtf(fmaxf(e2 - e1 * e1, 0.0f) + 1e-5f);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(trow + c * 32, r);
+        const float4* g4 = reinterpret_cast<const float4*>(s_gamma + cb + c * 32);
+        const float4* e4 = reinterpret_cast<const float4*>(s_beta + cb + c * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 gg = g4[i], bb = e4[i];
+          v[4 * i + 0] = fmaf((__uint_as_float(r[4 * i + 0]) - mean) * rstd, gg.x, bb.x);
+          v[4 * i + 1] = fmaf((__uint_as_float(r[4 * i + 1]) - mean) * rstd, gg.y, bb.y);
+          v[4 * i + 2] = fmaf((__uint_as_float(r[4 * i + 2]) - mean) * rstd, gg.z, bb.z);
+          v[4 * i + 3] = fmaf((__uint_as_float(r[4 * i + 3]) - mean) * rstd, gg.w, bb.w);
+        }
+        uint32_t ph[16], pl[16];
+        pack_split(v, ph, pl);
+        const int64_t o = (int64_t)wrow0 * p.ld_out + cb + c * 32;
+        store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
+        store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
+      }
+      epi_bar_sync();                              // s_part is reused by the next tile
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(bar_a2empty));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------ host side
@@ -694,6 +1025,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 static int g_force_bn = 0;   // MLDB_TC_BN=128: experiment knob (3-stage BN=128 tiles everywhere)
 
 struct TcCtx {
+  int ffn_fused = 1; // FFN1 + GELU + FFN2 + residual + LayerNorm as one launch (MLDB_FFN_FUSED=0: off)
   int cluster = 1;   // CTAs per cluster sharing one multicast W tile (1, 2 or 4)
   int dbg = 0;
   int device = 0;
@@ -716,6 +1048,7 @@ TcCtx* tc_create(int device) {
   c->encode = (PFN_tmapEncodeTiled)fn;
   if (const char* e = getenv("MLDB_TC_DBG")) c->dbg = atoi(e);
   if (const char* e = getenv("MLDB_TC_BN")) g_force_bn = atoi(e);
+  if (const char* e = getenv("MLDB_FFN_FUSED")) c->ffn_fused = atoi(e);
   if (const char* e = getenv("MLDB_TC_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->cluster = v; }
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   e = cudaSuccess;
@@ -725,6 +1058,7 @@ TcCtx* tc_create(int device) {
   opt_in(k_gemm_tc<256, 1>, TileCfg<256>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1>, TileCfg<128>::SMEM_BYTES);
   opt_in(k_gemm_tc<256, 2>, TileCfg<256>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2>, TileCfg<128>::SMEM_BYTES);
   opt_in(k_gemm_tc<256, 4>, TileCfg<256>::SMEM_BYTES); opt_in(k_gemm_tc<128, 4>, TileCfg<128>::SMEM_BYTES);
+  opt_in(k_ffn_tc, FfnCfg::SMEM_BYTES);
   if (e != cudaSuccess) {
     mldb_set_err(std::string("cudaFuncSetAttribute(k_gemm_tc): ") + cudaGetErrorString(e));
     delete c;
@@ -852,4 +1186,42 @@ void tc_gemm_pair(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs
   const PairCfg pc{1, counters};
   launch_pdl(k_gemm_tc<256, 1>, dim3(grid), dim3(NUM_THREADS), TileCfg<256>::SMEM_BYTES, st, mAh, mAl, mAh, mAl, mWh, mWl,
              mBh, mBl, mVh, mVl, p, p2, pc);
+}
+
+// FFN block (linear1 + GELU + linear2 + residual + LayerNorm) as one launch, d = 256.
+int tc_set_ffn_fused(TcCtx* c, int on) {
+  if (!c) return 0;
+  const int old = c->ffn_fused;
+  c->ffn_fused = on;
+  return old;
+}
+bool tc_ffn_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2) {
+  if (!c || !c->ffn_fused) return false;
+  if (!tc_gemm_supported(c, g1) || !tc_gemm_ln_supported(c, g2, l2)) return false;
+  if (g1.K1 != 256 || g1.K2 > 0 || g2.K2 > 0 || g1.M != g2.M) return false;
+  if (g1.w.N % FfnCfg::CHUNK || g1.w.N > MAX_N || g1.w.N != g2.K1) return false;
+  if (g1.act != ACT_GELU || g1.out_f32 || g1.addtab || g1.zero_lengths) return false;
+  if (g1.in_group < g1.M || g1.out_group != 0 || g1.out_off != 0 || l2.rowvec) return false;
+  return true;
+}
+void tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, cudaStream_t st) {
+  CUtensorMap mXh, mXl, mW1h, mW1l, mW2h, mW2l;
+  const bool ok = make_map(c, &mXh, g1.a1.hi, g1.M, g1.K1, BM) && make_map(c, &mXl, g1.a1.lo(), g1.M, g1.K1, BM) &&
+                  make_map(c, &mW1h, g1.w.w, g1.w.N, g1.w.K, FfnCfg::CHUNK) &&
+                  make_map(c, &mW1l, g1.w.w + g1.w.plane_stride, g1.w.N, g1.w.K, FfnCfg::CHUNK) &&
+                  make_map(c, &mW2h, g2.w.w, g2.w.N, g2.w.K, 256) &&
+                  make_map(c, &mW2l, g2.w.w + g2.w.plane_stride, g2.w.N, g2.w.K, 256);
+  if (!ok) {
+    fprintf(stderr, "libmldb200: cuTensorMapEncodeTiled failed (ffn M=%d)\n", g1.M);
+    c->ok = false;
+    return;
+  }
+  FfnParams p{};
+  p.M = g1.M; p.m_tiles = (g1.M + BM - 1) / BM; p.n_chunks = g1.w.N / FfnCfg::CHUNK;
+  p.inv_s1 = g1.w.inv_scale; p.inv_s2 = g2.w.inv_scale;
+  p.b1 = g1.w.bias; p.b2 = g2.w.bias; p.gamma = l2.gamma; p.beta = l2.beta;
+  p.res_hi = l2.res.hi; p.res_lo = l2.res.hi ? l2.res.lo() : nullptr; p.ld_res = l2.res.cols;
+  p.out_hi = l2.out.hi; p.out_lo = l2.out.lo(); p.ld_out = l2.out.cols;
+  const int grid = p.m_tiles < c->sm_count ? p.m_tiles : c->sm_count;
+  launch_pdl(k_ffn_tc, dim3(grid), dim3(NUM_THREADS), FfnCfg::SMEM_BYTES, st, mXh, mXl, mW1h, mW1l, mW2h, mW2l, p);
 }

@@ -86,6 +86,18 @@ class Engine:
               "mldb_debug_gemm")
         return out
 
+    def debug_ffn(self, X, W1, b1, W2, b2, gamma, beta, mode=2):
+        """Kernel unit-test hook (mldb_debug_ffn): LayerNorm(X + W2 gelu(W1 X + b1) + b2); mode 0 CUDA-core,
+        1 tcgen05 GEMMs (two launches), 2 fused tcgen05 FFN kernel.  X [M,d] (device), the rest host."""
+        X = _f32c(X, self.device)
+        host = [t.detach().float().contiguous().cpu() for t in (W1, b1, W2, b2, gamma, beta)]
+        M, d = X.shape
+        ff = host[0].shape[0]
+        out = torch.empty((M, d), dtype=torch.float32, device=self.device)
+        check(self.lib.mldb_debug_ffn(self._h, _ptr(X), *[_ptr(t) for t in host], M, d, ff, int(mode), _ptr(out),
+                                      self._stream()), "mldb_debug_ffn")
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.mldb_launch_count(self._h))

@@ -57,6 +57,25 @@ def test_tc_gemm_epilogues(eng, M, N, K, K1, act, ln):
     assert _rel(y_tc, ref) < 5e-6, "tcgen05 kernel vs float64 reference"
 
 
+@pytest.mark.parametrize("M,ff", [(100, 1024), (128 * 3 + 5, 1024), (148 * 128 * 2 + 777, 1024), (1000, 512)])
+def test_fused_ffn_block(eng, M, ff):
+    """k_ffn_tc (hidden activations kept on the SM) vs float64 and vs the unfused operators."""
+    d = 256
+    g = torch.Generator().manual_seed(M + ff)
+    X = torch.randn(M, d, generator=g)
+    W1, b1 = torch.randn(ff, d, generator=g) / d ** 0.5, 0.1 * torch.randn(ff, generator=g)
+    W2, b2 = torch.randn(d, ff, generator=g) / ff ** 0.5, 0.1 * torch.randn(d, generator=g)
+    gamma, beta = 1 + 0.1 * torch.randn(d, generator=g), 0.1 * torch.randn(d, generator=g)
+    Xd = X.double()
+    hid = F.gelu(F.linear(Xd, W1.double(), b1.double()))
+    ref = F.layer_norm(Xd + F.linear(hid, W2.double(), b2.double()), (d,), gamma.double(), beta.double(), 1e-5)
+    ys = [eng.debug_ffn(X, W1, b1, W2, b2, gamma, beta, mode=m).cpu().double() for m in (0, 1, 2)]
+    for name, y in zip(("cuda-core", "tc unfused", "tc fused"), ys):
+        assert torch.isfinite(y).all(), name
+        assert _rel(y, ref) < 5e-6, name
+    assert _rel(ys[2], ys[1]) < 2e-6
+
+
 def test_whole_path_tc_equals_cuda_core_path(built_lib):
     """The same 6-step sample through both GEMM paths agrees to fp32 re-association noise."""
     from mld_b200 import synth
@@ -80,8 +99,9 @@ def test_whole_path_tc_equals_cuda_core_path(built_lib):
 
 def test_scheduling_options_do_not_change_results(built_lib):
     """Engine scheduling options only reorder independent work: the fused FFN pair launch (one
-    persistent kernel running FFN1 -> FFN2 chains per CTA), the L2-sized producer/consumer chunking
-    and the sequence chunking must give bit-identical motions."""
+    persistent kernel running FFN1 -> FFN2 chains per CTA), the L2-sized producer/consumer chunking,
+    the sequence chunking and the number of concurrent sub-batch branches must give bit-identical
+    motions."""
     from mld_b200 import synth
     from mld_b200.engine import Engine, make_config
     eng = Engine(make_config(), 0)
@@ -93,8 +113,11 @@ def test_scheduling_options_do_not_change_results(built_lib):
     B = 300                                   # 600 sequences x 79 tokens = 371 m-tiles: > 2 waves + ragged tail
     ctx, noise = synth.text_context(B, 77, seed=15), synth.init_noise(B, seed=16)
     lengths = [196] * B
+    fused = eng.sample(ctx, noise, lengths, want=("latents",))["latents"].clone()
+    eng.set_option("ffn_fused", "0")          # the two-launch FFN: same math, hidden round-trips HBM
     base = eng.sample(ctx, noise, lengths, want=("latents",))["latents"].clone()
-    for name, value in (("ffn_pair", "1"), ("pair_chunk", "1"), ("chunk", "96")):
+    assert _rel(fused, base) < 1e-5
+    for name, value in (("branches", "1"), ("branches", "3"), ("ffn_pair", "1"), ("pair_chunk", "1"), ("chunk", "96")):
         eng.set_option(name, value)
         out = eng.sample(ctx, noise, lengths, want=("latents",))["latents"]
         assert torch.equal(out, base), f"option {name}={value} changed the result"

@@ -60,15 +60,23 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// multicast variant: the box lands at the same shared-memory offset of every CTA in `mask` and
-// completes `bytes` on the mbarrier at the same offset of each of them
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                               uint16_t mask) {
+// 2-SM (cta_group::2) variant, executed by both CTAs of a pair: the box lands in the executing CTA's
+// shared memory, the bytes are counted on `bar`, a shared::cluster address of the LEADER's mbarrier
+// (cute::SM100_TMA_2SM_LOAD_2D).
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -94,8 +102,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bit 4), A = B = F16 (0),
 // both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+__host__ __device__ constexpr uint32_t make_idesc(int n, int m = BM) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
@@ -108,10 +116,20 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// commit that arrives on the mbarrier at the same offset of every CTA in `mask`
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
+// 2-SM MMA: D[256 x N] (rows 0-127 in the leader's TMEM, 128-255 in the peer's) += A . B^T with A's
+// 128-row halves and B's N/2-row halves read from the two CTAs' shared memory at the same offsets.
+__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// commit of the pair's MMAs: arrives on the mbarrier at the same offset of both CTAs
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -177,11 +195,11 @@ constexpr int EPI_WARPS = 8;                         // two warps per TMEM lane 
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;     // producer warp + MMA warp + epilogue warps
 constexpr int MAX_N = 1024;                          // bias staging capacity
 
-template <int BN>
+template <int BN, int CG = 1>
 struct TileCfg {
-  static constexpr int STAGES = BN == 256 ? 2 : 3;
+  static constexpr int STAGES = CG == 2 ? (BN == 256 ? 3 : 4) : (BN == 256 ? 2 : 3);
   static constexpr int A_BYTES = BM * BK * 2;          // one plane of the A tile (16 KB)
-  static constexpr int W_BYTES = BN * BK * 2;          // one plane of the W tile
+  static constexpr int W_BYTES = BN / CG * BK * 2;     // one plane of this CTA's part of the W tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator
   // bias[MAX_N] + gamma[256] + beta[256] + LN partials [2][2][128] + barriers
@@ -285,9 +303,8 @@ __device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&
   }
 }
 
-// j-th work item of this CTA.  Single-GEMM mode: clusters of `cl` CTAs walk (m-group, n) items in
-// lockstep - CTA rank r of a cluster takes m-tile mg*cl + r - so that the W tile of an item is
-// fetched once per cluster (TMA multicast) instead of once per CTA.
+// j-th work item of this CTA.  Single-GEMM mode: CTA pairs (cl = 2, cta_group::2) walk (m-pair, n)
+// items in lockstep - CTA rank r of a pair owns m-tile mp*2 + r and half of the W tile.
 __device__ __forceinline__ WorkItem decode_item(int j, const TcParams& p, int pair, int bn, int cl, int rank) {
   WorkItem it;
   it.s0 = blockIdx.x * BM;
@@ -312,7 +329,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 // Persistent: CTA c walks tiles c, c + gridDim.x, ...; tile t -> (m = t / n_tiles, n = t % n_tiles).
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the TMA/MMA main loop of tile i + 1.
-template <int BN, int CL>
+template <int BN, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
@@ -320,10 +337,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
           const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
           const TcParams p, const TcParams p2, const PairCfg pc) {
-  using Cfg = TileCfg<BN>;
+  using Cfg = TileCfg<BN, CG>;
+  constexpr int CL = CG;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-B alignment by pointer arithmetic (an integer round trip would lose the shared address space
+  // and turn every staging access into a generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
   float* s_bias = reinterpret_cast<float*>(aux);              // [MAX_N]
   float* s_bias2 = s_bias + MAX_N;                            // [256] consumer GEMM bias (pair mode)
@@ -343,7 +363,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   const bool pair = pc.on != 0;
   // number of work items of this CTA
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
-  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
   const int ncl = (int)gridDim.x / CL, cid = (int)blockIdx.x / CL;          // clusters, this CTA's cluster
   const int ngroups = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;               // (m-group, n) items
   const int nlocal = pair ? ((p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (p.n_tiles + 1)
@@ -353,18 +372,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
-      mbar_init(smem_u32(&bar_empty[s]), CL);              // one MMA-commit arrival per CTA of the cluster
+      mbar_init(smem_u32(&bar_empty[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tfull[s]), 1);
-      mbar_init(smem_u32(&bar_tempty[s]), EPI_WARPS);
+      mbar_init(smem_u32(&bar_tempty[s]), EPI_WARPS * CG);  // 2-SM: the leader's barrier collects both CTAs' warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmA1h); tma_prefetch_desc(&tmA1l); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
   }
+  if (CG > 1) { __syncthreads(); cluster_sync_all(); }   // 2-SM TMEM allocation needs both CTAs of the pair resident
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.0f;
@@ -377,7 +402,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   pdl_trigger();               // let the next kernel's prologue overlap our tail
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // peers' barriers are initialised before anyone multicasts to them
+  if (CG > 1) cluster_sync_all();   // the peer's barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                  // everything below touches activations of the previous kernel
@@ -407,8 +432,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           const int s = kbg % STAGES;
           const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
           mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-          const uint32_t full = smem_u32(&bar_full[s]);
-          mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          uint32_t full = smem_u32(&bar_full[s]);
+          if (CG == 1) {
+            mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          } else {                                   // both CTAs' boxes are counted on the leader's barrier
+            if (rank == 0) mbar_expect_tx(full, 2 * Cfg::STAGE_BYTES);
+            full = mapa_u32(full, 0);
+          }
           const uint32_t sAh = smem_u32(smem + s * Cfg::STAGE_BYTES), sAl = sAh + Cfg::A_BYTES;
           const uint32_t sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
           if (wi.type) {
@@ -417,30 +447,36 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
             tma_load_2d(sWh, &tmVh, full, kb * BK, n0);
             tma_load_2d(sWl, &tmVl, full, kb * BK, n0);
           } else {
-            if (kb < q.kb1) {
-              tma_load_2d(sAh, &tmA1h, full, kb * BK, m0);
-              tma_load_2d(sAl, &tmA1l, full, kb * BK, m0);
-            } else {
-              tma_load_2d(sAh, &tmA2h, full, (kb - q.kb1) * BK, m0);
-              tma_load_2d(sAl, &tmA2l, full, (kb - q.kb1) * BK, m0);
-            }
-            if (CL == 1) {
+            if (CG == 1) {
+              if (kb < q.kb1) {
+                tma_load_2d(sAh, &tmA1h, full, kb * BK, m0);
+                tma_load_2d(sAl, &tmA1l, full, kb * BK, m0);
+              } else {
+                tma_load_2d(sAh, &tmA2h, full, (kb - q.kb1) * BK, m0);
+                tma_load_2d(sAl, &tmA2l, full, (kb - q.kb1) * BK, m0);
+              }
               tma_load_2d(sWh, &tmWh, full, kb * BK, n0);
               tma_load_2d(sWl, &tmWl, full, kb * BK, n0);
             } else {
-              // this CTA fetches rows [rank*BN/CL, (rank+1)*BN/CL) of the W tile for the whole cluster
-              constexpr int SL = BN / CL;
-              tma_load_2d_mc(sWh + rank * SL * 128, &tmWh, full, kb * BK, n0 + rank * SL, MC_MASK);
-              tma_load_2d_mc(sWl + rank * SL * 128, &tmWl, full, kb * BK, n0 + rank * SL, MC_MASK);
+              // this CTA's own 128 rows of A and rows [rank*BN/2, (rank+1)*BN/2) of the W tile
+              if (kb < q.kb1) {
+                tma_load_2d_2sm(sAh, &tmA1h, full, kb * BK, m0);
+                tma_load_2d_2sm(sAl, &tmA1l, full, kb * BK, m0);
+              } else {
+                tma_load_2d_2sm(sAh, &tmA2h, full, (kb - q.kb1) * BK, m0);
+                tma_load_2d_2sm(sAl, &tmA2l, full, (kb - q.kb1) * BK, m0);
+              }
+              tma_load_2d_2sm(sWh, &tmWh, full, kb * BK, n0 + rank * (BN / 2));
+              tma_load_2d_2sm(sWl, &tmWl, full, kb * BK, n0 + rank * (BN / 2));
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc = make_idesc(BN);
+    if (lane == 0 && rank == 0) {
+      // ---------------------------------------------------------------- MMA issuer (2-SM: the leader CTA)
+      constexpr uint32_t idesc = make_idesc(BN, BM * CG);
       int kbg = 0, it = 0;
       for (; it < nlocal; ++it) {
         const int as = it & 1;
@@ -461,15 +497,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
             const uint64_t ah = make_desc(sAh + off), al = make_desc(sAl + off);
             const uint64_t wh = make_desc(sWh + off), wl = make_desc(sWl + off);
             if (!(p.dbg & 4)) {
-              umma(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
-              umma(tacc, ah, wl, idesc, 1u);
-              umma(tacc, ah, wh, idesc, 1u);
+              if (CG == 1) {
+                umma(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
+                umma(tacc, ah, wl, idesc, 1u);
+                umma(tacc, ah, wh, idesc, 1u);
+              } else {
+                umma_2sm(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
+                umma_2sm(tacc, ah, wl, idesc, 1u);
+                umma_2sm(tacc, ah, wh, idesc, 1u);
+              }
             }
           }
-          if (CL == 1) umma_commit(smem_u32(&bar_empty[s]));      // frees the stage when these MMAs retire
-          else umma_commit_mc(smem_u32(&bar_empty[s]), MC_MASK);  // ... in every CTA of the cluster
+          if (CG == 1) umma_commit(smem_u32(&bar_empty[s]));      // frees the stage when these MMAs retire
+          else umma_commit_2sm(smem_u32(&bar_empty[s]));          // ... in both CTAs of the pair
         }
-        umma_commit(smem_u32(&bar_tfull[as]));       // accumulator complete
+        if (CG == 1) umma_commit(smem_u32(&bar_tfull[as]));       // accumulator complete
+        else umma_commit_2sm(smem_u32(&bar_tfull[as]));
       }
     }
   } else {
@@ -580,7 +623,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           tc_fence_after();
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
+          if (lane == 0) { if (CG == 1) mbar_arrive(smem_u32(&bar_tempty[as])); else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[as]), 0)); }
           continue;
         }
         const float* rv = (row_ok && pp.rowvec) ? pp.rowvec + (int64_t)(m / pp.rv_group) * BN : nullptr;
@@ -671,15 +714,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       // this warp is done reading the accumulator stage: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bar_tempty[as]));
+      if (lane == 0) { if (CG == 1) mbar_arrive(smem_u32(&bar_tempty[as])); else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[as]), 0)); }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();   // nobody exits while a peer may still signal its barriers / write its smem
+  if (CG > 1) cluster_sync_all();   // nobody exits while the peer may still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -718,7 +762,9 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   using Cfg = FfnCfg;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-B alignment by pointer arithmetic (an integer round trip would lose the shared address space
+  // and turn every staging access into a generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* hs = smem + STAGES * Cfg::STAGE_BYTES;
   uint8_t* aux = hs + Cfg::HS_BYTES;
   float* s_b1 = reinterpret_cast<float*>(aux);                // [MAX_N]
@@ -1026,7 +1072,7 @@ static int g_force_bn = 0;   // MLDB_TC_BN=128: experiment knob (3-stage BN=128 
 
 struct TcCtx {
   int ffn_fused = 1; // FFN1 + GELU + FFN2 + residual + LayerNorm as one launch (MLDB_FFN_FUSED=0: off)
-  int cluster = 1;   // CTAs per cluster sharing one multicast W tile (1, 2 or 4)
+  int cluster = 1;   // 2 = CTA pairs (cta_group::2 MMA, each CTA loads half of the W tile); MLDB_TC_2SM
   int dbg = 0;
   int device = 0;
   int sm_count = 148;
@@ -1049,15 +1095,14 @@ TcCtx* tc_create(int device) {
   if (const char* e = getenv("MLDB_TC_DBG")) c->dbg = atoi(e);
   if (const char* e = getenv("MLDB_TC_BN")) g_force_bn = atoi(e);
   if (const char* e = getenv("MLDB_FFN_FUSED")) c->ffn_fused = atoi(e);
-  if (const char* e = getenv("MLDB_TC_CLUSTER")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) c->cluster = v; }
+  if (const char* e = getenv("MLDB_TC_2SM")) c->cluster = atoi(e) ? 2 : 1;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   e = cudaSuccess;
   auto opt_in = [&](auto kernel, int bytes) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   };
-  opt_in(k_gemm_tc<256, 1>, TileCfg<256>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1>, TileCfg<128>::SMEM_BYTES);
-  opt_in(k_gemm_tc<256, 2>, TileCfg<256>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2>, TileCfg<128>::SMEM_BYTES);
-  opt_in(k_gemm_tc<256, 4>, TileCfg<256>::SMEM_BYTES); opt_in(k_gemm_tc<128, 4>, TileCfg<128>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 1>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1>, TileCfg<128, 1>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 2>, TileCfg<256, 2>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2>, TileCfg<128, 2>::SMEM_BYTES);
   opt_in(k_ffn_tc, FfnCfg::SMEM_BYTES);
   if (e != cudaSuccess) {
     mldb_set_err(std::string("cudaFuncSetAttribute(k_gemm_tc): ") + cudaGetErrorString(e));
@@ -1131,8 +1176,7 @@ void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   if (g.K2 > 0) ok = ok && make_map(c, &mA2h, g.a2.hi, g.M, g.K2, BM) && make_map(c, &mA2l, g.a2.lo(), g.M, g.K2, BM);
   else { mA2h = mA1h; mA2l = mA1l; }
   const int m_tiles_ = (g.M + BM - 1) / BM;
-  int cl = c->cluster;
-  while (cl > 1 && (m_tiles_ < 2 * cl || c->sm_count % cl)) cl >>= 1;     // small problems: no cluster
+  const int cl = (c->cluster == 2 && m_tiles_ >= 4 && c->sm_count % 2 == 0) ? 2 : 1;   // small problems: no pairs
   ok = ok && make_map(c, &mWh, g.w.w, g.w.N, g.w.K, bn / cl) &&
        make_map(c, &mWl, g.w.w + g.w.plane_stride, g.w.N, g.w.K, bn / cl);
   if (!ok) {
@@ -1146,11 +1190,11 @@ void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   const int ngroups = ((p.m_tiles + cl - 1) / cl) * p.n_tiles;
   const int ncl = ngroups < c->sm_count / cl ? ngroups : c->sm_count / cl;
   dim3 grid(ncl * cl);
-#define MLDB_LAUNCH(BN_, CL_)                                                                              \
-  launch_pdl_cluster(k_gemm_tc<BN_, CL_>, grid, dim3(NUM_THREADS), TileCfg<BN_>::SMEM_BYTES, st, CL_, mA1h, \
+#define MLDB_LAUNCH(BN_, CL_)                                                                                   \
+  launch_pdl_cluster(k_gemm_tc<BN_, CL_>, grid, dim3(NUM_THREADS), TileCfg<BN_, CL_>::SMEM_BYTES, st, CL_, mA1h, \
                      mA1l, mA2h, mA2l, mWh, mWl, mA1h, mA1l, mWh, mWl, p, p2, pc)
-  if (bn == 256) { if (cl == 4) MLDB_LAUNCH(256, 4); else if (cl == 2) MLDB_LAUNCH(256, 2); else MLDB_LAUNCH(256, 1); }
-  else           { if (cl == 4) MLDB_LAUNCH(128, 4); else if (cl == 2) MLDB_LAUNCH(128, 2); else MLDB_LAUNCH(128, 1); }
+  if (bn == 256) { if (cl == 2) MLDB_LAUNCH(256, 2); else MLDB_LAUNCH(256, 1); }
+  else           { if (cl == 2) MLDB_LAUNCH(128, 2); else MLDB_LAUNCH(128, 1); }
 #undef MLDB_LAUNCH
 }
 
@@ -1184,7 +1228,7 @@ void tc_gemm_pair(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs
   fill_params(c, g1, nullptr, 256, &p);
   fill_params(c, g2, &l2, 256, &p2);
   const PairCfg pc{1, counters};
-  launch_pdl(k_gemm_tc<256, 1>, dim3(grid), dim3(NUM_THREADS), TileCfg<256>::SMEM_BYTES, st, mAh, mAl, mAh, mAl, mWh, mWl,
+  launch_pdl(k_gemm_tc<256, 1>, dim3(grid), dim3(NUM_THREADS), TileCfg<256, 1>::SMEM_BYTES, st, mAh, mAl, mAh, mAl, mWh, mWl,
              mBh, mBl, mVh, mVl, p, p2, pc);
 }
 

@@ -54,6 +54,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   } while (!done);
 }
+// wait on an mbarrier that receives arrivals from the peer CTA (cluster-scope acquire)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  long long t0 = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && (++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ll) __trap();
+    }
+  } while (!done);
+}
+
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -89,6 +109,13 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+// one lane of a fully converged warp (elect.sync): lets ptxas keep the tcgen05 / TMA operands in
+// uniform registers instead of emitting a per-instruction ELECT loop for a lane-id branch
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -359,7 +386,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   uint64_t* bar_tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const bool pair = pc.on != 0;
   // number of work items of this CTA
   const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
@@ -408,14 +435,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   pdl_wait();                  // everything below touches activations of the previous kernel
 
   if (warp == 0) {
-    if (lane == 0) {
+    {
       // ---------------------------------------------------------------- TMA producer
+      // The whole warp walks the loop (uniform control flow), one elected lane issues: ptxas then keeps
+      // the TMA / MMA operands in uniform registers instead of wrapping every instruction in an ELECT loop.
       int kbg = 0;                                   // k-block counter across tiles (ring position)
       for (int j = 0; j < nlocal; ++j) {
         const WorkItem wi = decode_item(j, p, pair, BN, CL, rank);
         const TcParams& q = wi.type ? p2 : p;
         const int m0 = wi.m0, n0 = wi.n0;
-        if (wi.type) {
+        if (wi.type && lane == 0) {
           // consumer tile: wait until every producer-epilogue warp has published its part of the slot
           const int mt = blockIdx.x, target = EPI_WARPS * p.n_tiles;
           long long t0 = 0; unsigned spins = 0;
@@ -428,10 +457,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           pc.cnt[mt] = 0;                                   // ready for the next launch
           asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> TMA reads
         }
+        __syncwarp();
         for (int kb = 0; kb < q.kblocks; ++kb, ++kbg) {
           const int s = kbg % STAGES;
           const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
           mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+          if (elect_one()) {
           uint32_t full = smem_u32(&bar_full[s]);
           if (CG == 1) {
             mbar_expect_tx(full, Cfg::STAGE_BYTES);
@@ -470,17 +501,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
               tma_load_2d_2sm(sWl, &tmWl, full, kb * BK, n0 + rank * (BN / 2));
             }
           }
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       // ---------------------------------------------------------------- MMA issuer (2-SM: the leader CTA)
       constexpr uint32_t idesc = make_idesc(BN, BM * CG);
       int kbg = 0, it = 0;
       for (; it < nlocal; ++it) {
         const int as = it & 1;
-        mbar_wait(smem_u32(&bar_tempty[as]), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained it
+        if (CG == 1) mbar_wait(smem_u32(&bar_tempty[as]), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained it
+        else mbar_wait_cluster(smem_u32(&bar_tempty[as]), (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
         const int nkb = decode_item(it, p, pair, BN, CL, rank).type ? p2.kblocks : p.kblocks;
@@ -489,30 +523,35 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
           mbar_wait(smem_u32(&bar_full[s]), ph);
           tc_fence_after();
-          const uint32_t sAh = smem_u32(smem + s * Cfg::STAGE_BYTES), sAl = sAh + Cfg::A_BYTES;
-          const uint32_t sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
-#pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint32_t off = kk * 32;   // 16 halves = 32 bytes inside the 128B swizzle row
-            const uint64_t ah = make_desc(sAh + off), al = make_desc(sAl + off);
-            const uint64_t wh = make_desc(sWh + off), wl = make_desc(sWl + off);
+          if (elect_one()) {
+            const uint32_t sAh = smem_u32(smem + s * Cfg::STAGE_BYTES), sAl = sAh + Cfg::A_BYTES;
+            const uint32_t sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
+            // descriptors of the k-block's first 16-wide slice; +2 (32 B >> 4) per further slice
+            uint64_t ah = make_desc(sAh), al = make_desc(sAl), wh = make_desc(sWh), wl = make_desc(sWl);
             if (!(p.dbg & 4)) {
-              if (CG == 1) {
-                umma(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
-                umma(tacc, ah, wl, idesc, 1u);
-                umma(tacc, ah, wh, idesc, 1u);
-              } else {
-                umma_2sm(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
-                umma_2sm(tacc, ah, wl, idesc, 1u);
-                umma_2sm(tacc, ah, wh, idesc, 1u);
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk) {
+                if (CG == 1) {
+                  umma(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
+                  umma(tacc, ah, wl, idesc, 1u);
+                  umma(tacc, ah, wh, idesc, 1u);
+                } else {
+                  umma_2sm(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
+                  umma_2sm(tacc, ah, wl, idesc, 1u);
+                  umma_2sm(tacc, ah, wh, idesc, 1u);
+                }
+                ah += 2; al += 2; wh += 2; wl += 2;
               }
             }
+            if (CG == 1) umma_commit(smem_u32(&bar_empty[s]));      // frees the stage when these MMAs retire
+            else umma_commit_2sm(smem_u32(&bar_empty[s]));          // ... in both CTAs of the pair
+            if (kb == nkb - 1) {                                    // accumulator complete
+              if (CG == 1) umma_commit(smem_u32(&bar_tfull[as]));
+              else umma_commit_2sm(smem_u32(&bar_tfull[as]));
+            }
           }
-          if (CG == 1) umma_commit(smem_u32(&bar_empty[s]));      // frees the stage when these MMAs retire
-          else umma_commit_2sm(smem_u32(&bar_empty[s]));          // ... in both CTAs of the pair
+          __syncwarp();
         }
-        if (CG == 1) umma_commit(smem_u32(&bar_tfull[as]));       // accumulator complete
-        else umma_commit_2sm(smem_u32(&bar_tfull[as]));
       }
     }
   } else {
@@ -745,25 +784,36 @@ struct FfnParams {
   const __half* res_hi; const __half* res_lo; int ld_res;
   __half* out_hi; __half* out_lo; int ld_out;
 };
+template <int CG>
 struct FfnCfg {
   static constexpr int CHUNK = 128;                      // hidden columns per chunk
-  static constexpr int STAGES = 2, STAGE_BYTES = 65536;  // F1: xh|xl|w1h|w1l (16 KB each); F2: w2h|w2l (32 KB each)
-  static constexpr int HS_BYTES = 65536;                 // [plane][k-block][128 rows x 128 B]
+  // ring slot, per CTA.  F1 k-block: xh | xl (16 KB each) | w1h | w1l (128/CG rows x 128 B each);
+  // F2 k-block: w2h | w2l (256/CG rows x 128 B each).  2-SM pairs load half of every W tile per CTA.
+  static constexpr int W1_BYTES = CHUNK / CG * 128, W2_BYTES = 256 / CG * 128;
+  static constexpr int F1_BYTES = 32768 + 2 * W1_BYTES, F2_BYTES = 2 * W2_BYTES;
+  static constexpr int STAGE_BYTES = F1_BYTES > F2_BYTES ? F1_BYTES : F2_BYTES;   // 64 KB / 48 KB
+  static constexpr int STAGES = CG == 2 ? 3 : 2;
+  static constexpr int HS_BYTES = 65536;                 // [plane][k-block][128 rows x 128 B]; also the
+                                                         // LayerNorm epilogue's staging (Hs is idle then)
   static constexpr int TMEM_COLS = 512;                  // acc1 x 2 (128 cols each) + acc2 (256 cols)
-  static constexpr int STG_BYTES = EPI_WARPS * 2048;
-  static constexpr int AUX_BYTES = MAX_N * 4 + 3 * 256 * 4 + 4 * 128 * 4 + 256 + STG_BYTES;
+  static constexpr int AUX_BYTES = MAX_N * 4 + 3 * 256 * 4 + 4 * 128 * 4 + 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + HS_BYTES + AUX_BYTES + 1024;
 };
 
+// CG = 2: CTA pairs (cta_group::2).  The pair owns 256 rows (rank r: rows mp*256 + r*128); each CTA
+// stages its own x rows, its own hidden chunk (Hs) and HALF of every W1 / W2 tile, the leader issues
+// M = 256 MMAs that read both CTAs' shared memory - which halves the weight bytes every SM has to
+// pull through TMA and, more importantly, the shared-memory bandwidth the B operand costs per MMA
+// (the 3-product split scheme reads every operand byte twice; at N = 128 a 1-SM MMA needs the full
+// 128 B/clk of shared-memory bandwidth for its operands alone).
+template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
          const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW1l,
          const __grid_constant__ CUtensorMap tmW2h, const __grid_constant__ CUtensorMap tmW2l, const FfnParams p) {
-  using Cfg = FfnCfg;
+  using Cfg = FfnCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  // 1024-B alignment by pointer arithmetic (an integer round trip would lose the shared address space
-  // and turn every staging access into a generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* hs = smem + STAGES * Cfg::STAGE_BYTES;
   uint8_t* aux = hs + Cfg::HS_BYTES;
@@ -772,40 +822,50 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   float* s_gamma = s_b2 + 256;
   float* s_beta = s_gamma + 256;
   float* s_part = s_beta + 256;                               // [2][2][128]
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_part + 4 * 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + Cfg::STG_BYTES);
-  uint64_t* bar_full = bars;                  // [2] ring stage filled (TMA tx)
-  uint64_t* bar_empty = bars + 2;             // [2] ring stage consumed (MMA commit)
-  uint64_t* bar_a1full = bars + 4;            // [2] F1 chunk accumulated
-  uint64_t* bar_a1empty = bars + 6;           // [2] ... and drained by the epilogue warps
-  uint64_t* bar_hfull = bars + 8;             // Hs written (epilogue warps)
-  uint64_t* bar_hempty = bars + 9;            // Hs consumed (MMA commit)
-  uint64_t* bar_a2full = bars + 10;           // tile's acc2 complete
-  uint64_t* bar_a2empty = bars + 11;          // ... and drained by the LayerNorm epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 4 * 128);
+  uint64_t* bar_full = bars;                  // [STAGES] ring stage filled (TMA tx; 2-SM: the leader's)
+  uint64_t* bar_empty = bars + 4;             // [STAGES] ring stage consumed (MMA commit, both CTAs)
+  uint64_t* bar_a1full = bars + 8;            // [2] F1 chunk accumulated (MMA commit, both CTAs)
+  uint64_t* bar_a1empty = bars + 10;          // [2] ... and drained by the epilogue warps (2-SM: leader's)
+  uint64_t* bar_hfull = bars + 12;            // Hs written by the epilogue warps (2-SM: leader's)
+  uint64_t* bar_hempty = bars + 13;           // Hs consumed (MMA commit, both CTAs)
+  uint64_t* bar_a2full = bars + 14;           // tile's acc2 complete (MMA commit, both CTAs)
+  uint64_t* bar_a2empty = bars + 15;          // ... and drained by the LayerNorm epilogue (2-SM: leader's)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   const int NC = p.n_chunks;
-  const int nlocal = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int rank = CG > 1 ? (int)cluster_ctarank() : 0;
+  const int ncl = (int)gridDim.x / CG, cid = (int)blockIdx.x / CG;
+  const int ngroups = (p.m_tiles + CG - 1) / CG;
+  const int nlocal = (ngroups - cid + ncl - 1) / ncl;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bar_full[s]), 1);
       mbar_init(smem_u32(&bar_empty[s]), 1);
-      mbar_init(smem_u32(&bar_a1full[s]), 1);
-      mbar_init(smem_u32(&bar_a1empty[s]), EPI_WARPS);
     }
-    mbar_init(smem_u32(bar_hfull), EPI_WARPS);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&bar_a1full[s]), 1);
+      mbar_init(smem_u32(&bar_a1empty[s]), EPI_WARPS * CG);
+    }
+    mbar_init(smem_u32(bar_hfull), EPI_WARPS * CG);
     mbar_init(smem_u32(bar_hempty), 1);
     mbar_init(smem_u32(bar_a2full), 1);
-    mbar_init(smem_u32(bar_a2empty), EPI_WARPS);
+    mbar_init(smem_u32(bar_a2empty), EPI_WARPS * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmXh); tma_prefetch_desc(&tmXl); tma_prefetch_desc(&tmW1h);
     tma_prefetch_desc(&tmW1l); tma_prefetch_desc(&tmW2h); tma_prefetch_desc(&tmW2l);
   }
+  if (CG > 1) { __syncthreads(); cluster_sync_all(); }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_b1[i] = (p.b1 && i < NC * Cfg::CHUNK) ? p.b1[i] : 0.0f;
@@ -816,106 +876,134 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   pdl_trigger();
   tc_fence_before();
   __syncthreads();
+  if (CG > 1) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
 
+  // arrive on a barrier that lives in the leader CTA (2-SM) or in this CTA (1-SM)
+  auto arrive_leader = [&](uint64_t* bar) {
+    if (CG == 1) mbar_arrive(smem_u32(bar));
+    else mbar_arrive_cluster(mapa_u32(smem_u32(bar), 0));
+  };
+
   if (warp == 0) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- TMA producer
+    {
+      // ---------------------------------------------------------------- TMA producer (both CTAs)
+      // whole warp walks the loop, one elected lane issues (operands stay in uniform registers)
       int kbg = 0;
-      auto acquire = [&]() -> uint32_t {           // next ring stage: wait until free, arm its barrier
+      auto stage_begin = [&](uint32_t bytes, uint32_t& full) -> uint32_t {   // elected lane: arm the barrier
         const int s = kbg % STAGES;
-        mbar_wait(smem_u32(&bar_empty[s]), (((uint32_t)(kbg / STAGES)) & 1u) ^ 1u);
-        mbar_expect_tx(smem_u32(&bar_full[s]), Cfg::STAGE_BYTES);
-        ++kbg;
-        return (uint32_t)s;
+        full = smem_u32(&bar_full[s]);
+        if (CG == 1) {
+          mbar_expect_tx(full, bytes);
+        } else {
+          if (rank == 0) mbar_expect_tx(full, 2 * bytes);  // both CTAs' boxes are counted on the leader's barrier
+          full = mapa_u32(full, 0);
+        }
+        return smem_u32(smem + s * Cfg::STAGE_BYTES);
+      };
+      auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t full, int c0, int c1) {
+        if (CG == 1) tma_load_2d(dst, map, full, c0, c1);
+        else tma_load_2d_2sm(dst, map, full, c0, c1);
       };
       for (int j = 0; j < nlocal; ++j) {
-        const int m0 = ((int)blockIdx.x + j * (int)gridDim.x) * BM;
+        const int m0 = ((cid + j * ncl) * CG + rank) * BM;
         for (int i = 0; i <= NC; ++i) {
           if (i < NC) {
-            for (int kb = 0; kb < 4; ++kb) {
-              const uint32_t s = acquire();
-              const uint32_t full = smem_u32(&bar_full[s]), dst = smem_u32(smem + s * Cfg::STAGE_BYTES);
-              tma_load_2d(dst, &tmXh, full, kb * BK, m0);
-              tma_load_2d(dst + 16384, &tmXl, full, kb * BK, m0);
-              tma_load_2d(dst + 32768, &tmW1h, full, kb * BK, i * Cfg::CHUNK);
-              tma_load_2d(dst + 49152, &tmW1l, full, kb * BK, i * Cfg::CHUNK);
+            for (int kb = 0; kb < 4; ++kb, ++kbg) {
+              mbar_wait(smem_u32(&bar_empty[kbg % STAGES]), (((uint32_t)(kbg / STAGES)) & 1u) ^ 1u);
+              if (elect_one()) {
+                uint32_t full;
+                const uint32_t dst = stage_begin(Cfg::F1_BYTES, full);
+                load(dst, &tmXh, full, kb * BK, m0);
+                load(dst + 16384, &tmXl, full, kb * BK, m0);
+                load(dst + 32768, &tmW1h, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
+                load(dst + 32768 + Cfg::W1_BYTES, &tmW1l, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
+              }
+              __syncwarp();
             }
           }
           if (i >= 1) {
-            for (int kb = 0; kb < 2; ++kb) {
-              const uint32_t s = acquire();
-              const uint32_t full = smem_u32(&bar_full[s]), dst = smem_u32(smem + s * Cfg::STAGE_BYTES);
-              tma_load_2d(dst, &tmW2h, full, (i - 1) * Cfg::CHUNK + kb * BK, 0);
-              tma_load_2d(dst + 32768, &tmW2l, full, (i - 1) * Cfg::CHUNK + kb * BK, 0);
+            for (int kb = 0; kb < 2; ++kb, ++kbg) {
+              mbar_wait(smem_u32(&bar_empty[kbg % STAGES]), (((uint32_t)(kbg / STAGES)) & 1u) ^ 1u);
+              if (elect_one()) {
+                uint32_t full;
+                const uint32_t dst = stage_begin(Cfg::F2_BYTES, full);
+                load(dst, &tmW2h, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
+                load(dst + Cfg::W2_BYTES, &tmW2l, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
+              }
+              __syncwarp();
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
-      constexpr uint32_t idesc1 = make_idesc(Cfg::CHUNK), idesc2 = make_idesc(256);
+    if (rank == 0) {
+      // ---------------------------------------------------------------- MMA issuer (2-SM: the leader)
+      // The whole warp walks the loop (uniform control flow); one elected lane issues each k-block.
+      constexpr uint32_t idesc1 = make_idesc(Cfg::CHUNK, BM * CG), idesc2 = make_idesc(256, BM * CG);
       const uint32_t hs_u = smem_u32(hs);
+      // one k-block (64 deep): 4 x (A_lo.W_hi + A_hi.W_lo + A_hi.W_hi), then release the ring slot
+      auto kblock = [&](uint32_t tacc, uint32_t sAh, uint32_t sAl, uint32_t sWh, uint32_t sWl, uint32_t idesc,
+                        bool first, uint64_t* slot_bar, uint64_t* bar2, uint64_t* bar3) {
+        if (elect_one()) {
+          uint64_t ah = make_desc(sAh), al = make_desc(sAl), wh = make_desc(sWh), wl = make_desc(sWl);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint32_t acc = (first && kk == 0) ? 0u : 1u;
+            if (CG == 1) {
+              umma(tacc, al, wh, idesc, acc); umma(tacc, ah, wl, idesc, 1u); umma(tacc, ah, wh, idesc, 1u);
+            } else {
+              umma_2sm(tacc, al, wh, idesc, acc); umma_2sm(tacc, ah, wl, idesc, 1u); umma_2sm(tacc, ah, wh, idesc, 1u);
+            }
+            ah += 2; al += 2; wh += 2; wl += 2;        // next 16-wide slice: +32 B (>> 4)
+          }
+          for (uint64_t* bar : {slot_bar, bar2, bar3})
+            if (bar) { if (CG == 1) umma_commit(smem_u32(bar)); else umma_commit_2sm(smem_u32(bar)); }
+        }
+        __syncwarp();
+      };
+      auto wait_epi = [&](uint64_t* bar, uint32_t parity) {     // barriers the epilogue warps arrive on
+        if (CG == 1) mbar_wait(smem_u32(bar), parity); else mbar_wait_cluster(smem_u32(bar), parity);
+      };
       int kbg = 0, g1 = 0, g2 = 0;                 // ring position, F1 chunks issued, F2 chunks issued
       for (int j = 0; j < nlocal; ++j) {
         for (int i = 0; i <= NC; ++i) {
           if (i < NC) {                            // F1(i)
             const int b = g1 & 1;
-            mbar_wait(smem_u32(&bar_a1empty[b]), (((uint32_t)g1 >> 1) & 1u) ^ 1u);
+            wait_epi(&bar_a1empty[b], (((uint32_t)g1 >> 1) & 1u) ^ 1u);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)(b * Cfg::CHUNK);
             for (int kb = 0; kb < 4; ++kb, ++kbg) {
               const int s = kbg % STAGES;
               mbar_wait(smem_u32(&bar_full[s]), ((uint32_t)(kbg / STAGES)) & 1u);
               tc_fence_after();
-              const uint32_t sXh = smem_u32(smem + s * Cfg::STAGE_BYTES), sXl = sXh + 16384;
-              const uint32_t sWh = sXh + 32768, sWl = sXh + 49152;
-#pragma unroll
-              for (int kk = 0; kk < BK / 16; ++kk) {
-                const uint32_t off = kk * 32;
-                const uint64_t ah = make_desc(sXh + off), al = make_desc(sXl + off);
-                const uint64_t wh = make_desc(sWh + off), wl = make_desc(sWl + off);
-                umma(tacc, al, wh, idesc1, (kb | kk) != 0 ? 1u : 0u);
-                umma(tacc, ah, wl, idesc1, 1u);
-                umma(tacc, ah, wh, idesc1, 1u);
-              }
-              umma_commit(smem_u32(&bar_empty[s]));
+              const uint32_t sXh = smem_u32(smem + s * Cfg::STAGE_BYTES);
+              kblock(tacc, sXh, sXh + 16384, sXh + 32768, sXh + 32768 + Cfg::W1_BYTES, idesc1, kb == 0,
+                     &bar_empty[s], kb == 3 ? &bar_a1full[b] : nullptr, nullptr);
             }
-            umma_commit(smem_u32(&bar_a1full[b]));
             ++g1;
           }
           if (i >= 1) {                            // F2(i - 1)
             if (i == 1) {                          // the previous tile's LayerNorm epilogue has drained acc2
-              mbar_wait(smem_u32(bar_a2empty), ((uint32_t)j & 1u) ^ 1u);
+              wait_epi(bar_a2empty, ((uint32_t)j & 1u) ^ 1u);
               tc_fence_after();
             }
-            mbar_wait(smem_u32(bar_hfull), (uint32_t)g2 & 1u);
+            wait_epi(bar_hfull, (uint32_t)g2 & 1u);
             tc_fence_after();
             const uint32_t tacc = tmem_base + 2u * Cfg::CHUNK;
             for (int kb = 0; kb < 2; ++kb, ++kbg) {
               const int s = kbg % STAGES;
               mbar_wait(smem_u32(&bar_full[s]), ((uint32_t)(kbg / STAGES)) & 1u);
               tc_fence_after();
-              const uint32_t sHh = hs_u + kb * 16384, sHl = hs_u + 32768 + kb * 16384;
-              const uint32_t sWh = smem_u32(smem + s * Cfg::STAGE_BYTES), sWl = sWh + 32768;
-#pragma unroll
-              for (int kk = 0; kk < BK / 16; ++kk) {
-                const uint32_t off = kk * 32;
-                const uint64_t ah = make_desc(sHh + off), al = make_desc(sHl + off);
-                const uint64_t wh = make_desc(sWh + off), wl = make_desc(sWl + off);
-                umma(tacc, al, wh, idesc2, ((i - 1) | kb | kk) != 0 ? 1u : 0u);
-                umma(tacc, ah, wl, idesc2, 1u);
-                umma(tacc, ah, wh, idesc2, 1u);
-              }
-              umma_commit(smem_u32(&bar_empty[s]));
+              const uint32_t sWh = smem_u32(smem + s * Cfg::STAGE_BYTES);
+              kblock(tacc, hs_u + kb * 16384, hs_u + 32768 + kb * 16384, sWh, sWh + Cfg::W2_BYTES, idesc2,
+                     i == 1 && kb == 0, &bar_empty[s], kb == 1 ? bar_hempty : nullptr,
+                     (kb == 1 && i == NC) ? bar_a2full : nullptr);
             }
-            umma_commit(smem_u32(bar_hempty));
             ++g2;
-            if (i == NC) umma_commit(smem_u32(bar_a2full));
           }
         }
       }
@@ -925,12 +1013,12 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
     const int q = warp & 3;                          // TMEM lane quarter
     const int hf = (warp - 2) >> 2;                  // column half of a chunk / of the output row
     const int row = q * 32 + lane;
-    uint8_t* const stg = s_stage + (warp - 2) * 2048;
+    uint8_t* const stg = hs + (warp - 2) * 2048;     // LayerNorm staging lives in the (then idle) Hs buffer
     uint32_t r[32];
     float v[32];
     int g = 0;                                       // hidden chunks handled so far
     for (int j = 0; j < nlocal; ++j) {
-      const int m0 = ((int)blockIdx.x + j * (int)gridDim.x) * BM;
+      const int m0 = ((cid + j * ncl) * CG + rank) * BM;
       // ---- E1: hidden chunks -> Hs
       for (int c = 0; c < NC; ++c, ++g) {
         const int b = g & 1;
@@ -946,7 +1034,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bar_a1empty[b]));
+        if (lane == 0) arrive_leader(&bar_a1empty[b]);
         mbar_wait(smem_u32(bar_hempty), ((uint32_t)g & 1u) ^ 1u);     // F2(g - 1) has read Hs
         // this thread's row, k-block hf: 128 B per plane = 8 x 16 B, 16-B index XOR (row & 7) (SWIZZLE_128B)
         uint8_t* const hrow = hs + hf * 16384 + row * 128;
@@ -960,7 +1048,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
           }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tcgen05.mma reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(bar_hfull));
+        if (lane == 0) arrive_leader(bar_hfull);
       }
       // ---- residual + LayerNorm on acc2 (same scheme as k_gemm_tc's LN epilogue)
       const int m = m0 + row;
@@ -978,7 +1066,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         load_plane_issue(rbh, p.ld_res, rows_valid, lane, gh);
         load_plane_issue(rbl, p.ld_res, rows_valid, lane, gl);
       }
-      mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);
+      mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);      // all F2 MMAs retired: acc2 complete, Hs idle
       tc_fence_after();
       float s1 = 0.0f, s2 = 0.0f;
       const float sc = p.inv_s2;
@@ -1046,17 +1134,19 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
         store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
       }
-      epi_bar_sync();                              // s_part is reused by the next tile
+      epi_bar_sync();                              // s_part / the staging rows are reused by the next tile
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(bar_a2empty));
+      if (lane == 0) arrive_leader(bar_a2empty);
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CG > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -1071,6 +1161,7 @@ typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuin
 static int g_force_bn = 0;   // MLDB_TC_BN=128: experiment knob (3-stage BN=128 tiles everywhere)
 
 struct TcCtx {
+  int ffn_2sm = 1;   // fused FFN on CTA pairs (cta_group::2); MLDB_FFN_2SM=0: one CTA per tile
   int ffn_fused = 1; // FFN1 + GELU + FFN2 + residual + LayerNorm as one launch (MLDB_FFN_FUSED=0: off)
   int cluster = 1;   // 2 = CTA pairs (cta_group::2 MMA, each CTA loads half of the W tile); MLDB_TC_2SM
   int dbg = 0;
@@ -1095,6 +1186,7 @@ TcCtx* tc_create(int device) {
   if (const char* e = getenv("MLDB_TC_DBG")) c->dbg = atoi(e);
   if (const char* e = getenv("MLDB_TC_BN")) g_force_bn = atoi(e);
   if (const char* e = getenv("MLDB_FFN_FUSED")) c->ffn_fused = atoi(e);
+  if (const char* e = getenv("MLDB_FFN_2SM")) c->ffn_2sm = atoi(e);
   if (const char* e = getenv("MLDB_TC_2SM")) c->cluster = atoi(e) ? 2 : 1;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   e = cudaSuccess;
@@ -1103,7 +1195,7 @@ TcCtx* tc_create(int device) {
   };
   opt_in(k_gemm_tc<256, 1>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1>, TileCfg<128, 1>::SMEM_BYTES);
   opt_in(k_gemm_tc<256, 2>, TileCfg<256, 2>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2>, TileCfg<128, 2>::SMEM_BYTES);
-  opt_in(k_ffn_tc, FfnCfg::SMEM_BYTES);
+  opt_in(k_ffn_tc<1>, FfnCfg<1>::SMEM_BYTES); opt_in(k_ffn_tc<2>, FfnCfg<2>::SMEM_BYTES);
   if (e != cudaSuccess) {
     mldb_set_err(std::string("cudaFuncSetAttribute(k_gemm_tc): ") + cudaGetErrorString(e));
     delete c;
@@ -1243,29 +1335,36 @@ bool tc_ffn_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, co
   if (!c || !c->ffn_fused) return false;
   if (!tc_gemm_supported(c, g1) || !tc_gemm_ln_supported(c, g2, l2)) return false;
   if (g1.K1 != 256 || g1.K2 > 0 || g2.K2 > 0 || g1.M != g2.M) return false;
-  if (g1.w.N % FfnCfg::CHUNK || g1.w.N > MAX_N || g1.w.N != g2.K1) return false;
+  if (g1.w.N % FfnCfg<1>::CHUNK || g1.w.N > MAX_N || g1.w.N != g2.K1) return false;
   if (g1.act != ACT_GELU || g1.out_f32 || g1.addtab || g1.zero_lengths) return false;
   if (g1.in_group < g1.M || g1.out_group != 0 || g1.out_off != 0 || l2.rowvec) return false;
   return true;
 }
 void tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, cudaStream_t st) {
   CUtensorMap mXh, mXl, mW1h, mW1l, mW2h, mW2l;
+  const int m_tiles = (g1.M + BM - 1) / BM;
+  const int cg = (c->ffn_2sm && m_tiles >= 2 && c->sm_count % 2 == 0) ? 2 : 1;
   const bool ok = make_map(c, &mXh, g1.a1.hi, g1.M, g1.K1, BM) && make_map(c, &mXl, g1.a1.lo(), g1.M, g1.K1, BM) &&
-                  make_map(c, &mW1h, g1.w.w, g1.w.N, g1.w.K, FfnCfg::CHUNK) &&
-                  make_map(c, &mW1l, g1.w.w + g1.w.plane_stride, g1.w.N, g1.w.K, FfnCfg::CHUNK) &&
-                  make_map(c, &mW2h, g2.w.w, g2.w.N, g2.w.K, 256) &&
-                  make_map(c, &mW2l, g2.w.w + g2.w.plane_stride, g2.w.N, g2.w.K, 256);
+                  make_map(c, &mW1h, g1.w.w, g1.w.N, g1.w.K, FfnCfg<1>::CHUNK / cg) &&
+                  make_map(c, &mW1l, g1.w.w + g1.w.plane_stride, g1.w.N, g1.w.K, FfnCfg<1>::CHUNK / cg) &&
+                  make_map(c, &mW2h, g2.w.w, g2.w.N, g2.w.K, 256 / cg) &&
+                  make_map(c, &mW2l, g2.w.w + g2.w.plane_stride, g2.w.N, g2.w.K, 256 / cg);
   if (!ok) {
     fprintf(stderr, "libmldb200: cuTensorMapEncodeTiled failed (ffn M=%d)\n", g1.M);
     c->ok = false;
     return;
   }
   FfnParams p{};
-  p.M = g1.M; p.m_tiles = (g1.M + BM - 1) / BM; p.n_chunks = g1.w.N / FfnCfg::CHUNK;
+  p.M = g1.M; p.m_tiles = m_tiles; p.n_chunks = g1.w.N / FfnCfg<1>::CHUNK;
   p.inv_s1 = g1.w.inv_scale; p.inv_s2 = g2.w.inv_scale;
   p.b1 = g1.w.bias; p.b2 = g2.w.bias; p.gamma = l2.gamma; p.beta = l2.beta;
   p.res_hi = l2.res.hi; p.res_lo = l2.res.hi ? l2.res.lo() : nullptr; p.ld_res = l2.res.cols;
   p.out_hi = l2.out.hi; p.out_lo = l2.out.lo(); p.ld_out = l2.out.cols;
-  const int grid = p.m_tiles < c->sm_count ? p.m_tiles : c->sm_count;
-  launch_pdl(k_ffn_tc, dim3(grid), dim3(NUM_THREADS), FfnCfg::SMEM_BYTES, st, mXh, mXl, mW1h, mW1l, mW2h, mW2l, p);
+  const int groups = (m_tiles + cg - 1) / cg;
+  const int ncl = groups < c->sm_count / cg ? groups : c->sm_count / cg;
+  if (cg == 2)
+    launch_pdl_cluster(k_ffn_tc<2>, dim3(ncl * 2), dim3(NUM_THREADS), FfnCfg<2>::SMEM_BYTES, st, 2, mXh, mXl, mW1h, mW1l,
+                       mW2h, mW2l, p);
+  else
+    launch_pdl(k_ffn_tc<1>, dim3(ncl), dim3(NUM_THREADS), FfnCfg<1>::SMEM_BYTES, st, mXh, mXl, mW1h, mW1l, mW2h, mW2l, p);
 }

@@ -198,10 +198,11 @@ int mldb_profile_op(mldb_handle* h, const char* op, int32_t B, int32_t S_ctx, in
 /* Debug aid for the kernel unit tests: y = act(A W^T + b), or LayerNorm(A W^T + b + R) when gamma is
  * given, through the engine's GEMM operators (use_tc: 1 = tcgen05 path, 0 = CUDA-core path).
  * A [M,K], R [M,N], out [M,N]: fp32 DEVICE; W [N,K], bias/gamma/beta [N]: fp32 HOST.  0 < K1 < K feeds
- * A as two concatenated sources (the skip-connection GEMM).  Synchronous. */
+ * A as two concatenated sources (the skip-connection GEMM).  split_out != 0: the plain epilogue writes
+ * split16 planes (the production path; N % 8 == 0) which are then widened to fp32.  Synchronous. */
 int mldb_debug_gemm(mldb_handle* h, const float* A, const float* W, const float* bias, const float* gamma,
                     const float* beta, const float* R, int32_t M, int32_t N, int32_t K, int32_t K1,
-                    int32_t act, int32_t use_tc, float* out, void* stream);
+                    int32_t act, int32_t use_tc, int32_t split_out, float* out, void* stream);
 
 /* Debug aid: one post-norm FFN block y = LayerNorm(x + W2 gelu(W1 x + b1) + b2) through the engine's
  * operators (cross_attention.py:266-271).  mode 0 = CUDA-core kernels, 1 = tcgen05 GEMMs as two

@@ -59,7 +59,7 @@ _SIGNATURES = {
     "mldb_sample_host": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mldb_profile_op": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
     "mldb_debug_gemm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                  C.c_int32, C.c_int32, _P, _P]),
+                                  C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mldb_debug_ffn": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mldb_last_error": (C.c_char_p, []),
     "mldb_abi_version": (C.c_int, []),

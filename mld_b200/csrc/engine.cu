@@ -1519,7 +1519,8 @@ __global__ void k_split_to_f32(ActBuf X, float* __restrict__ out, int64_t n) {
 }
 extern "C" int mldb_debug_gemm(mldb_handle* h, const float* A, const float* W, const float* bias,
                                const float* gamma, const float* beta, const float* R, int32_t M, int32_t N,
-                               int32_t K, int32_t K1, int32_t act, int32_t use_tc, float* out, void* stream) {
+                               int32_t K, int32_t K1, int32_t act, int32_t use_tc, int32_t split_out, float* out,
+                               void* stream) {
   if (!h || !A || !W || !out || M <= 0 || N <= 0 || K <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)stream;
@@ -1550,6 +1551,11 @@ extern "C" int mldb_debug_gemm(mldb_handle* h, const float* A, const float* W, c
     }
     LnArgs l; l.res = res; l.gamma = g; l.beta = b; l.M = M; l.d = N; l.out = o;
     op_gemm_ln(h, ga, l, cf32, st);
+    k_split_to_f32<<<nblk((int64_t)M * N), 256, 0, st>>>(o, out, (int64_t)M * N);
+  } else if (split_out && N % 8 == 0) {
+    TRY(alloc_act(h, M, N, &o));                   // the production epilogue: split16 planes
+    ga.out = o;
+    op_gemm(h, ga, st);
     k_split_to_f32<<<nblk((int64_t)M * N), 256, 0, st>>>(o, out, (int64_t)M * N);
   } else {
     ga.out_f32 = out; ga.ldc = N;

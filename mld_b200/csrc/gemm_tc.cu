@@ -107,6 +107,15 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// shared -> global bulk tensor store (box given by the map), tracked in the issuing thread's bulk group
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -202,6 +211,7 @@ struct TcParams {
   const float* rowvec; int rv_group;
   const float* gamma; const float* beta;
   const float* gamma2; const float* beta2;
+  int tma_out;   // fast-path epilogue drains through TMA stores (maps tmOh / tmOl cover out + out_col0)
   int dbg;   // timing experiments only (MLDB_TC_DBG): 1 = no global stores, 2 = no epilogue math/loads, 4 = no MMA
 };
 
@@ -224,13 +234,16 @@ constexpr int MAX_N = 1024;                          // bias staging capacity
 
 template <int BN, int CG = 1>
 struct TileCfg {
-  static constexpr int STAGES = CG == 2 ? (BN == 256 ? 3 : 4) : (BN == 256 ? 2 : 3);
+  static constexpr int STAGES = CG == 2 ? (BN == 256 ? 2 : 3) : (BN == 256 ? 2 : 3);
   static constexpr int A_BYTES = BM * BK * 2;          // one plane of the A tile (16 KB)
   static constexpr int W_BYTES = BN / CG * BK * 2;     // one plane of this CTA's part of the W tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator
   // bias[MAX_N] + gamma[256] + beta[256] + LN partials [2][2][128] + barriers
-  static constexpr int STG_BYTES = EPI_WARPS * 2048;   // per-warp 32 rows x 64 B transpose buffer
+  // per-warp staging: one 32 rows x 64 B transpose buffer (CG = 1: st.global epilogue) or two
+  // {hi, lo} pairs of them (CG = 2: the fast-path epilogue drains through TMA bulk stores)
+  static constexpr int STG_WARP = CG == 2 ? 8192 : 2048;
+  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;
   // bias[MAX_N] + bias2[256] + gamma[256] + beta[256] + LN partials + staging + barriers
   static constexpr int AUX_BYTES = MAX_N * 4 + 3 * 256 * 4 + 4 * 128 * 4 + 256 + STG_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;   // + alignment slack
@@ -363,6 +376,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
           const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
           const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
+          const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
           const TcParams p, const TcParams p2, const PairCfg pc) {
   using Cfg = TileCfg<BN, CG>;
   constexpr int CL = CG;
@@ -395,6 +409,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   const int nlocal = pair ? ((p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (p.n_tiles + 1)
                           : (ngroups - cid + ncl - 1) / ncl;
   const TcParams& pl = pair ? p2 : p;                         // the GEMM whose epilogue is the LayerNorm
+  const int nst = (p.dbg & 8) ? 2 : STAGES;                   // timing experiment: use two ring stages only
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -459,8 +474,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         }
         __syncwarp();
         for (int kb = 0; kb < q.kblocks; ++kb, ++kbg) {
-          const int s = kbg % STAGES;
-          const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
+          const int s = kbg % nst;
+          const uint32_t ph = (uint32_t)(kbg / nst) & 1u;
           mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
           if (elect_one()) {
           uint32_t full = smem_u32(&bar_full[s]);
@@ -519,8 +534,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
         const int nkb = decode_item(it, p, pair, BN, CL, rank).type ? p2.kblocks : p.kblocks;
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
-          const int s = kbg % STAGES;
-          const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
+          const int s = kbg % nst;
+          const uint32_t ph = (uint32_t)(kbg / nst) & 1u;
           mbar_wait(smem_u32(&bar_full[s]), ph);
           tc_fence_after();
           if (elect_one()) {
@@ -563,6 +578,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     uint32_t r[32];
     float v[32];
     int it = 0;
+    int tbuf = 0;                                    // staging pair for the next TMA store
     for (; it < nlocal; ++it) {
       const int as = it & 1;
       const WorkItem wi = decode_item(it, p, pair, BN, CL, rank);
@@ -572,7 +588,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       const int m = m0 + row;
       const bool row_ok = m < pp.M;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + hf * (BN / 2));
-      uint8_t* const stg = s_stage + (warp - 2) * 2048;
+      uint8_t* const stg = s_stage + (warp - 2) * Cfg::STG_WARP;
       const bool to_slot = pair && wi.type == 0;             // producer tile: write into the CTA's slot
       const int wrow0 = (to_slot ? wi.s0 : m0) + q * 32;     // first output row owned by this warp
       const int rows_valid = to_slot ? 32 : min(32, pp.M - wrow0);   // <= 0: nothing to write
@@ -605,7 +621,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
             }
             uint32_t ph[16], pl[16];
             pack_split(v, ph, pl);
-            if (!(p.dbg & 1)) {
+            if (CG == 2 && p.tma_out) {
+              // row-owner writes into a SWIZZLE_64B staging pair, then two bulk tensor stores (the map
+              // clips rows >= M); lane 0 owns the warp's bulk groups, at most one older pair in flight
+              if (lane == 0) tma_store_wait_read<1>();
+              __syncwarp();
+              uint8_t* const sb2 = stg + tbuf * 4096;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                *reinterpret_cast<uint4*>(sb2 + stg_off(lane, j)) = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                *reinterpret_cast<uint4*>(sb2 + 2048 + stg_off(lane, j)) = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+              }
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+              __syncwarp();
+              if (lane == 0 && !(p.dbg & 1)) {
+                tma_store_2d(&tmOh, smem_u32(sb2), nb, wrow0);
+                tma_store_2d(&tmOl, smem_u32(sb2 + 2048), nb, wrow0);
+                tma_store_commit();
+              }
+              tbuf ^= 1;
+            } else if (!(p.dbg & 1)) {
               const int64_t o = (int64_t)wrow0 * pp.ld_out + pp.out_col0 + nb;
               store_plane_coalesced(stg, ph, ohi + o, pp.ld_out, rows_valid, lane);
               store_plane_coalesced(stg, pl, olo + o, pp.ld_out, rows_valid, lane);
@@ -756,6 +791,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       if (lane == 0) { if (CG == 1) mbar_arrive(smem_u32(&bar_tempty[as])); else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[as]), 0)); }
     }
   }
+  if (CG == 2 && warp >= 2 && lane == 0) tma_store_wait_read<0>();   // staging fully read by the TMA engine
   tc_fence_before();
   __syncthreads();
   if (CG > 1) cluster_sync_all();   // nobody exits while the peer may still signal its barriers / read its smem
@@ -1163,7 +1199,8 @@ static int g_force_bn = 0;   // MLDB_TC_BN=128: experiment knob (3-stage BN=128 
 struct TcCtx {
   int ffn_2sm = 1;   // fused FFN on CTA pairs (cta_group::2); MLDB_FFN_2SM=0: one CTA per tile
   int ffn_fused = 1; // FFN1 + GELU + FFN2 + residual + LayerNorm as one launch (MLDB_FFN_FUSED=0: off)
-  int cluster = 1;   // 2 = CTA pairs (cta_group::2 MMA, each CTA loads half of the W tile); MLDB_TC_2SM
+  int no_tma_store = 0;   // MLDB_TC_TMA_STORE=0: 2-SM kernels keep the st.global epilogue
+  int cluster = 2;   // 2 = CTA pairs (cta_group::2 MMA, each CTA loads half of the W tile); MLDB_TC_2SM
   int dbg = 0;
   int device = 0;
   int sm_count = 148;
@@ -1188,6 +1225,7 @@ TcCtx* tc_create(int device) {
   if (const char* e = getenv("MLDB_FFN_FUSED")) c->ffn_fused = atoi(e);
   if (const char* e = getenv("MLDB_FFN_2SM")) c->ffn_2sm = atoi(e);
   if (const char* e = getenv("MLDB_TC_2SM")) c->cluster = atoi(e) ? 2 : 1;
+  if (const char* e = getenv("MLDB_TC_TMA_STORE")) c->no_tma_store = atoi(e) ? 0 : 1;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   e = cudaSuccess;
   auto opt_in = [&](auto kernel, int bytes) {
@@ -1215,6 +1253,19 @@ static bool make_map(const TcCtx* c, CUtensorMap* m, const __half* base, int row
   CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// output map for the TMA-store epilogue: fp16 plane [rows, cols] with row pitch ld, 32 x 32 boxes whose
+// shared-memory image is SWIZZLE_64B (= stg_off); rows / columns beyond the extents are clipped
+static bool make_map_out(const TcCtx* c, CUtensorMap* m, const __half* base, int rows, int cols, int ld) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(__half)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = c->encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)base, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
@@ -1278,13 +1329,20 @@ void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   }
   TcParams p, p2{};
   fill_params(c, g, ln, bn, &p);
+  CUtensorMap mOh = mA1h, mOl = mA1l;
+  if (cl == 2 && !ln && g.out.hi && !g.out_f32 && !g.addtab && !g.zero_lengths && g.in_group >= g.M &&
+      g.out_group == 0 && g.out_off == 0 && !c->no_tma_store) {
+    if (make_map_out(c, &mOh, g.out.hi + g.out_col0, g.M, g.w.N, g.out.cols) &&
+        make_map_out(c, &mOl, g.out.lo() + g.out_col0, g.M, g.w.N, g.out.cols))
+      p.tma_out = 1;
+  }
   const PairCfg pc{0, nullptr};
   const int ngroups = ((p.m_tiles + cl - 1) / cl) * p.n_tiles;
   const int ncl = ngroups < c->sm_count / cl ? ngroups : c->sm_count / cl;
   dim3 grid(ncl * cl);
 #define MLDB_LAUNCH(BN_, CL_)                                                                                   \
   launch_pdl_cluster(k_gemm_tc<BN_, CL_>, grid, dim3(NUM_THREADS), TileCfg<BN_, CL_>::SMEM_BYTES, st, CL_, mA1h, \
-                     mA1l, mA2h, mA2l, mWh, mWl, mA1h, mA1l, mWh, mWl, p, p2, pc)
+                     mA1l, mA2h, mA2l, mWh, mWl, mA1h, mA1l, mWh, mWl, mOh, mOl, p, p2, pc)
   if (bn == 256) { if (cl == 2) MLDB_LAUNCH(256, 2); else MLDB_LAUNCH(256, 1); }
   else           { if (cl == 2) MLDB_LAUNCH(128, 2); else MLDB_LAUNCH(128, 1); }
 #undef MLDB_LAUNCH
@@ -1321,7 +1379,7 @@ void tc_gemm_pair(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs
   fill_params(c, g2, &l2, 256, &p2);
   const PairCfg pc{1, counters};
   launch_pdl(k_gemm_tc<256, 1>, dim3(grid), dim3(NUM_THREADS), TileCfg<256, 1>::SMEM_BYTES, st, mAh, mAl, mAh, mAl, mWh, mWl,
-             mBh, mBl, mVh, mVl, p, p2, pc);
+             mBh, mBl, mVh, mVl, mAh, mAl, p, p2, pc);
 }
 
 // FFN block (linear1 + GELU + linear2 + residual + LayerNorm) as one launch, d = 256.

@@ -72,7 +72,7 @@ class Engine:
         check(self.lib.mldb_profile_op(self._h, op.encode(), B, S_ctx, iters, C.byref(ms)), "mldb_profile_op")
         return float(ms.value)
 
-    def debug_gemm(self, A, W, bias=None, gamma=None, beta=None, R=None, K1=0, act=0, use_tc=True):
+    def debug_gemm(self, A, W, bias=None, gamma=None, beta=None, R=None, K1=0, act=0, use_tc=True, split_out=False):
         """Kernel unit-test hook (mldb_debug_gemm): A [M,K] (device), W [N,K] / bias / gamma / beta (host)."""
         A = _f32c(A, self.device)
         Wc = W.detach().float().contiguous().cpu()
@@ -82,7 +82,7 @@ class Engine:
         N = Wc.shape[0]
         out = torch.empty((M, N), dtype=torch.float32, device=self.device)
         check(self.lib.mldb_debug_gemm(self._h, _ptr(A), _ptr(Wc), _ptr(host[0]), _ptr(host[1]), _ptr(host[2]),
-                                       _ptr(Rd), M, N, K, K1, act, int(use_tc), _ptr(out), self._stream()),
+                                       _ptr(Rd), M, N, K, K1, act, int(use_tc), int(split_out), _ptr(out), self._stream()),
               "mldb_debug_gemm")
         return out
 

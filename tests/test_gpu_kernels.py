@@ -55,6 +55,10 @@ def test_tc_gemm_epilogues(eng, M, N, K, K1, act, ln):
     assert torch.isfinite(y_tc).all()
     assert _rel(y_cc, ref) < 5e-6, "CUDA-core kernel vs float64 reference"
     assert _rel(y_tc, ref) < 5e-6, "tcgen05 kernel vs float64 reference"
+    if not ln and N % 8 == 0:
+        # the production epilogue: split16 planes (TMA bulk stores on the CTA-pair kernels)
+        y_sp = eng.debug_gemm(A, W, bias, K1=K1, act=act, use_tc=True, split_out=True)
+        assert _rel(y_sp, ref) < 5e-6, "tcgen05 kernel, split16 output"
 
 
 @pytest.mark.parametrize("M,ff", [(100, 1024), (128 * 3 + 5, 1024), (148 * 128 * 2 + 777, 1024), (1000, 512)])

@@ -336,7 +336,7 @@ __device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&
     const float4 b = b4[i];
     float x0 = fmaf(__uint_as_float(r[4 * i + 0]), s, b.x), x1 = fmaf(__uint_as_float(r[4 * i + 1]), s, b.y);
     float x2 = fmaf(__uint_as_float(r[4 * i + 2]), s, b.z), x3 = fmaf(__uint_as_float(r[4 * i + 3]), s, b.w);
-    if (ACT == ACT_GELU) { x0 = gelu_fast(x0); x1 = gelu_fast(x1); x2 = gelu_fast(x2); x3 = gelu_fast(x3); }
+    if (ACT == ACT_GELU) { gelu_fast2(x0, x1); gelu_fast2(x2, x3); }
     if (ACT == ACT_RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
     if (ACT == ACT_SILU) { x0 = silu_f(x0); x1 = silu_f(x1); x2 = silu_f(x2); x3 = silu_f(x3); }
     v[4 * i + 0] = x0; v[4 * i + 1] = x1; v[4 * i + 2] = x2; v[4 * i + 3] = x3;

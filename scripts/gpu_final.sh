@@ -5,6 +5,6 @@ timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python scripts/prof_step.py > gpurun_out/prof_step.log 2>&1
-PROF_ITERS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_gemm_tc|k_attn" -c 20 -f -o gpurun_out/prof_ops python scripts/prof_ops.py > gpurun_out/prof_ops.log 2>&1
-tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; tail -4 gpurun_out/bench.err; cut -c1-600 gpurun_out/bench.log; cut -c1-400 gpurun_out/bench_ref.log; tail -2 gpurun_out/prof_step.log; tail -2 gpurun_out/prof_ops.log
+MLDB_BRANCHES=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv python scripts/prof_step.py > gpurun_out/prof_step.log 2>&1
+PROF_ITERS=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_gemm_tc|k_attn|k_ffn_tc" -c 8 -f -o gpurun_out/prof_ops python scripts/prof_ops.py qkv attn outproj_ln ffn > gpurun_out/prof_ops.log 2>&1
+tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/smoke.log; tail -4 gpurun_out/bench.err; cut -c1-900 gpurun_out/bench.log; cut -c1-400 gpurun_out/bench_ref.log; tail -2 gpurun_out/prof_step.log; tail -2 gpurun_out/prof_ops.log

@@ -972,11 +972,48 @@ static int enc_plan(mldb_handle* h, int kind, int B, int Bx, int S, Plan** out) 
 
 // condition tokens -> X0 (once per batch; step invariant, hoisted out of the loop although the
 // reference recomputes emb_proj every step, mld_denoiser.py:165)
-static int place_condition(mldb_handle* h, Plan* p, const void* cond, cudaStream_t st) {
+// Independent lanes: with `lanes` > 1 the motions are split into contiguous groups, and lane k keeps ALL
+// its sequences - the unconditional and the conditional copy of its motions - in one contiguous block
+// of workspace rows ([uncond b0..b1 | cond b0..b1]), so that the whole 50-step loop of a lane
+// (token assembly, stack, guidance + scheduler step) is one dependency chain with no per-step join.
+// Sequence g of the caller's [uncond B | cond B] order sits in slot lane_slot(g).
+static int reverse_lanes(const mldb_handle* h, const Plan* p, int B) {
+  const mldb_config& c = h->cfg;
+  const bool tc_ctx = c.cond_kind == MLDB_COND_TEXT && c.text_dim != c.latent_dim && h->use_tc && p->ctx_split.hi &&
+                      c.text_dim % 64 == 0;
+  // Off by default: measured 2.3 % SLOWER than the per-step fork/join of denoiser_pass (1826 vs 1869
+  // motions/s) - free-running lanes drift into the same phase and their identical heavy kernels contend,
+  // while the per-step join keeps the two ranges one kernel apart.  MLDB_LANES=1 enables it.
+  static const bool lanes_on = getenv("MLDB_LANES") && atoi(getenv("MLDB_LANES")) != 0;
+  if (!lanes_on || !tc_ctx || h->branches <= 1 || h->chunk_seqs > 0) return 1;
+  if (B < 2 * h->branches || (int64_t)p->Bx * p->Ntok < 2 * 128 * h->branches) return 1;
+  return h->branches;
+}
+
+static int place_condition(mldb_handle* h, Plan* p, const void* cond, cudaStream_t st, int lanes = 1) {
   const mldb_config& c = h->cfg;
   const int d = c.latent_dim, Bx = p->Bx;
   if (c.cond_kind == MLDB_COND_TEXT) {
     const int S = p->S;
+    if (lanes > 1) {
+      // ReLU + split once over the whole context, then one emb_proj GEMM per (lane, half) block
+      const int B = p->B, X = Bx / B;
+      k_rows_to_split<<<nblk((int64_t)Bx * S * c.text_dim), 256, 0, st>>>(p->ctx_split, (const float*)cond, c.text_dim,
+                                                                       Bx * S, c.text_dim, 1 << 30, 0, 0, 0, nullptr, 1);
+      count_launch(h);
+      for (int k = 0; k < lanes; ++k) {
+        const int b0 = (int)((int64_t)B * k / lanes), nb = (int)((int64_t)B * (k + 1) / lanes) - b0;
+        for (int hh = 0; hh < X; ++hh) {
+          const int64_t g0 = (int64_t)hh * B + b0, slot0 = (int64_t)X * b0 + (int64_t)hh * nb;
+          GemmArgs g; g.M = nb * S; g.w = h->emb_proj; g.a1 = rows_of(p->ctx_split, g0 * S, nb * S); g.K1 = c.text_dim;
+          g.out = rows_of(p->ws.x0, slot0 * p->Ntok, nb * p->Ntok);
+          g.in_group = S; g.out_group = p->Ntok; g.out_off = c.n_lat + 1; g.addtab = h->query_pe;
+          op_gemm(h, g, st);
+        }
+      }
+      CK(cudaGetLastError());
+      return MLDB_OK;
+    }
     if (c.text_dim != d) {
       // emb_proj = ReLU -> Linear (mld_denoiser.py:67-68): ReLU + hi/lo split in one pass over the
       // CLIP context, then the tensor-core GEMM writes the tokens (+ PE) straight into X0
@@ -1007,6 +1044,19 @@ static int place_condition(mldb_handle* h, Plan* p, const void* cond, cudaStream
   return MLDB_OK;
 }
 
+// the stack + final norm over the n sequences of workspace (slice) wsv: eps[n, n_lat*d]
+static void denoiser_range(mldb_handle* h, Plan* p, const StackWs& wsv, int n, float* eps, cudaStream_t s) {
+  const mldb_config& c = h->cfg;
+  SeqInfo si;
+  StackWs w = wsv;
+  ActBuf x = run_stack(h, h->den, w.x0, ActBuf{}, w, si, s);
+  // encoder.norm on the latent tokens only (cross_attention.py:62-63, mld_denoiser.py:206)
+  LnArgs l; l.res = x; l.gamma = h->den.norm.g; l.beta = h->den.norm.b; l.M = n * c.n_lat; l.d = c.latent_dim;
+  if (w.n_sel == 0) { l.sel_group = c.n_lat; l.in_group = p->Ntok; }   // else x is already compact
+  l.out_f32 = eps; l.ld_out = c.latent_dim;
+  op_ln(h, l, s);
+}
+
 // one denoiser pass over the assembled tokens: eps[Bx, n_lat*d] = norm(stack(X0))[:n_lat]
 static void denoiser_pass(mldb_handle* h, Plan* p, const float* latents, int lat_mod, const float* tt,
                           float* eps_out, cudaStream_t st) {
@@ -1015,20 +1065,13 @@ static void denoiser_pass(mldb_handle* h, Plan* p, const float* latents, int lat
   launch_pdl(k_assemble_tokens, dim3(nblk((int64_t)p->Bx * (c.n_lat + 1) * d)), dim3(256), 0, st,
              p->ws.x0, p->Ntok, p->Bx, lat_mod, c.n_lat, d, latents, (const float*)h->query_pe, tt);
   count_launch(h);
-  SeqInfo si;
   // Sequences are independent, so the stack runs over chunks of `chunk_seqs` sequences that reuse
   // the SAME workspace rows: a chunk's activations (qkv, FFN hidden, ...) then stay resident in the
   // 126 MB L2 from the kernel that writes them to the kernel that reads them instead of streaming
   // through HBM (~870 MB per layer for the whole 40 448-token batch).
   const int cs = (h->chunk_seqs > 0 && h->chunk_seqs < p->Bx) ? h->chunk_seqs : p->Bx;
   auto run_range = [&](const StackWs& wsv, int s0, int n, cudaStream_t s) {
-    StackWs w = wsv;
-    ActBuf x = run_stack(h, h->den, w.x0, ActBuf{}, w, si, s);
-    // encoder.norm on the latent tokens only (cross_attention.py:62-63, mld_denoiser.py:206)
-    LnArgs l; l.res = x; l.gamma = h->den.norm.g; l.beta = h->den.norm.b; l.M = n * c.n_lat; l.d = d;
-    if (w.n_sel == 0) { l.sel_group = c.n_lat; l.in_group = p->Ntok; }   // else x is already compact
-    l.out_f32 = eps_out + (size_t)s0 * c.n_lat * d; l.ld_out = d;
-    op_ln(h, l, s);
+    denoiser_range(h, p, wsv, n, eps_out + (size_t)s0 * c.n_lat * d, s);
   };
   const int nbr = (cs == p->Bx && h->branches > 1 && p->Bx * p->Ntok >= 2 * 128 * h->branches) ? h->branches : 1;
   if (nbr > 1) {
@@ -1223,11 +1266,41 @@ static int run_reverse(mldb_handle* h, const void* cond, const float* init_noise
   TRY(enc_plan(h, 0, B, Bx, S, &p));
   const int d = c.latent_dim;
   const int64_t per = (int64_t)c.n_lat * d;
-  TRY(place_condition(h, p, cond, st));
+  const int lanes = reverse_lanes(h, p, B);
+  TRY(place_condition(h, p, cond, st, lanes));
   // latents = init_noise * init_noise_sigma (== 1 for DDIM/DDPM), mld.py:310
   CK(cudaMemcpyAsync(p->latents, init_noise, (size_t)B * per * sizeof(float), cudaMemcpyDeviceToDevice, st));
   const int nsteps = (int)h->timesteps.size();
   TRY(run_graphed(h, p, st, [&](cudaStream_t s) {
+    if (lanes > 1) {
+      // one dependency chain per lane for the whole loop (fork once, join once): a lane's kernel tails,
+      // its small kernels (token assembly, final norm, guidance + scheduler step) and its kernel
+      // boundaries are filled by the other lanes' GEMMs, and the lanes drift out of lockstep
+      const int X = Bx / B;
+      cudaEventRecord(h->ev_fork, s);
+      for (int k = 0; k < lanes; ++k) {
+        cudaStream_t sk = k == 0 ? s : h->br_stream[k - 1];
+        if (k) cudaStreamWaitEvent(sk, h->ev_fork, 0);
+        const int b0 = (int)((int64_t)B * k / lanes), nb = (int)((int64_t)B * (k + 1) / lanes) - b0;
+        const StackWs wk = ws_slice(p->ws, X * b0, X * nb);
+        float* const eps_k = p->eps + (size_t)X * b0 * per;
+        float* const lat_k = p->latents + (size_t)b0 * per;
+        for (int i = 0; i < nsteps; ++i) {                                       // mld.py:323
+          launch_pdl(k_assemble_tokens, dim3(nblk((int64_t)X * nb * (c.n_lat + 1) * d)), dim3(256), 0, sk, wk.x0, p->Ntok,
+                     X * nb, nb, c.n_lat, d, (const float*)lat_k, (const float*)h->query_pe,
+                     (const float*)(h->d_tt + (size_t)i * d));
+          count_launch(h);
+          denoiser_range(h, p, wk, X * nb, eps_k, sk);
+          launch_pdl(k_cfg_sched, dim3(nblk((int64_t)nb * per)), dim3(256), 0, sk, (const float*)eps_k, lat_k,
+                     (const float*)nullptr, (int64_t)nb * per, cfg_on ? 1 : 0, c.guidance_scale,
+                     (const StepCoef*)h->d_coefs, i);
+          count_launch(h);
+        }
+        if (k) cudaEventRecord(h->ev_join[k - 1], sk);
+      }
+      for (int k = 1; k < lanes; ++k) cudaStreamWaitEvent(s, h->ev_join[k - 1], 0);
+      return;
+    }
     for (int i = 0; i < nsteps; ++i) {                                           // mld.py:323
       denoiser_pass(h, p, p->latents, B, h->d_tt + (size_t)i * d, p->eps, s);
       launch_pdl(k_cfg_sched, dim3(nblk(B * per)), dim3(256), 0, s, (const float*)p->eps, p->latents,

@@ -652,6 +652,8 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   if (env) h->chunk_seqs = atoi(env);
   env = getenv("MLDB_GRAPH");
   if (env && !strcmp(env, "0")) h->use_graph = false;
+  env = getenv("MLDB_LANES");
+  if (env) h->lanes = atoi(env) != 0;
   env = getenv("MLDB_BRANCHES");
   if (env) h->branches = std::min(std::max(atoi(env), 1), (int)mldb_handle::MAX_BRANCHES);
   e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
@@ -697,6 +699,8 @@ extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* val
     h->pair_chunk = atoi(value) != 0;
   } else if (!strcmp(name, "chunk")) {
     h->chunk_seqs = atoi(value);
+  } else if (!strcmp(name, "lanes")) {
+    h->lanes = atoi(value) != 0;
   } else if (!strcmp(name, "branches")) {
     h->branches = std::min(std::max(atoi(value), 1), (int)mldb_handle::MAX_BRANCHES);
   } else if (!strcmp(name, "graph")) {
@@ -983,9 +987,8 @@ static int reverse_lanes(const mldb_handle* h, const Plan* p, int B) {
                       c.text_dim % 64 == 0;
   // Off by default: measured 2.3 % SLOWER than the per-step fork/join of denoiser_pass (1826 vs 1869
   // motions/s) - free-running lanes drift into the same phase and their identical heavy kernels contend,
-  // while the per-step join keeps the two ranges one kernel apart.  MLDB_LANES=1 enables it.
-  static const bool lanes_on = getenv("MLDB_LANES") && atoi(getenv("MLDB_LANES")) != 0;
-  if (!lanes_on || !tc_ctx || h->branches <= 1 || h->chunk_seqs > 0) return 1;
+  // while the per-step join keeps the two ranges one kernel apart.  Option `lanes` / MLDB_LANES=1 enables it.
+  if (!h->lanes || !tc_ctx || h->branches <= 1 || h->chunk_seqs > 0) return 1;
   if (B < 2 * h->branches || (int64_t)p->Bx * p->Ntok < 2 * 128 * h->branches) return 1;
   return h->branches;
 }

@@ -122,6 +122,7 @@ struct mldb_handle {
   // so one range's kernel tails (316 m-tiles on 148 SMs = 2.13 rounds) and kernel boundaries are
   // filled by the other range's kernels.  1 = off.
   int branches = 2;
+  bool lanes = false;        // free-running per-lane chains over the whole reverse loop (see reverse_lanes)
   static constexpr int MAX_BRANCHES = 4;
   cudaStream_t br_stream[MAX_BRANCHES - 1] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_BRANCHES - 1] = {};

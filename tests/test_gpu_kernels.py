@@ -126,3 +126,8 @@ def test_scheduling_options_do_not_change_results(built_lib):
         out = eng.sample(ctx, noise, lengths, want=("latents",))["latents"]
         assert torch.equal(out, base), f"option {name}={value} changed the result"
         eng.set_option(name, "0")
+    # free-running per-lane chains (each lane holds the uncond + cond copies of its motions contiguously)
+    eng.set_option("branches", "3")
+    eng.set_option("lanes", "1")
+    out = eng.sample(ctx, noise, lengths, want=("latents",))["latents"]
+    assert torch.equal(out, base), "lanes changed the result"

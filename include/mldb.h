@@ -217,7 +217,16 @@ const char* mldb_last_error(void);
 int mldb_abi_version(void);
 /* number of kernel launches the library has issued (graph replays count their nodes) */
 int64_t mldb_launch_count(const mldb_handle* h);
-/* set an engine option by name ("gemm" = "tc"|"simt", "chunk" = sequences per pass, ...) */
+/* Set an engine option by name.  Options only change HOW the same arithmetic is scheduled; results are
+ * identical for every setting (tests/test_gpu_kernels.py).  Each also has an environment default:
+ *   "gemm"       "tc" | "simt"   tcgen05 kernels (default) or the CUDA-core reference kernels   MLDB_GEMM
+ *   "ffn_fused"  0 | 1           fused FFN kernel k_ffn_tc (default 1)                           MLDB_FFN_FUSED
+ *   "branches"   1..4            concurrent sub-batch branches inside a denoiser step (2)        MLDB_BRANCHES
+ *   "lanes"      0 | 1           free-running per-lane chains over the whole reverse loop (0)    MLDB_LANES
+ *   "graph"      0 | 1           CUDA-graph replay of the step loop (1)                          MLDB_GRAPH
+ *   "chunk", "pair_chunk", "ffn_pair"   measured-slower experiments kept for the record (0)
+ * Environment only: MLDB_TC_2SM (CTA-pair GEMMs, 1), MLDB_FFN_2SM (CTA-pair fused FFN, 1),
+ * MLDB_TC_TMA_STORE (TMA-store epilogue of the pair GEMMs, 1), MLDB_PDL (programmatic dependent launch, 1). */
 int mldb_set_option(mldb_handle* h, const char* name, const char* value);
 
 #ifdef __cplusplus

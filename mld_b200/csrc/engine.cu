@@ -652,6 +652,8 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   if (env) h->chunk_seqs = atoi(env);
   env = getenv("MLDB_GRAPH");
   if (env && !strcmp(env, "0")) h->use_graph = false;
+  env = getenv("MLDB_BRANCH_ROUND");
+  if (env) h->branch_round = atoi(env) != 0;
   env = getenv("MLDB_LANES");
   if (env) h->lanes = atoi(env) != 0;
   env = getenv("MLDB_BRANCHES");
@@ -699,6 +701,8 @@ extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* val
     h->pair_chunk = atoi(value) != 0;
   } else if (!strcmp(name, "chunk")) {
     h->chunk_seqs = atoi(value);
+  } else if (!strcmp(name, "branch_round")) {
+    h->branch_round = atoi(value) != 0;
   } else if (!strcmp(name, "lanes")) {
     h->lanes = atoi(value) != 0;
   } else if (!strcmp(name, "branches")) {
@@ -1076,14 +1080,26 @@ static void denoiser_pass(mldb_handle* h, Plan* p, const float* latents, int lat
   auto run_range = [&](const StackWs& wsv, int s0, int n, cudaStream_t s) {
     denoiser_range(h, p, wsv, n, eps_out + (size_t)s0 * c.n_lat * d, s);
   };
-  const int nbr = (cs == p->Bx && h->branches > 1 && p->Bx * p->Ntok >= 2 * 128 * h->branches) ? h->branches : 1;
+  int nbr = (cs == p->Bx && h->branches > 1 && p->Bx * p->Ntok >= 2 * 128 * h->branches) ? h->branches : 1;
+  int bounds[mldb_handle::MAX_BRANCHES + 1];
+  for (int k = 0; k <= nbr; ++k) bounds[k] = (int)((int64_t)p->Bx * k / nbr);
+  if (nbr > 1 && h->branch_round && h->use_tc) {
+    // whole-round ranges: as many sequences as fill every SM with exactly one 128-row tile (no partial
+    // last round inside a range's persistent kernels), the remainder as one more, small range
+    const int per = (h->sm_count * 128) / p->Ntok;
+    const int chunks = per > 0 ? (p->Bx + per - 1) / per : 0;
+    if (chunks >= 2 && chunks <= mldb_handle::MAX_BRANCHES) {
+      nbr = chunks;
+      for (int k = 0; k <= nbr; ++k) bounds[k] = std::min(p->Bx, k * per);
+    }
+  }
   if (nbr > 1) {
     // fork: every range waits for the token assembly; join: the caller's stream waits for every range
     cudaEventRecord(h->ev_fork, st);
     for (int k = 0; k < nbr; ++k) {
       cudaStream_t s = k == 0 ? st : h->br_stream[k - 1];
       if (k) cudaStreamWaitEvent(s, h->ev_fork, 0);
-      const int s0 = (int)((int64_t)p->Bx * k / nbr), s1 = (int)((int64_t)p->Bx * (k + 1) / nbr);
+      const int s0 = bounds[k], s1 = bounds[k + 1];
       run_range(ws_slice(p->ws, s0, s1 - s0), s0, s1 - s0, s);
       if (k) cudaEventRecord(h->ev_join[k - 1], s);
     }

@@ -35,7 +35,7 @@ extern "C" {
 #define MLDB_ERR_STATE 3     /* call out of order (weights not finalized, ...) */
 #define MLDB_ERR_UNSUPPORTED 4
 
-#define MLDB_ABI_VERSION 1
+#define MLDB_ABI_VERSION 2
 
 typedef struct mldb_handle mldb_handle;
 

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmldb200.so")
 
-MLDB_ABI_VERSION = 1
+MLDB_ABI_VERSION = 2
 COND_TEXT, COND_ACTION = 0, 1
 ARCH_TRANS_ENC, ARCH_TRANS_DEC = 0, 1
 VAE_NONE, VAE_MLD, VAE_ACTOR = 0, 1, 2

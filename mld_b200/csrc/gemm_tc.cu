@@ -1,4 +1,5 @@
-// tcgen05 (5th-gen tensor core) split-fp16 GEMM for sm_100a with fused epilogues.
+// tcgen05 (5th-gen tensor core) split-fp16 kernels for sm_100a: the persistent GEMM with fused
+// epilogues (k_gemm_tc) and the fused FFN block (k_ffn_tc).
 //
 //   D[128 x BN] (fp32, TMEM) = A_hi W_hi^T + A_lo W_hi^T + A_hi W_lo^T        per 128-row tile
 //
@@ -6,13 +7,17 @@
 // [N, K] (PyTorch's [out, in] layout is already the K-major B operand), also split into hi/lo
 // planes.  Three kind::f16 MMAs per K-step reproduce the reference's fp32 GEMM to ~1e-6.
 //
-// CTA = 6 warps: warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA issuer
-// (one lane), warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  Operands stream through a
-// STAGES-deep ring of 128B-swizzled shared-memory tiles (BK = 64 halves = one swizzle row) filled
-// by cp.async.bulk.tensor (TMA) and released by tcgen05.commit; the accumulator is read back with
-// tcgen05.ld.  Epilogues: bias (+ positional table) + activation -> split16 / fp32 store, or
-// bias + residual + LayerNorm over the full row (BN == N == 256) -> split16 store, with the row's
-// pre-norm values parked in TMEM between the statistics passes.
+// CTA = 10 warps, one CTA per SM, persistent over tiles: warp 0 = TMA producer, warp 1 = TMEM
+// allocator + MMA issuer (both walk their loops warp-uniformly, one elect.sync lane issues), warps
+// 2..9 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter split the columns).
+// Operands stream through a ring of 128B-swizzled shared-memory tiles (BK = 64 halves = one swizzle
+// row) filled by cp.async.bulk.tensor (TMA) and released by tcgen05.commit; accumulators are
+// double-buffered in TMEM and read back with tcgen05.ld.  CG = 2 runs CTA pairs (cta_group::2,
+// M = 256 MMAs issued by the leader, each CTA stages its own A rows and half of the W tile).
+// Epilogues: bias (+ positional table) + activation -> split16 (TMA bulk stores on the pair kernels,
+// st.global through a warp transpose otherwise) / fp32 store, or bias + residual + LayerNorm over
+// the full row (BN == N == 256) -> split16 store, with the row's pre-norm values parked in TMEM
+// between the statistics and the normalise pass.
 #include "gemm_tc.h"
 
 #include <cuda.h>
@@ -372,7 +377,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 }
 
 // ------------------------------------------------------------------------------ the kernel
-// Persistent: CTA c walks tiles c, c + gridDim.x, ...; tile t -> (m = t / n_tiles, n = t % n_tiles).
+// Persistent: CTA (pair) c walks items c, c + #CTAs (pairs), ...; item t -> (m = t / n_tiles, n = t % n_tiles).
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the TMA/MMA main loop of tile i + 1.
 template <int BN, int CG>
@@ -818,7 +823,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
 //   F2(c): acc2 (TMEM, 256 cols)      += Hs[128 x 128] . W2[:, c*128..]^T        (2 k-blocks)
 // and finishes with the residual + LayerNorm epilogue on acc2.  The MMA warp issues
 // F1(0) F1(1) F2(0) F1(2) F2(1) ... so E1(c) runs under F1(c+1); the TMA warp streams the x / W1 /
-// W2 k-blocks through one 2 x 64 KB ring in exactly that order.
+// W2 k-blocks through one ring (2 x 64 KB; 3 x 48 KB per CTA of a pair) in exactly that order.
 struct FfnParams {
   int M, m_tiles, n_chunks;
   float inv_s1, inv_s2;

@@ -350,7 +350,8 @@ static void op_gemm_ln(mldb_handle* h, GemmArgs g, LnArgs l, float* cf32, cudaSt
 }
 static void op_ln(mldb_handle* h, const LnArgs& l, cudaStream_t st) { simt_ln(l, st); count_launch(h); }
 static void op_attn(mldb_handle* h, const AttnArgs& a, cudaStream_t st) {
-  if (h->use_tc && mma_attention_supported(a)) mma_attention(a, st);
+  if (h->use_tc && h->attn_tc && tc_attention_supported(a)) tc_attention(a, st);   // experimental, off by default
+  else if (h->use_tc && mma_attention_supported(a)) mma_attention(a, st);
   else simt_attention(a, st);
   count_launch(h);
 }
@@ -652,6 +653,8 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   if (env) h->chunk_seqs = atoi(env);
   env = getenv("MLDB_GRAPH");
   if (env && !strcmp(env, "0")) h->use_graph = false;
+  env = getenv("MLDB_ATTN_TC");
+  if (env) h->attn_tc = atoi(env) != 0;
   env = getenv("MLDB_BRANCH_ROUND");
   if (env) h->branch_round = atoi(env) != 0;
   env = getenv("MLDB_LANES");
@@ -701,6 +704,8 @@ extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* val
     h->pair_chunk = atoi(value) != 0;
   } else if (!strcmp(name, "chunk")) {
     h->chunk_seqs = atoi(value);
+  } else if (!strcmp(name, "attn_tc")) {
+    h->attn_tc = atoi(value) != 0;
   } else if (!strcmp(name, "branch_round")) {
     h->branch_round = atoi(value) != 0;
   } else if (!strcmp(name, "lanes")) {

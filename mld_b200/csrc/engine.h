@@ -122,6 +122,7 @@ struct mldb_handle {
   // so one range's kernel tails (316 m-tiles on 148 SMs = 2.13 rounds) and kernel boundaries are
   // filled by the other range's kernels.  1 = off.
   int branches = 2;
+  bool attn_tc = false;      // EXPERIMENTAL tcgen05 attention core (attn_tc.cu): not yet validated on hardware
   bool branch_round = false; // branch ranges sized to whole rounds of m-tiles (+ a small remainder range)
   bool lanes = false;        // free-running per-lane chains over the whole reverse loop (see reverse_lanes)
   static constexpr int MAX_BRANCHES = 4;

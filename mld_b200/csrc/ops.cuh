@@ -71,6 +71,10 @@ void simt_attention(const AttnArgs& a, cudaStream_t st);
 bool mma_attention_supported(const AttnArgs& a);
 void mma_attention_init();
 void mma_attention(const AttnArgs& a, cudaStream_t st);
+// attn_tc.cu: tcgen05 attention core (EXPERIMENTAL, not yet validated on hardware; engine option attn_tc)
+bool tc_attention_init(int device);
+bool tc_attention_supported(const AttnArgs& a);
+void tc_attention(const AttnArgs& a, cudaStream_t st);
 void simt_init();
 // --- tcgen05 implementations (gemm_tc.cu) ---
 struct TcCtx;

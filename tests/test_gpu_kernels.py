@@ -1,6 +1,8 @@
 """GPU kernel unit tests (pytest -m gpu): each GEMM epilogue of the tcgen05 kernel against a
 float64 torch reference of the same op, and against the CUDA-core kernel, through the C ABI's
 debug hook.  Tolerance 5e-6 relative-to-max: the split-fp16 3-product scheme keeps ~22 bits."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -131,3 +133,27 @@ def test_scheduling_options_do_not_change_results(built_lib):
     eng.set_option("lanes", "1")
     out = eng.sample(ctx, noise, lengths, want=("latents",))["latents"]
     assert torch.equal(out, base), "lanes changed the result"
+
+
+@pytest.mark.skipif(os.environ.get("MLDB_EXPERIMENTAL") != "1",
+                    reason="attn_tc.cu has not been validated on hardware yet (set MLDB_EXPERIMENTAL=1)")
+def test_tc_attention_matches_mma(built_lib):
+    """The experimental tcgen05 attention core (option attn_tc) against the product mma.sync kernel on
+    the whole sampling path (ragged lengths exercise the key mask in the VAE decoder's fallback)."""
+    from mld_b200 import synth
+    from mld_b200.engine import Engine, make_config
+    eng = Engine(make_config(), 0)
+    eng.load_state_dict(synth.denoiser_state_dict(1234), "denoiser.")
+    eng.load_state_dict(synth.mld_vae_state_dict(4321), "vae.")
+    eng.finalize()
+    eng.set_mean_std(*synth.mean_std())
+    eng.set_timesteps(4)
+    ctx, noise = synth.text_context(5, 77, seed=25), synth.init_noise(5, seed=26)
+    lengths = [196, 64, 120, 33, 196]
+    a = eng.sample(ctx, noise, lengths, want=("latents", "joints"))
+    a = {k: v.clone() for k, v in a.items()}
+    eng.set_option("attn_tc", "1")
+    b = eng.sample(ctx, noise, lengths, want=("latents", "joints"))
+    assert torch.isfinite(b["latents"]).all()
+    assert _rel(b["latents"], a["latents"]) < 1e-4
+    assert _rel(b["joints"], a["joints"]) < 1e-4

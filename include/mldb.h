@@ -212,6 +212,13 @@ int mldb_debug_ffn(mldb_handle* h, const float* X, const float* W1, const float*
                    const float* b2, const float* gamma, const float* beta, int32_t M, int32_t d, int32_t ff,
                    int32_t mode, float* out, void* stream);
 
+/* Debug aid: the multi-head attention core softmax(Q K^T / sqrt(hd)) V per (sequence, head) on a packed
+ * QKV [nseq*L, 3*heads*hd] fp32 DEVICE tensor (q | k | v column blocks, torch in_proj order); lengths
+ * (device int32 [nseq], nullable) = valid keys per sequence.  mode 0 = CUDA-core kernel, 1 = mma.sync
+ * kernel (product path), 2 = tcgen05 kernel (experimental).  out [nseq*L, heads*hd] fp32 DEVICE.  Synchronous. */
+int mldb_debug_attention(mldb_handle* h, const float* QKV, const int32_t* lengths, int32_t nseq, int32_t L,
+                         int32_t heads, int32_t hd, int32_t mode, float* out, void* stream);
+
 /* Introspection */
 const char* mldb_last_error(void);
 int mldb_abi_version(void);

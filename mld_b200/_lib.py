@@ -61,6 +61,7 @@ _SIGNATURES = {
     "mldb_debug_gemm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mldb_debug_ffn": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "mldb_debug_attention": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mldb_last_error": (C.c_char_p, []),
     "mldb_abi_version": (C.c_int, []),
     "mldb_launch_count": (C.c_int64, [_P]),

@@ -1702,3 +1702,30 @@ extern "C" int mldb_debug_ffn(mldb_handle* h, const float* X, const float* W1, c
   if (e != cudaSuccess) FAIL(MLDB_ERR_CUDA, "debug ffn: %s", cudaGetErrorString(e));
   return MLDB_OK;
 }
+
+extern "C" int mldb_debug_attention(mldb_handle* h, const float* QKV, const int32_t* lengths, int32_t nseq, int32_t L,
+                                    int32_t heads, int32_t hd, int32_t mode, float* out, void* stream) {
+  if (!h || !QKV || !out || nseq <= 0 || L <= 0 || heads <= 0 || hd <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n_alloc0 = h->allocs.size();
+  const int d = heads * hd, M = nseq * L;
+  ActBuf qkv, o;
+  TRY(alloc_act(h, M, 3 * d, &qkv));
+  TRY(alloc_act(h, M, d, &o));
+  k_rows_to_split<<<nblk((int64_t)M * 3 * d), 256, 0, st>>>(qkv, QKV, 3 * d, M, 3 * d, 1 << 30, 0, 0, 0, nullptr);
+  AttnArgs a; a.q = qkv; a.q_col0 = 0; a.Lq = L; a.kv = qkv; a.k_col0 = d; a.v_col0 = 2 * d; a.Lk = L;
+  a.nseq = nseq; a.heads = heads; a.hd = hd; a.lengths = lengths; a.kv_prefix = 0; a.out = o;
+  int rc = MLDB_OK;
+  if (mode == 0) simt_attention(a, st);
+  else if (mode == 1 && mma_attention_supported(a)) mma_attention(a, st);
+  else if (mode == 2 && tc_attention_supported(a)) tc_attention(a, st);
+  else rc = MLDB_ERR_UNSUPPORTED;
+  if (rc == MLDB_OK) k_split_to_f32<<<nblk((int64_t)M * d), 256, 0, st>>>(o, out, (int64_t)M * d);
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  while (h->allocs.size() > n_alloc0) { cudaFree(h->allocs.back()); h->allocs.pop_back(); }
+  if (e != cudaSuccess) FAIL(MLDB_ERR_CUDA, "debug attention: %s", cudaGetErrorString(e));
+  if (rc != MLDB_OK) FAIL(rc, "attention mode %d does not support this shape", mode);
+  return MLDB_OK;
+}

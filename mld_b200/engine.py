@@ -98,6 +98,17 @@ class Engine:
                                       self._stream()), "mldb_debug_ffn")
         return out
 
+    def debug_attention(self, qkv, nseq, L, heads, lengths=None, mode=1):
+        """Kernel unit-test hook (mldb_debug_attention): qkv [nseq*L, 3*heads*hd] (device), mode 0 CUDA-core,
+        1 mma.sync (product), 2 tcgen05 (experimental).  Returns [nseq*L, heads*hd]."""
+        qkv = _f32c(qkv, self.device)
+        d = qkv.shape[1] // 3
+        ln = None if lengths is None else torch.as_tensor(lengths, dtype=torch.int32, device=self.device).contiguous()
+        out = torch.empty((nseq * L, d), dtype=torch.float32, device=self.device)
+        check(self.lib.mldb_debug_attention(self._h, _ptr(qkv), _ptr(ln), nseq, L, heads, d // heads, int(mode), _ptr(out),
+                                            self._stream()), "mldb_debug_attention")
+        return out
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.mldb_launch_count(self._h))

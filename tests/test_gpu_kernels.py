@@ -157,3 +157,30 @@ def test_tc_attention_matches_mma(built_lib):
     assert torch.isfinite(b["latents"]).all()
     assert _rel(b["latents"], a["latents"]) < 1e-4
     assert _rel(b["joints"], a["joints"]) < 1e-4
+
+
+def _attention_ref(qkv, nseq, L, heads, lengths=None):
+    d = qkv.shape[1] // 3
+    hd = d // heads
+    q, k, v = (t.reshape(nseq, L, heads, hd).permute(0, 2, 1, 3).double() for t in qkv.split(d, dim=1))
+    s = q @ k.transpose(-1, -2) / hd ** 0.5
+    if lengths is not None:
+        mask = torch.arange(L)[None, :] >= torch.as_tensor(lengths)[:, None]
+        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    return (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(nseq * L, d)
+
+
+@pytest.mark.skipif(os.environ.get("MLDB_EXPERIMENTAL") != "1",
+                    reason="debug hook + attn_tc.cu not validated on hardware yet (set MLDB_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("nseq,L,masked", [(3, 79, False), (5, 79, True), (2, 128, False), (4, 33, True), (300, 79, False)])
+def test_attention_kernels_unit(eng, nseq, L, masked):
+    """Attention cores in isolation against float64: CUDA-core, mma.sync (product) and tcgen05 (experimental)."""
+    heads, hd = 4, 64
+    g = torch.Generator().manual_seed(nseq * 131 + L)
+    qkv = torch.randn(nseq * L, 3 * heads * hd, generator=g)
+    lengths = [max(1, (7 * i + 5) % L) for i in range(nseq)] if masked else None
+    ref = _attention_ref(qkv, nseq, L, heads, lengths)
+    for mode, name in ((0, "cuda-core"), (1, "mma.sync"), (2, "tcgen05")):
+        y = eng.debug_attention(qkv, nseq, L, heads, lengths, mode=mode).cpu().double()
+        assert torch.isfinite(y).all(), name
+        assert _rel(y, ref) < 5e-6, name

@@ -35,7 +35,7 @@ extern "C" {
 #define MLDB_ERR_STATE 3     /* call out of order (weights not finalized, ...) */
 #define MLDB_ERR_UNSUPPORTED 4
 
-#define MLDB_ABI_VERSION 2
+#define MLDB_ABI_VERSION 3
 
 typedef struct mldb_handle mldb_handle;
 
@@ -150,9 +150,11 @@ int mldb_denoise(mldb_handle* h, const float* sample, int64_t timestep, const vo
  *   cond        [2B, S_ctx, text_dim] uncond half first (mld.py:225-230) when guidance > 1,
  *               else [B, ...]; int64 [2B,1] for the action model
  *   init_noise  [B, n_lat, d] (or [B, T, nfeats] when diffusion_only)
- *   step_noise  DDPM only: [n_steps, B, T, nfeats] or NULL
+ *   step_noise  DDPM only (required then): the N(0,1) draws of scheduler.step, [n_steps, B, n_lat, d]
+ *               (or [n_steps, B, T, nfeats] when diffusion_only); NULL for DDIM
  *   latents_out [n_lat, B, d]  (mld.py:359)  (or [T, B, nfeats])
- * The n scheduler steps are replayed from one CUDA graph per (B, S_ctx, T) shape. */
+ * The n scheduler steps are replayed from one CUDA graph per (B, S_ctx, T) shape (the no-VAE model: one
+ * captured step, replayed n times with a device-side step counter). */
 int mldb_diffusion_reverse(mldb_handle* h, const void* cond, const float* init_noise,
                            const float* step_noise, const int32_t* lengths, int32_t B,
                            int32_t S_ctx, int32_t T, float* latents_out, void* stream);
@@ -183,10 +185,30 @@ int mldb_sample(mldb_handle* h, const void* cond, const float* init_noise,
 /* Same as mldb_sample but through HOST buffers (pinned or pageable): copies cond/noise/
  * lengths host->device, runs, copies joints device->host, all on `stream`; returns after
  * enqueue (synchronise the stream before reading joints_host).  This is the call the
- * end-to-end benchmark times. */
+ * end-to-end benchmark times.  With a communicator attached joints_host receives the GATHERED motions
+ * [nranks * B, T, njoints, 3]. */
 int mldb_sample_host(mldb_handle* h, const void* cond_host, const float* init_noise_host,
                      const int32_t* lengths_host, int32_t B, int32_t S_ctx, int32_t T,
                      float* joints_host, void* stream);
+
+/* ---- multi-GPU: batch-sharded replicas + ONE all-gather of the finished motions.
+ * One process (handle) per GPU; NCCL is bound at run time (dlopen libnccl.so.2).  Either build the
+ * communicator here - rank 0 calls mldb_comm_unique_id, ships the 128 bytes to the other ranks by any means
+ * (torch.distributed object broadcast, MPI, a file), every rank calls mldb_comm_init - or attach an existing
+ * ncclComm_t with mldb_comm_attach.  The communicator is destroyed with the handle when it was built here. */
+int mldb_comm_unique_id(void* out128 /* HOST, 128 bytes */);
+int mldb_comm_init(mldb_handle* h, const void* unique_id128, int32_t nranks, int32_t rank);
+int mldb_comm_attach(mldb_handle* h, void* nccl_comm, int32_t nranks, int32_t rank);
+int mldb_comm_info(const mldb_handle* h, int32_t* nranks, int32_t* rank);
+/* ncclAllGather of `count` floats per rank on `stream` (in place when local == global + rank * count). */
+int mldb_allgather(mldb_handle* h, const float* local, float* global, int64_t count, void* stream);
+/* mldb_sample on this rank's shard, the joints of all ranks gathered into joints_global
+ * [nranks * B, T, njoints, 3]: this rank's joints are written straight into its slot and the in-place
+ * all-gather runs on a side stream, overlapping whatever is enqueued next on `stream`.  Alternate two
+ * joints_global buffers between consecutive calls; mldb_gather_wait makes `stream` wait for the last gather. */
+int mldb_sample_gather(mldb_handle* h, const void* cond, const float* init_noise, const int32_t* lengths,
+                       int32_t B, int32_t S_ctx, int32_t T, float* joints_global, void* stream);
+int mldb_gather_wait(mldb_handle* h, void* stream);
 
 /* Profiling aid used by bench.py's roofline leg: time one operator of denoiser layer 0 in
  * isolation on the (B, S_ctx) workspace (`iters` back-to-back launches between CUDA events on an
@@ -194,6 +216,12 @@ int mldb_sample_host(mldb_handle* h, const void* cond_host, const float* init_no
  * avg_ms_out: HOST float. */
 int mldb_profile_op(mldb_handle* h, const char* op, int32_t B, int32_t S_ctx, int32_t iters,
                     float* avg_ms_out);
+
+/* Profiling aid: device time of every scheduler step of the reverse loop (the kernels of the captured graph
+ * launched eagerly on an internal stream with a CUDA event between steps).  ms_out: HOST float[n_steps].
+ * Synchronous.  bench.py reports the median as the step p50. */
+int mldb_profile_steps(mldb_handle* h, const void* cond, const float* init_noise, int32_t B, int32_t S_ctx,
+                       float* ms_out);
 
 /* Debug aid for the kernel unit tests: y = act(A W^T + b), or LayerNorm(A W^T + b + R) when gamma is
  * given, through the engine's GEMM operators (use_tc: 1 = tcgen05 path, 0 = CUDA-core path).
@@ -212,28 +240,47 @@ int mldb_debug_ffn(mldb_handle* h, const float* X, const float* W1, const float*
                    const float* b2, const float* gamma, const float* beta, int32_t M, int32_t d, int32_t ff,
                    int32_t mode, float* out, void* stream);
 
-/* Debug aid: the multi-head attention core softmax(Q K^T / sqrt(hd)) V per (sequence, head) on a packed
- * QKV [nseq*L, 3*heads*hd] fp32 DEVICE tensor (q | k | v column blocks, torch in_proj order); lengths
- * (device int32 [nseq], nullable) = valid keys per sequence.  mode 0 = CUDA-core kernel, 1 = mma.sync
- * kernel (product path), 2 = tcgen05 kernel (experimental).  out [nseq*L, heads*hd] fp32 DEVICE.  Synchronous. */
-int mldb_debug_attention(mldb_handle* h, const float* QKV, const int32_t* lengths, int32_t nseq, int32_t L,
-                         int32_t heads, int32_t hd, int32_t mode, float* out, void* stream);
+/* Debug aid: the multi-head attention core softmax(Q K^T / sqrt(hd)) V per (sequence, head).
+ *   KV == NULL: Q is a packed QKV [nseq*Lq, 3*heads*hd] fp32 DEVICE tensor (q | k | v column blocks, torch
+ *               in_proj order; self-attention, Lk == Lq) - the layout the denoiser / VAE stacks use;
+ *   KV != NULL: Q [nseq*Lq, heads*hd] and KV [nseq*Lk, 2*heads*hd] (k | v) - cross-attention.
+ * lengths (device int32 [nseq], nullable): valid keys per sequence = min(Lk, kv_prefix + lengths[s]).
+ * mode 0 = CUDA-core kernel, 1 = mma.sync kernel, 2 = tcgen05 kernel (product path).
+ * out [nseq*Lq, heads*hd] fp32 DEVICE.  Synchronous. */
+int mldb_debug_attention(mldb_handle* h, const float* Q, const float* KV, const int32_t* lengths, int32_t kv_prefix,
+                         int32_t nseq, int32_t Lq, int32_t Lk, int32_t heads, int32_t hd, int32_t mode, float* out,
+                         void* stream);
 
 /* Introspection */
 const char* mldb_last_error(void);
 int mldb_abi_version(void);
 /* number of kernel launches the library has issued (graph replays count their nodes) */
 int64_t mldb_launch_count(const mldb_handle* h);
+/* Which kernel every operator of the path was ENQUEUED on since the last reset (recorded launches: a CUDA
+ * graph counts once, at capture).  out: HOST int64[MLDB_KSTAT_COUNT], index = MLDB_KSTAT_*.  Lets a caller
+ * (and the tests) assert that nothing fell back from the tcgen05 kernels to the CUDA-core kernels. */
+#define MLDB_KSTAT_GEMM_TC 0      /* k_gemm_tc, plain epilogue */
+#define MLDB_KSTAT_GEMM_LN_TC 1   /* k_gemm_tc, fused residual + LayerNorm epilogue */
+#define MLDB_KSTAT_FFN_TC 2       /* k_ffn_tc (fused FFN block) */
+#define MLDB_KSTAT_ATTN_TC 3      /* k_attn_tc (tcgen05 attention) */
+#define MLDB_KSTAT_ATTN_MMA 4     /* k_attn_mma (mma.sync attention; option attn=mma) */
+#define MLDB_KSTAT_ATTN_SIMT 5    /* k_attn_simt (CUDA cores) */
+#define MLDB_KSTAT_GEMM_SIMT 6    /* k_gemm_simt (CUDA cores: odd-K embeddings, time MLP, gemm=simt) */
+#define MLDB_KSTAT_LN_SIMT 7      /* k_ln stand-alone LayerNorm (stack-final norms, cross-attention collapse) */
+#define MLDB_KSTAT_LN_UNFUSED 8   /* k_ln behind a GEMM whose LayerNorm could NOT be fused (a fallback) */
+#define MLDB_KSTAT_MISC 9         /* token assembly, scheduler step, feats2joints, ... */
+#define MLDB_KSTAT_COUNT 10
+int mldb_kernel_stats(const mldb_handle* h, int64_t* out, int32_t n);
+int mldb_reset_kernel_stats(mldb_handle* h);
+
 /* Set an engine option by name.  Options only change HOW the same arithmetic is scheduled; results are
- * identical for every setting (tests/test_gpu_kernels.py).  Each also has an environment default:
- *   "gemm"       "tc" | "simt"   tcgen05 kernels (default) or the CUDA-core reference kernels   MLDB_GEMM
- *   "ffn_fused"  0 | 1           fused FFN kernel k_ffn_tc (default 1)                           MLDB_FFN_FUSED
- *   "branches"   1..4            concurrent sub-batch branches inside a denoiser step (2)        MLDB_BRANCHES
- *   "lanes"      0 | 1           free-running per-lane chains over the whole reverse loop (0)    MLDB_LANES
- *   "graph"      0 | 1           CUDA-graph replay of the step loop (1)                          MLDB_GRAPH
- *   "chunk", "pair_chunk", "ffn_pair"   measured-slower experiments kept for the record (0)
- * Environment only: MLDB_TC_2SM (CTA-pair GEMMs, 1), MLDB_FFN_2SM (CTA-pair fused FFN, 1),
- * MLDB_TC_TMA_STORE (TMA-store epilogue of the pair GEMMs, 1), MLDB_PDL (programmatic dependent launch, 1). */
+ * identical (gemm, attn: to fp32 re-association noise) for every setting (tests/test_gpu_kernels.py).
+ *   "gemm"       "tc" | "simt"          tcgen05 kernels (default) or the CUDA-core reference kernels  MLDB_GEMM
+ *   "attn"       "tc" | "mma" | "simt"  attention core: tcgen05 (default), mma.sync, CUDA cores       MLDB_ATTN
+ *   "ffn_fused"  0 | 1                  fused FFN kernel k_ffn_tc (default 1)
+ *   "branches"   1..4                   concurrent sub-batch branches inside a denoiser step (2)      MLDB_BRANCHES
+ *   "graph"      0 | 1                  CUDA-graph replay of the step loop (1)                        MLDB_GRAPH
+ * Environment only: MLDB_PDL (programmatic dependent launch, 1). */
 int mldb_set_option(mldb_handle* h, const char* name, const char* value);
 
 #ifdef __cplusplus

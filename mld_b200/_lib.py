@@ -12,12 +12,15 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmldb200.so")
 
-MLDB_ABI_VERSION = 2
+MLDB_ABI_VERSION = 3
 COND_TEXT, COND_ACTION = 0, 1
 ARCH_TRANS_ENC, ARCH_TRANS_DEC = 0, 1
 VAE_NONE, VAE_MLD, VAE_ACTOR = 0, 1, 2
 SCHED_DDIM, SCHED_DDPM = 0, 1
 DTYPE_F32 = 0
+# mldb_kernel_stats indices (MLDB_KSTAT_* in include/mldb.h)
+KSTAT_NAMES = ("gemm_tc", "gemm_ln_tc", "ffn_tc", "attn_tc", "attn_mma", "attn_simt", "gemm_simt", "ln_simt",
+               "ln_unfused", "misc")
 
 
 class MldbConfig(C.Structure):
@@ -58,10 +61,21 @@ _SIGNATURES = {
     "mldb_sample": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "mldb_sample_host": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mldb_profile_op": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_float)]),
+    "mldb_profile_steps": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, _P]),
     "mldb_debug_gemm": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "mldb_debug_ffn": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
-    "mldb_debug_attention": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "mldb_debug_attention": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       C.c_int32, _P, _P]),
+    "mldb_comm_unique_id": (C.c_int, [_P]),
+    "mldb_comm_init": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
+    "mldb_comm_attach": (C.c_int, [_P, _P, C.c_int32, C.c_int32]),
+    "mldb_comm_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mldb_allgather": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    "mldb_sample_gather": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "mldb_gather_wait": (C.c_int, [_P, _P]),
+    "mldb_kernel_stats": (C.c_int, [_P, _P, C.c_int32]),
+    "mldb_reset_kernel_stats": (C.c_int, [_P]),
     "mldb_last_error": (C.c_char_p, []),
     "mldb_abi_version": (C.c_int, []),
     "mldb_launch_count": (C.c_int64, [_P]),

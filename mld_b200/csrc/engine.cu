@@ -42,6 +42,19 @@ extern "C" int mldb_abi_version(void) { return MLDB_ABI_VERSION; }
     if (rc__ != MLDB_OK) return rc__; \
   } while (0)
 
+// Every ABI call runs on the handle's device and restores the caller's current device afterwards
+// (a single-process multi-GPU program must not find torch.cuda.current_device() changed under it).
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 static inline void count_launch(mldb_handle* h, int n = 1) {
   if (h->capturing) h->capture_nodes += n; else h->launches += n;
 }
@@ -168,8 +181,10 @@ static int upload_f32(mldb_handle* h, const float* src, size_t n, float** out) {
 }
 static const RawTensor& rt(mldb_handle* h, const std::string& k) { return h->raw.at(k); }
 
-// Pack rows [row0, row0+N) of a host [*, K] fp32 matrix into split fp16 planes scaled by 2^s.
-static int pack_linear(mldb_handle* h, const float* W, int N, int K, const float* bias, LinW* out) {
+// Pack a host [N, K] fp32 matrix into split fp16 planes scaled by 2^s.  Kpad > K zero-pads the rows
+// (odd K such as the 263 motion features: the tensor-core GEMM wants K % 64 == 0).
+static int pack_linear(mldb_handle* h, const float* W, int N, int K, const float* bias, LinW* out, int Kpad = 0) {
+  if (Kpad < K) Kpad = K;
   float mx = 0.0f;
   for (int64_t i = 0; i < (int64_t)N * K; ++i) mx = std::max(mx, fabsf(W[i]));
   int s = 0;
@@ -178,17 +193,18 @@ static int pack_linear(mldb_handle* h, const float* W, int N, int K, const float
     s = std::max(-14, std::min(14, s));
   }
   const float sc = ldexpf(1.0f, s);
-  std::vector<__half> buf((size_t)2 * N * K);
-  for (int64_t i = 0; i < (int64_t)N * K; ++i) {
-    const float w = W[i] * sc;
-    const __half hi = __float2half_rn(w);
-    buf[i] = hi;
-    buf[(size_t)N * K + i] = __float2half_rn(w - __half2float(hi));
-  }
+  std::vector<__half> buf((size_t)2 * N * Kpad, __float2half_rn(0.0f));
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      const float w = W[(size_t)n * K + k] * sc;
+      const __half hi = __float2half_rn(w);
+      buf[(size_t)n * Kpad + k] = hi;
+      buf[(size_t)N * Kpad + (size_t)n * Kpad + k] = __float2half_rn(w - __half2float(hi));
+    }
   TRY(dev_alloc(h, (void**)&out->w, buf.size() * sizeof(__half)));
   CK(cudaMemcpy(out->w, buf.data(), buf.size() * sizeof(__half), cudaMemcpyHostToDevice));
-  out->plane_stride = (int64_t)N * K;
-  out->N = N; out->K = K; out->inv_scale = ldexpf(1.0f, -s);
+  out->plane_stride = (int64_t)N * Kpad;
+  out->N = N; out->K = Kpad; out->inv_scale = ldexpf(1.0f, -s);
   out->bias = nullptr;
   if (bias) TRY(upload_f32(h, bias, N, &out->bias));
   static int next_id = 0;
@@ -196,13 +212,13 @@ static int pack_linear(mldb_handle* h, const float* W, int N, int K, const float
   return MLDB_OK;
 }
 static int pack_named(mldb_handle* h, const std::string& wkey, const std::string& bkey, LinW* out,
-                      int row0 = 0, int nrows = -1) {
+                      int row0 = 0, int nrows = -1, bool pad_k = false) {
   const RawTensor& w = rt(h, wkey);
   const int K = (int)w.shape.back();
   const int Nall = (int)w.shape[0];
   if (nrows < 0) nrows = Nall;
   const float* b = bkey.empty() ? nullptr : rt(h, bkey).host.data() + row0;
-  return pack_linear(h, w.host.data() + (size_t)row0 * K, nrows, K, b, out);
+  return pack_linear(h, w.host.data() + (size_t)row0 * K, nrows, K, b, out, pad_k ? (K + 63) / 64 * 64 : 0);
 }
 static int pack_ln(mldb_handle* h, const std::string& p, int d, LnW* out) {
   TRY(upload_f32(h, rt(h, p + "weight").host.data(), d, &out->g));
@@ -330,30 +346,52 @@ static StepCoef make_coef(const mldb_handle* h, int64_t t, int n_inference) {
 static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
 // ----------------------------------------------------------------------------- op dispatch
+static inline void kcount(mldb_handle* h, int kind) { h->kstat[kind]++; count_launch(h); }
 static void op_gemm(mldb_handle* h, const GemmArgs& g, cudaStream_t st) {
-  if (h->use_tc && tc_gemm_supported(h->tc, g)) tc_gemm(h->tc, g, nullptr, st);
-  else simt_gemm(g, st);
-  count_launch(h);
+  if (h->use_tc && tc_gemm_supported(h->tc, g)) {
+    if (!tc_gemm(h->tc, g, nullptr, st)) h->op_failed = true;
+    kcount(h, MLDB_KSTAT_GEMM_TC);
+    return;
+  }
+  simt_gemm(g, st);
+  kcount(h, MLDB_KSTAT_GEMM_SIMT);
 }
 // GEMM followed by residual + LayerNorm (one fused tcgen05 kernel when the tile covers a row)
 static void op_gemm_ln(mldb_handle* h, GemmArgs g, LnArgs l, float* cf32, cudaStream_t st) {
   if (h->use_tc && tc_gemm_ln_supported(h->tc, g, l)) {
-    tc_gemm(h->tc, g, &l, st);
-    count_launch(h);
+    if (!tc_gemm(h->tc, g, &l, st)) h->op_failed = true;
+    kcount(h, MLDB_KSTAT_GEMM_LN_TC);
     return;
   }
   g.out = ActBuf{}; g.out_f32 = cf32; g.ldc = g.w.N;
   op_gemm(h, g, st);
   l.c = cf32; l.ldc = g.w.N;
   simt_ln(l, st);
-  count_launch(h);
+  kcount(h, h->use_tc ? MLDB_KSTAT_LN_UNFUSED : MLDB_KSTAT_LN_SIMT);
 }
-static void op_ln(mldb_handle* h, const LnArgs& l, cudaStream_t st) { simt_ln(l, st); count_launch(h); }
+static void op_ln(mldb_handle* h, const LnArgs& l, cudaStream_t st) { simt_ln(l, st); kcount(h, MLDB_KSTAT_LN_SIMT); }
 static void op_attn(mldb_handle* h, const AttnArgs& a, cudaStream_t st) {
-  if (h->use_tc && h->attn_tc && tc_attention_supported(a)) tc_attention(a, st);   // experimental, off by default
-  else if (h->use_tc && mma_attention_supported(a)) mma_attention(a, st);
-  else simt_attention(a, st);
-  count_launch(h);
+  if (h->use_tc && h->attn_kind == 0 && tc_attention_supported(a)) {
+    if (!tc_attention(a, st)) h->op_failed = true;
+    kcount(h, MLDB_KSTAT_ATTN_TC);
+  } else if (h->use_tc && h->attn_kind <= 1 && mma_attention_supported(a)) {
+    mma_attention(a, st);
+    kcount(h, MLDB_KSTAT_ATTN_MMA);
+  } else {
+    simt_attention(a, st);
+    kcount(h, MLDB_KSTAT_ATTN_SIMT);
+  }
+}
+// the fused FFN block when the shape allows it, else the two GEMMs
+static void op_ffn(mldb_handle* h, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, float* cf32, cudaStream_t st) {
+  if (h->use_tc && tc_ffn_supported(h->tc, g1, g2, l2)) {
+    // one launch: the hidden activations stay in shared memory / TMEM (gemm_tc.cu k_ffn_tc)
+    if (!tc_ffn(h->tc, g1, g2, l2, st)) h->op_failed = true;
+    kcount(h, MLDB_KSTAT_FFN_TC);
+    return;
+  }
+  op_gemm(h, g1, st);
+  op_gemm_ln(h, g2, l2, cf32, st);
 }
 
 // ----------------------------------------------------------------------------- workspaces
@@ -428,66 +466,26 @@ static StackWs ws_slice(const StackWs& ws, int s0, int n) {
   w.sx = sel(ws.sx); w.sq = sel(ws.sq); w.satt = sel(ws.satt); w.sx1 = sel(ws.sx1); w.sh = sel(ws.sh); w.sout = sel(ws.sout);
   return w;
 }
-// Producer -> consumer pairs whose intermediate is larger than L2 at full batch (qkv: 124 MB,
-// FFN hidden: 166 MB) run over row chunks that REUSE one chunk-sized intermediate buffer: the
-// consumer kernel then reads it from L2 and the dirty lines are overwritten in place by the next
-// chunk instead of being written back, which removes most of the path's HBM traffic.  Chunks are
-// sized in whole waves of GEMM tiles (sm_count x 128 rows) so no tile rounds are lost.
 static void self_attn_block(mldb_handle* h, const LinW& in_proj, const LinW& out_proj, const LnW& n,
                             ActBuf xin, ActBuf xout, StackWs& ws, const SeqInfo& si, int heads,
                             cudaStream_t st) {
   const int d = ws.d;
-  int cseq = ws.nseq;
-  if (h->pair_chunk && h->use_tc) cseq = std::max(1, (h->sm_count * 128 - 127) / ws.L);   // <= one wave of m-tiles
-  for (int s0 = 0; s0 < ws.nseq; s0 += cseq) {
-    const int ns = std::min(cseq, ws.nseq - s0);
-    const int64_t r0 = (int64_t)s0 * ws.L;
-    const int rows = ns * ws.L;
-    ActBuf qkv = rows_of(ws.qkv, 0, rows);                 // the same rows for every chunk
-    GemmArgs g; g.a1 = rows_of(xin, r0, rows); g.K1 = d; g.M = rows; g.w = in_proj; g.out = qkv;
-    op_gemm(h, g, st);
-    AttnArgs a; a.q = qkv; a.q_col0 = 0; a.Lq = ws.L; a.kv = qkv; a.k_col0 = d; a.v_col0 = 2 * d;
-    a.Lk = ws.L; a.nseq = ns; a.heads = heads; a.hd = d / heads;
-    a.lengths = si.lengths ? si.lengths + (si.len_mod > 0 ? 0 : s0) : nullptr;
-    a.kv_prefix = si.kv_prefix; a.len_mod = si.len_mod; a.seq0 = s0; a.out = rows_of(ws.att, r0, rows);
-    op_attn(h, a, st);
-  }
+  GemmArgs g; g.a1 = xin; g.K1 = d; g.M = ws.M; g.w = in_proj; g.out = ws.qkv;
+  op_gemm(h, g, st);
+  AttnArgs a; a.q = ws.qkv; a.q_col0 = 0; a.Lq = ws.L; a.kv = ws.qkv; a.k_col0 = d; a.v_col0 = 2 * d;
+  a.Lk = ws.L; a.nseq = ws.nseq; a.heads = heads; a.hd = d / heads;
+  a.lengths = si.lengths; a.kv_prefix = si.kv_prefix; a.len_mod = si.len_mod; a.seq0 = 0; a.out = ws.att;
+  op_attn(h, a, st);
   GemmArgs g2; g2.a1 = ws.att; g2.K1 = d; g2.M = ws.M; g2.w = out_proj;
   LnArgs l; l.res = xin; l.gamma = n.g; l.beta = n.b; l.M = ws.M; l.d = d; l.out = xout;
   op_gemm_ln(h, g2, l, ws.cf32, st);
 }
 static void ffn_block(mldb_handle* h, const LinW& l1, const LinW& l2, const LnW& n, ActBuf xin,
                       ActBuf xout, StackWs& ws, int act, cudaStream_t st) {
-  int crow = ws.M;
-  if (h->pair_chunk && h->use_tc && ws.d == 256) crow = h->sm_count * 128;   // one wave of FFN2 tiles
-  // Pair launch on whole waves of m-tiles only (every CTA runs the same number of FFN1->FFN2 chains);
-  // the ragged remainder goes through the two plain launches so that it spreads over all SMs.
-  const int wave_rows = h->sm_count * 128;
-  if (h->ffn_pair && h->use_tc && !h->pair_chunk && ws.M > wave_rows && ws.M % wave_rows != 0)
-    crow = (ws.M / wave_rows) * wave_rows;
-  for (int64_t r0 = 0; r0 < ws.M; r0 += crow) {
-    const int rows = (int)std::min<int64_t>(crow, ws.M - r0);
-    ActBuf hb = rows_of(ws.h, 0, rows);                    // the same rows for every chunk
-    GemmArgs g; g.a1 = rows_of(xin, r0, rows); g.K1 = ws.d; g.M = rows; g.w = l1; g.act = act; g.out = hb;
-    GemmArgs g2; g2.a1 = hb; g2.K1 = ws.ff; g2.M = rows; g2.w = l2;
-    LnArgs l; l.res = rows_of(xin, r0, rows); l.gamma = n.g; l.beta = n.b; l.M = rows; l.d = ws.d;
-    l.out = rows_of(xout, r0, rows);
-    if (h->use_tc && tc_ffn_supported(h->tc, g, g2, l)) {
-      // one launch: the hidden activations stay in shared memory / TMEM (gemm_tc.cu k_ffn_tc)
-      tc_ffn(h->tc, g, g2, l, st);
-      count_launch(h);
-      continue;
-    }
-    if (h->use_tc && h->ffn_pair && (rows % wave_rows == 0 || ws.M <= wave_rows) &&
-        rows <= 128 * MLDB_PAIR_MAX_TILES && tc_gemm_pair_supported(h->tc, g, g2, l)) {
-      // FFN1 and FFN2 as one persistent launch: the hidden activations are consumed from L2
-      tc_gemm_pair(h->tc, g, g2, l, h->pair_cnt, st);
-      count_launch(h);
-      continue;
-    }
-    op_gemm(h, g, st);
-    op_gemm_ln(h, g2, l, ws.cf32, st);
-  }
+  GemmArgs g; g.a1 = xin; g.K1 = ws.d; g.M = ws.M; g.w = l1; g.act = act; g.out = ws.h;
+  GemmArgs g2; g2.a1 = ws.h; g2.K1 = ws.ff; g2.M = ws.M; g2.w = l2;
+  LnArgs l; l.res = xin; l.gamma = n.g; l.beta = n.b; l.M = ws.M; l.d = ws.d; l.out = xout;
+  op_ffn(h, g, g2, l, ws.cf32, st);
 }
 // TransformerEncoderLayer.forward_post (cross_attention.py:259-272)
 static void enc_layer(mldb_handle* h, const StackW& sw, const EncW& w, ActBuf xin, ActBuf xout,
@@ -558,7 +556,7 @@ static ActBuf enc_layer_selected(mldb_handle* h, const StackW& sw, const EncW& w
   GemmArgs gk; gk.a1 = xin; gk.K1 = d; gk.M = ws.M; gk.w = w.kv_only; gk.out = ws.qkv;   // K | V in cols [0, 2d)
   op_gemm(h, gk, st);
   launch_pdl(k_gather_rows, dim3(nblk((int64_t)R * (d / 8))), dim3(256), 0, st, xin, ws.sx, ws.L, ws.n_sel, R, d);
-  count_launch(h);
+  kcount(h, MLDB_KSTAT_MISC);
   GemmArgs gq; gq.a1 = ws.sx; gq.K1 = d; gq.M = R; gq.w = w.q_only; gq.out = ws.sq;
   op_gemm(h, gq, st);
   AttnArgs a; a.q = ws.sq; a.q_col0 = 0; a.Lq = ws.n_sel; a.kv = ws.qkv; a.k_col0 = 0; a.v_col0 = d;
@@ -571,13 +569,7 @@ static ActBuf enc_layer_selected(mldb_handle* h, const StackW& sw, const EncW& w
   GemmArgs g1; g1.a1 = ws.sx1; g1.K1 = d; g1.M = R; g1.w = w.l1; g1.act = ACT_GELU; g1.out = ws.sh;
   GemmArgs g2; g2.a1 = ws.sh; g2.K1 = ws.ff; g2.M = R; g2.w = w.l2;
   LnArgs l2; l2.res = ws.sx1; l2.gamma = w.n2.g; l2.beta = w.n2.b; l2.M = R; l2.d = d; l2.out = ws.sout;
-  if (h->use_tc && tc_ffn_supported(h->tc, g1, g2, l2)) {
-    tc_ffn(h->tc, g1, g2, l2, st);
-    count_launch(h);
-    return ws.sout;
-  }
-  op_gemm(h, g1, st);
-  op_gemm_ln(h, g2, l2, ws.cf32, st);
+  op_ffn(h, g1, g2, l2, ws.cf32, st);
   return ws.sout;
 }
 
@@ -630,7 +622,7 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) FAIL(MLDB_ERR_UNSUPPORTED, "device %d is sm_%d%d; libmldb200 is sm_100a only", device, prop.major, prop.minor);
-  CK(cudaSetDevice(device));
+  DeviceGuard guard(device);
   mldb_handle* h = new mldb_handle();
   h->cfg = *cfg; h->device = device; h->sm_count = prop.multiProcessorCount;
   build_spec(h);
@@ -641,24 +633,13 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   mma_attention_init();
   h->tc = tc_create(device);
   if (!h->tc) { delete h; return MLDB_ERR_CUDA; }
-  if (dev_alloc(h, (void**)&h->pair_cnt, MLDB_PAIR_MAX_TILES * sizeof(int)) != MLDB_OK ||
-      cudaMemset(h->pair_cnt, 0, MLDB_PAIR_MAX_TILES * sizeof(int)) != cudaSuccess) { delete h; return MLDB_ERR_CUDA; }
+  if (!tc_attention_init(device)) { tc_destroy(h->tc); delete h; FAIL(MLDB_ERR_CUDA, "tcgen05 attention kernel: setup failed"); }
   const char* env = getenv("MLDB_GEMM");
   if (env && !strcmp(env, "simt")) h->use_tc = false;
-  env = getenv("MLDB_FFN_PAIR");
-  if (env) h->ffn_pair = atoi(env) != 0;
-  env = getenv("MLDB_PAIR_CHUNK");
-  if (env) h->pair_chunk = atoi(env) != 0;
-  env = getenv("MLDB_CHUNK");
-  if (env) h->chunk_seqs = atoi(env);
   env = getenv("MLDB_GRAPH");
   if (env && !strcmp(env, "0")) h->use_graph = false;
-  env = getenv("MLDB_ATTN_TC");
-  if (env) h->attn_tc = atoi(env) != 0;
-  env = getenv("MLDB_BRANCH_ROUND");
-  if (env) h->branch_round = atoi(env) != 0;
-  env = getenv("MLDB_LANES");
-  if (env) h->lanes = atoi(env) != 0;
+  env = getenv("MLDB_ATTN");
+  if (env) h->attn_kind = !strcmp(env, "mma") ? 1 : (!strcmp(env, "simt") ? 2 : 0);
   env = getenv("MLDB_BRANCHES");
   if (env) h->branches = std::min(std::max(atoi(env), 1), (int)mldb_handle::MAX_BRANCHES);
   e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
@@ -673,7 +654,7 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
 
 extern "C" void mldb_destroy(mldb_handle* h) {
   if (!h) return;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   cudaDeviceSynchronize();
   for (auto& kv : h->plans) {
     if (kv.second->exec) cudaGraphExecDestroy(kv.second->exec);
@@ -686,6 +667,7 @@ extern "C" void mldb_destroy(mldb_handle* h) {
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  mldb_comm_release(h);
   tc_destroy(h->tc);
   delete h;
 }
@@ -698,18 +680,11 @@ extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* val
     else FAIL(MLDB_ERR_INVALID, "gemm must be tc|simt");
   } else if (!strcmp(name, "ffn_fused")) {
     tc_set_ffn_fused(h->tc, atoi(value) != 0);
-  } else if (!strcmp(name, "ffn_pair")) {
-    h->ffn_pair = atoi(value) != 0;
-  } else if (!strcmp(name, "pair_chunk")) {
-    h->pair_chunk = atoi(value) != 0;
-  } else if (!strcmp(name, "chunk")) {
-    h->chunk_seqs = atoi(value);
-  } else if (!strcmp(name, "attn_tc")) {
-    h->attn_tc = atoi(value) != 0;
-  } else if (!strcmp(name, "branch_round")) {
-    h->branch_round = atoi(value) != 0;
-  } else if (!strcmp(name, "lanes")) {
-    h->lanes = atoi(value) != 0;
+  } else if (!strcmp(name, "attn")) {
+    if (!strcmp(value, "tc")) h->attn_kind = 0;
+    else if (!strcmp(value, "mma")) h->attn_kind = 1;
+    else if (!strcmp(value, "simt")) h->attn_kind = 2;
+    else FAIL(MLDB_ERR_INVALID, "attn must be tc|mma|simt");
   } else if (!strcmp(name, "branches")) {
     h->branches = std::min(std::max(atoi(value), 1), (int)mldb_handle::MAX_BRANCHES);
   } else if (!strcmp(name, "graph")) {
@@ -746,7 +721,7 @@ extern "C" int mldb_load_tensor(mldb_handle* h, const char* key, const void* dat
     n *= (size_t)shape[i];
   }
   t.host.resize(n);
-  CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   CK(cudaMemcpy(t.host.data(), data, n * sizeof(float), cudaMemcpyDefault));
   t.loaded = true;
   return MLDB_OK;
@@ -758,7 +733,7 @@ extern "C" int mldb_finalize_weights(mldb_handle* h, void* stream) {
   if (h->finalized) FAIL(MLDB_ERR_STATE, "already finalized");
   for (auto& kv : h->raw)
     if (!kv.second.loaded) FAIL(MLDB_ERR_STATE, "missing state-dict key '%s' (strict load)", kv.first.c_str());
-  CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const mldb_config& c = h->cfg;
   const int d = c.latent_dim;
   const std::string D = "denoiser.", V = "vae.";
@@ -773,7 +748,7 @@ extern "C" int mldb_finalize_weights(mldb_handle* h, void* stream) {
   TRY(upload_pe(h, D + "query_pos.pe", &h->query_pe));
   TRY(upload_pe(h, D + "mem_pos.pe", &h->mem_pe));
   if (c.diffusion_only) {
-    TRY(pack_named(h, D + "pose_embd.weight", D + "pose_embd.bias", &h->pose_embd));
+    TRY(pack_named(h, D + "pose_embd.weight", D + "pose_embd.bias", &h->pose_embd, 0, -1, true));
     TRY(pack_named(h, D + "pose_proj.weight", D + "pose_proj.bias", &h->pose_proj));
   }
   if (c.arch == MLDB_ARCH_TRANS_ENC) {
@@ -794,7 +769,7 @@ extern "C" int mldb_finalize_weights(mldb_handle* h, void* stream) {
     TRY(upload_pe(h, V + "query_pos_decoder.pe", &h->vae_dec_pe, &h->vae_dec_pe_rows));
     TRY(upload_pe(h, V + "query_pos_encoder.pe", &h->vae_enc_pe));
     TRY(upload_f32(h, rt(h, V + "global_motion_token").host.data(), (size_t)2 * c.n_lat * d, &h->global_token));
-    TRY(pack_named(h, V + "skel_embedding.weight", V + "skel_embedding.bias", &h->skel_emb));
+    TRY(pack_named(h, V + "skel_embedding.weight", V + "skel_embedding.bias", &h->skel_emb, 0, -1, true));
     TRY(pack_named(h, V + "final_layer.weight", V + "final_layer.bias", &h->final_layer));
   } else if (c.vae_kind == MLDB_VAE_ACTOR) {
     h->vdec.kind = STACK_PLAIN_DEC; h->vdec.d = d; h->vdec.ff = c.vae_ff; h->vdec.heads = c.vae_heads;
@@ -813,7 +788,7 @@ extern "C" int mldb_finalize_weights(mldb_handle* h, void* stream) {
 
 extern "C" int mldb_set_mean_std(mldb_handle* h, const float* mean, const float* stdv, int32_t nfeats) {
   if (!h || !mean || !stdv || nfeats <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
-  CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   if (!h->mean || h->nstat != nfeats) {
     TRY(dev_alloc(h, (void**)&h->mean, nfeats * sizeof(float)));
     TRY(dev_alloc(h, (void**)&h->stdv, nfeats * sizeof(float)));
@@ -834,15 +809,15 @@ static int time_tokens(mldb_handle* h, const int64_t* d_ts, int64_t t_scalar, in
   const int tdim = c.cond_kind == MLDB_COND_TEXT ? c.text_dim : d;
   const int half = tdim / 2;
   k_timestep_features<<<(n * half + 255) / 256, 256, 0, st>>>(d_ts, t_scalar, n, tdim, c.flip_sin_to_cos, c.freq_shift, scratch_feats);
-  count_launch(h);
+  kcount(h, MLDB_KSTAT_MISC);
   GemmArgs g; g.a_kind = A_F32; g.a_f32 = scratch_feats; g.lda = tdim; g.M = n; g.w = h->time_l1;
   g.act = ACT_SILU; g.out_f32 = scratch_h; g.ldc = d;
-  simt_gemm(g, st); count_launch(h);
+  simt_gemm(g, st); kcount(h, MLDB_KSTAT_GEMM_SIMT);
   GemmArgs g2; g2.a_kind = A_F32; g2.a_f32 = scratch_h; g2.lda = d; g2.M = n; g2.w = h->time_l2;
   g2.out_f32 = out; g2.ldc = d; g2.in_group = 1; g2.out_group = 1; g2.out_off = 0;
   // addtab row index is (out_off + r % in_group) = 0 -> pe_row
   g2.addtab = pe_row;
-  simt_gemm(g2, st); count_launch(h);
+  simt_gemm(g2, st); kcount(h, MLDB_KSTAT_GEMM_SIMT);
   return MLDB_OK;
 }
 
@@ -850,17 +825,31 @@ extern "C" int mldb_scheduler_set_timesteps(mldb_handle* h, int32_t n, int64_t* 
   if (!h) FAIL(MLDB_ERR_INVALID, "null handle");
   if (!h->finalized) FAIL(MLDB_ERR_STATE, "finalize weights first");
   if (n <= 0 || n > h->cfg.num_train_timesteps) FAIL(MLDB_ERR_INVALID, "bad number of inference steps %d", n);
-  CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   const mldb_config& c = h->cfg;
-  h->timesteps.resize(n);
-  TRY(mldb_scheduler_timesteps(&c, n, h->timesteps.data()));
+  if ((int)h->timesteps.size() == n) {          // the reference calls set_timesteps before every reverse loop
+    if (timesteps_out) memcpy(timesteps_out, h->timesteps.data(), n * sizeof(int64_t));
+    return MLDB_OK;
+  }
+  std::vector<int64_t> ts(n);
+  TRY(mldb_scheduler_timesteps(&c, n, ts.data()));
+  for (int i = 0; i < n; ++i)
+    if (ts[i] < 0 || ts[i] >= c.num_train_timesteps)
+      FAIL(MLDB_ERR_INVALID, "timestep %lld is outside the %d training timesteps (steps_offset with n == num_train_timesteps)",
+           (long long)ts[i], c.num_train_timesteps);
+  h->timesteps = ts;
   h->coefs_host.resize(n);
   for (int i = 0; i < n; ++i) h->coefs_host[i] = make_coef(h, h->timesteps[i], n);
   const int d = c.latent_dim;
   const int tdim = c.cond_kind == MLDB_COND_TEXT ? c.text_dim : d;
-  TRY(dev_alloc(h, (void**)&h->d_timesteps, n * sizeof(int64_t)));
-  TRY(dev_alloc(h, (void**)&h->d_coefs, n * sizeof(StepCoef)));
-  TRY(dev_alloc(h, (void**)&h->d_tt, (size_t)n * d * sizeof(float)));
+  const int cap = c.num_train_timesteps;        // n <= cap: the tables are allocated once
+  if (!h->d_timesteps) {
+    TRY(dev_alloc(h, (void**)&h->d_timesteps, cap * sizeof(int64_t)));
+    TRY(dev_alloc(h, (void**)&h->d_coefs, cap * sizeof(StepCoef)));
+    TRY(dev_alloc(h, (void**)&h->d_tt, (size_t)cap * d * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&h->d_tfeats, (size_t)cap * tdim * sizeof(float)));
+    TRY(dev_alloc(h, (void**)&h->d_thid, (size_t)cap * d * sizeof(float)));
+  }
   CK(cudaMemcpy(h->d_timesteps, h->timesteps.data(), n * sizeof(int64_t), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(h->d_coefs, h->coefs_host.data(), n * sizeof(StepCoef), cudaMemcpyHostToDevice));
   if (c.num_layers == 0) {   // scheduler-only use (no denoiser loaded)
@@ -868,9 +857,7 @@ extern "C" int mldb_scheduler_set_timesteps(mldb_handle* h, int32_t n, int64_t* 
     if (timesteps_out) memcpy(timesteps_out, h->timesteps.data(), n * sizeof(int64_t));
     return MLDB_OK;
   }
-  float *feats = nullptr, *hid = nullptr;
-  TRY(dev_alloc(h, (void**)&feats, (size_t)n * tdim * sizeof(float)));
-  TRY(dev_alloc(h, (void**)&hid, (size_t)n * d * sizeof(float)));
+  float *feats = h->d_tfeats, *hid = h->d_thid;
   // the time token sits at row n_lat of the encoder sequence (mld_denoiser.py:171,187) or at
   // row 0 of the decoder memory (mld_denoiser.py:215)
   const float* pe_row = c.arch == MLDB_ARCH_TRANS_ENC ? h->query_pe + (size_t)c.n_lat * d : h->mem_pe;
@@ -887,11 +874,11 @@ extern "C" int mldb_scheduler_step(mldb_handle* h, const float* model_output, in
   if (!h || !model_output || !sample || !prev_sample) FAIL(MLDB_ERR_INVALID, "null argument");
   if (h->timesteps.empty()) FAIL(MLDB_ERR_STATE, "call mldb_scheduler_set_timesteps first");
   if (timestep < 0 || timestep >= h->cfg.num_train_timesteps) FAIL(MLDB_ERR_INVALID, "timestep out of range");
-  CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   StepCoef k = make_coef(h, timestep, (int)h->timesteps.size());
   if (k.kind == 1 && k.sigma != 0.0f && !noise) FAIL(MLDB_ERR_INVALID, "DDPM step at t > 0 needs the injected noise tensor");
   k_sched_step<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(model_output, sample, noise, prev_sample, count, k);
-  count_launch(h);
+  kcount(h, MLDB_KSTAT_MISC);
   CK(cudaGetLastError());
   return MLDB_OK;
 }
@@ -912,10 +899,18 @@ static Plan* add_plan(mldb_handle* h, int kind, int B, int S, int T) {
   return p;
 }
 
+// an operator could not be enqueued (its tensor maps could not be encoded): the output is unwritten,
+// so the call must not report success (mldb_last_error() holds the encoder's message)
+static int check_ops(mldb_handle* h) {
+  if (!h->op_failed) return MLDB_OK;
+  h->op_failed = false;
+  return MLDB_ERR_CUDA;
+}
+
 // Run `record` either directly on `st` or as a (cached) CUDA graph.
 template <typename F>
 static int run_graphed(mldb_handle* h, Plan* p, cudaStream_t st, F record) {
-  if (!h->use_graph) { record(st); CK(cudaGetLastError()); return MLDB_OK; }
+  if (!h->use_graph) { record(st); CK(cudaGetLastError()); return check_ops(h); }
   if (!p->exec || p->sched_epoch != h->sched_epoch) {
     if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
     cudaGraph_t graph = nullptr;
@@ -927,6 +922,7 @@ static int run_graphed(mldb_handle* h, Plan* p, cudaStream_t st, F record) {
     }
     h->capturing = false;
     if (e != cudaSuccess) FAIL(MLDB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    if (h->op_failed) { cudaGraphDestroy(graph); return check_ops(h); }
     e = cudaGraphInstantiate(&p->exec, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) FAIL(MLDB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
@@ -985,72 +981,47 @@ static int enc_plan(mldb_handle* h, int kind, int B, int Bx, int S, Plan** out) 
 
 // condition tokens -> X0 (once per batch; step invariant, hoisted out of the loop although the
 // reference recomputes emb_proj every step, mld_denoiser.py:165)
-// Independent lanes: with `lanes` > 1 the motions are split into contiguous groups, and lane k keeps ALL
-// its sequences - the unconditional and the conditional copy of its motions - in one contiguous block
-// of workspace rows ([uncond b0..b1 | cond b0..b1]), so that the whole 50-step loop of a lane
-// (token assembly, stack, guidance + scheduler step) is one dependency chain with no per-step join.
-// Sequence g of the caller's [uncond B | cond B] order sits in slot lane_slot(g).
-static int reverse_lanes(const mldb_handle* h, const Plan* p, int B) {
-  const mldb_config& c = h->cfg;
-  const bool tc_ctx = c.cond_kind == MLDB_COND_TEXT && c.text_dim != c.latent_dim && h->use_tc && p->ctx_split.hi &&
-                      c.text_dim % 64 == 0;
-  // Off by default: measured 2.3 % SLOWER than the per-step fork/join of denoiser_pass (1826 vs 1869
-  // motions/s) - free-running lanes drift into the same phase and their identical heavy kernels contend,
-  // while the per-step join keeps the two ranges one kernel apart.  Option `lanes` / MLDB_LANES=1 enables it.
-  if (!h->lanes || !tc_ctx || h->branches <= 1 || h->chunk_seqs > 0) return 1;
-  if (B < 2 * h->branches || (int64_t)p->Bx * p->Ntok < 2 * 128 * h->branches) return 1;
-  return h->branches;
+// fp32 rows -> split16 rows (+ table row, ReLU) with the (seq, pos) mapping of k_rows_to_split; the
+// 128-bit path whenever the shapes allow it
+static void rows_to_split(mldb_handle* h, ActBuf X, const float* src, int ld_src, int M, int d, int in_group,
+                          int out_group, int out_off, int src_bcast, const float* tab, int relu, cudaStream_t st) {
+  const bool vec = d % 8 == 0 && X.cols % 8 == 0 && (!src || (ld_src % 4 == 0 && ((uintptr_t)src & 15) == 0)) &&
+                   (!tab || ((uintptr_t)tab & 15) == 0) && ((uintptr_t)X.hi & 15) == 0 && X.plane_stride % 8 == 0;
+  if (vec)
+    k_rows_to_split8<<<nblk((int64_t)M * (d / 8)), 256, 0, st>>>(X, src, ld_src, M, d, in_group, out_group, out_off,
+                                                                 src_bcast, tab, relu);
+  else
+    k_rows_to_split<<<nblk((int64_t)M * d), 256, 0, st>>>(X, src, ld_src, M, d, in_group, out_group, out_off, src_bcast,
+                                                          tab, relu);
+  kcount(h, MLDB_KSTAT_MISC);
 }
 
-static int place_condition(mldb_handle* h, Plan* p, const void* cond, cudaStream_t st, int lanes = 1) {
+static int place_condition(mldb_handle* h, Plan* p, const void* cond, cudaStream_t st) {
   const mldb_config& c = h->cfg;
   const int d = c.latent_dim, Bx = p->Bx;
   if (c.cond_kind == MLDB_COND_TEXT) {
     const int S = p->S;
-    if (lanes > 1) {
-      // ReLU + split once over the whole context, then one emb_proj GEMM per (lane, half) block
-      const int B = p->B, X = Bx / B;
-      k_rows_to_split<<<nblk((int64_t)Bx * S * c.text_dim), 256, 0, st>>>(p->ctx_split, (const float*)cond, c.text_dim,
-                                                                       Bx * S, c.text_dim, 1 << 30, 0, 0, 0, nullptr, 1);
-      count_launch(h);
-      for (int k = 0; k < lanes; ++k) {
-        const int b0 = (int)((int64_t)B * k / lanes), nb = (int)((int64_t)B * (k + 1) / lanes) - b0;
-        for (int hh = 0; hh < X; ++hh) {
-          const int64_t g0 = (int64_t)hh * B + b0, slot0 = (int64_t)X * b0 + (int64_t)hh * nb;
-          GemmArgs g; g.M = nb * S; g.w = h->emb_proj; g.a1 = rows_of(p->ctx_split, g0 * S, nb * S); g.K1 = c.text_dim;
-          g.out = rows_of(p->ws.x0, slot0 * p->Ntok, nb * p->Ntok);
-          g.in_group = S; g.out_group = p->Ntok; g.out_off = c.n_lat + 1; g.addtab = h->query_pe;
-          op_gemm(h, g, st);
-        }
-      }
-      CK(cudaGetLastError());
-      return MLDB_OK;
-    }
     if (c.text_dim != d) {
       // emb_proj = ReLU -> Linear (mld_denoiser.py:67-68): ReLU + hi/lo split in one pass over the
       // CLIP context, then the tensor-core GEMM writes the tokens (+ PE) straight into X0
       GemmArgs g; g.M = Bx * S; g.w = h->emb_proj; g.out = p->ws.x0;
       g.in_group = S; g.out_group = p->Ntok; g.out_off = c.n_lat + 1; g.addtab = h->query_pe;
       if (h->use_tc && p->ctx_split.hi && c.text_dim % 64 == 0) {
-        k_rows_to_split<<<nblk((int64_t)Bx * S * c.text_dim), 256, 0, st>>>(p->ctx_split, (const float*)cond, c.text_dim,
-                                                                         Bx * S, c.text_dim, 1 << 30, 0, 0, 0, nullptr, 1);
-        count_launch(h);
+        rows_to_split(h, p->ctx_split, (const float*)cond, c.text_dim, Bx * S, c.text_dim, 1 << 30, 0, 0, 0, nullptr, 1, st);
         g.a1 = p->ctx_split; g.K1 = c.text_dim;
       } else {
         g.a_kind = A_F32_RELU; g.a_f32 = (const float*)cond; g.lda = c.text_dim;
       }
       op_gemm(h, g, st);
     } else {
-      k_rows_to_split<<<nblk((int64_t)Bx * S * d), 256, 0, st>>>(p->ws.x0, (const float*)cond, d, Bx * S, d, S,
-                                                                p->Ntok, c.n_lat + 1, 0, h->query_pe);
-      count_launch(h);
+      rows_to_split(h, p->ws.x0, (const float*)cond, d, Bx * S, d, S, p->Ntok, c.n_lat + 1, 0, h->query_pe, 0, st);
     }
   } else {
     const int cfg_on = c.guidance_scale > 1.0f;
     k_action_tokens<<<nblk((int64_t)Bx * d), 256, 0, st>>>(p->ws.x0, p->Ntok, Bx, c.n_lat + 1, d, (const int64_t*)cond,
                                                           h->action_emb, c.nclasses, cfg_on,
                                                           h->query_pe + (size_t)(c.n_lat + 1) * d);
-    count_launch(h);
+    kcount(h, MLDB_KSTAT_MISC);
   }
   CK(cudaGetLastError());
   return MLDB_OK;
@@ -1076,48 +1047,24 @@ static void denoiser_pass(mldb_handle* h, Plan* p, const float* latents, int lat
   const int d = c.latent_dim;
   launch_pdl(k_assemble_tokens, dim3(nblk((int64_t)p->Bx * (c.n_lat + 1) * d)), dim3(256), 0, st,
              p->ws.x0, p->Ntok, p->Bx, lat_mod, c.n_lat, d, latents, (const float*)h->query_pe, tt);
-  count_launch(h);
-  // Sequences are independent, so the stack runs over chunks of `chunk_seqs` sequences that reuse
-  // the SAME workspace rows: a chunk's activations (qkv, FFN hidden, ...) then stay resident in the
-  // 126 MB L2 from the kernel that writes them to the kernel that reads them instead of streaming
-  // through HBM (~870 MB per layer for the whole 40 448-token batch).
-  const int cs = (h->chunk_seqs > 0 && h->chunk_seqs < p->Bx) ? h->chunk_seqs : p->Bx;
-  auto run_range = [&](const StackWs& wsv, int s0, int n, cudaStream_t s) {
-    denoiser_range(h, p, wsv, n, eps_out + (size_t)s0 * c.n_lat * d, s);
-  };
-  int nbr = (cs == p->Bx && h->branches > 1 && p->Bx * p->Ntok >= 2 * 128 * h->branches) ? h->branches : 1;
-  int bounds[mldb_handle::MAX_BRANCHES + 1];
-  for (int k = 0; k <= nbr; ++k) bounds[k] = (int)((int64_t)p->Bx * k / nbr);
-  if (nbr > 1 && h->branch_round && h->use_tc) {
-    // whole-round ranges: as many sequences as fill every SM with exactly one 128-row tile (no partial
-    // last round inside a range's persistent kernels), the remainder as one more, small range
-    const int per = (h->sm_count * 128) / p->Ntok;
-    const int chunks = per > 0 ? (p->Bx + per - 1) / per : 0;
-    if (chunks >= 2 && chunks <= mldb_handle::MAX_BRANCHES) {
-      nbr = chunks;
-      for (int k = 0; k <= nbr; ++k) bounds[k] = std::min(p->Bx, k * per);
-    }
-  }
-  if (nbr > 1) {
-    // fork: every range waits for the token assembly; join: the caller's stream waits for every range
-    cudaEventRecord(h->ev_fork, st);
-    for (int k = 0; k < nbr; ++k) {
-      cudaStream_t s = k == 0 ? st : h->br_stream[k - 1];
-      if (k) cudaStreamWaitEvent(s, h->ev_fork, 0);
-      const int s0 = bounds[k], s1 = bounds[k + 1];
-      run_range(ws_slice(p->ws, s0, s1 - s0), s0, s1 - s0, s);
-      if (k) cudaEventRecord(h->ev_join[k - 1], s);
-    }
-    for (int k = 1; k < nbr; ++k) cudaStreamWaitEvent(st, h->ev_join[k - 1], 0);
+  kcount(h, MLDB_KSTAT_MISC);
+  // Sequences are independent: the stack runs as `branches` contiguous sequence ranges with their own
+  // workspace rows on parallel streams (parallel chains inside the captured graph).
+  const int nbr = (h->branches > 1 && p->Bx * p->Ntok >= 2 * 128 * h->branches) ? h->branches : 1;
+  if (nbr == 1) {
+    denoiser_range(h, p, p->ws, p->Bx, eps_out, st);
     return;
   }
-  for (int s0 = 0; s0 < p->Bx; s0 += cs) {
-    const int n = std::min(cs, p->Bx - s0);
-    StackWs w = p->ws;                                   // every chunk reuses the first rows
-    w.nseq = n; w.M = n * p->Ntok;
-    w.x0 = rows_of(p->ws.x0, (int64_t)s0 * p->Ntok, w.M);
-    run_range(w, s0, n, st);
+  // fork: every range waits for the token assembly; join: the caller's stream waits for every range
+  cudaEventRecord(h->ev_fork, st);
+  for (int k = 0; k < nbr; ++k) {
+    cudaStream_t s = k == 0 ? st : h->br_stream[k - 1];
+    if (k) cudaStreamWaitEvent(s, h->ev_fork, 0);
+    const int s0 = (int)((int64_t)p->Bx * k / nbr), s1 = (int)((int64_t)p->Bx * (k + 1) / nbr);
+    denoiser_range(h, p, ws_slice(p->ws, s0, s1 - s0), s1 - s0, eps_out + (size_t)s0 * c.n_lat * d, s);
+    if (k) cudaEventRecord(h->ev_join[k - 1], s);
   }
+  for (int k = 1; k < nbr; ++k) cudaStreamWaitEvent(st, h->ev_join[k - 1], 0);
 }
 
 // ----------------------------------------------------------------------------- denoiser (trans_dec)
@@ -1142,6 +1089,8 @@ static int decden_plan(mldb_handle* h, int kind, int B, int Bx, int S, int T, Pl
     TRY(dev_alloc(h, (void**)&p->stage_f32, (size_t)Bx * per * sizeof(float)));
     TRY(dev_alloc(h, (void**)&p->lengths, (size_t)Bx * sizeof(int32_t)));
     TRY(dev_alloc(h, (void**)&p->tt_single, (size_t)3 * std::max(c.text_dim, c.latent_dim) * sizeof(float) + 64));
+    TRY(dev_alloc(h, (void**)&p->d_step, sizeof(int)));
+    if (h->pose_embd.K % 64 == 0 && h->pose_embd.K >= c.nfeats) TRY(alloc_act(h, Bx * T, h->pose_embd.K, &p->in_split));
   }
   *out = p;
   return MLDB_OK;
@@ -1158,30 +1107,45 @@ static int place_condition_dec(mldb_handle* h, Plan* p, const void* cond, cudaSt
       g.in_group = S; g.out_group = Lmem; g.out_off = 1; g.addtab = h->mem_pe;
       op_gemm(h, g, st);
     } else {
-      k_rows_to_split<<<nblk((int64_t)Bx * S * d), 256, 0, st>>>(p->mem, (const float*)cond, d, Bx * S, d, S, Lmem, 1, 0, h->mem_pe);
-      count_launch(h);
+      rows_to_split(h, p->mem, (const float*)cond, d, Bx * S, d, S, Lmem, 1, 0, h->mem_pe, 0, st);
     }
   } else {
     const int cfg_on = c.guidance_scale > 1.0f;
     k_action_tokens<<<nblk((int64_t)Bx * d), 256, 0, st>>>(p->mem, Lmem, Bx, 1, d, (const int64_t*)cond, h->action_emb,
                                                           c.nclasses, cfg_on, h->mem_pe + (size_t)d);
-    count_launch(h);
+    kcount(h, MLDB_KSTAT_MISC);
   }
   CK(cudaGetLastError());
   return MLDB_OK;
 }
 
-// model_in: [Bx, T, F] fp32 (device); lengths: device int32[Bx]; eps_out [Bx, T, F]
-static void denoiser_pass_dec(mldb_handle* h, Plan* p, const float* model_in, const float* tt, float* eps_out,
-                              cudaStream_t st) {
+// model_in: [rows_in, T, F] fp32 (device) fed `rep` times (rep * rows_in == Bx: torch.cat([latents] * 2),
+// mld.py:325); lengths: device int32[Bx]; eps_out [Bx, T, F].  tt: time token(s); step_ptr != null selects
+// row *step_ptr of tt (replayed step graph).
+static void denoiser_pass_dec(mldb_handle* h, Plan* p, const float* model_in, int rep, const float* tt,
+                              const int* step_ptr, float* eps_out, cudaStream_t st) {
   const mldb_config& c = h->cfg;
   const int d = c.latent_dim, Bx = p->Bx, T = p->T, F = c.nfeats, Lmem = p->ws.Lmem;
   // memory row 0 = time token (mem_pos.pe[0] already added)
-  k_rows_to_split<<<nblk((int64_t)Bx * d), 256, 0, st>>>(p->mem, tt, d, Bx, d, 1, Lmem, 0, 1, nullptr);
-  count_launch(h);
-  // pose_embd + query_pos (mld_denoiser.py:210,214)
-  GemmArgs g; g.a_kind = A_F32; g.a_f32 = model_in; g.lda = F; g.M = Bx * T; g.w = h->pose_embd;
+  k_rows_to_split<<<nblk((int64_t)Bx * d), 256, 0, st>>>(p->mem, tt, d, Bx, d, 1, Lmem, 0, 1, nullptr, 0, step_ptr, (int64_t)d);
+  kcount(h, MLDB_KSTAT_MISC);
+  // pose_embd + query_pos (mld_denoiser.py:210,214): the 263 features zero-padded to the packed K (320)
+  // so that the embedding runs on the tensor cores
+  GemmArgs g; g.M = Bx * T; g.w = h->pose_embd;
   g.out = p->ws.x0; g.in_group = T; g.out_group = T; g.out_off = 0; g.addtab = h->query_pe;
+  if (h->use_tc && p->in_split.hi) {
+    k_f32_to_split_pad<<<nblk((int64_t)(Bx / rep) * T * p->in_split.cols), 256, 0, st>>>(p->in_split, model_in, F, (Bx / rep) * T, F, rep);
+    kcount(h, MLDB_KSTAT_MISC);
+    g.a1 = p->in_split; g.K1 = p->in_split.cols;
+  } else {
+    if (rep > 1) {   // CUDA-core reference path: materialise the duplicated input
+      for (int k = 0; k < rep; ++k)
+        cudaMemcpyAsync(p->stage_f32 + (size_t)k * (Bx / rep) * T * F, model_in, (size_t)(Bx / rep) * T * F * sizeof(float),
+                        cudaMemcpyDeviceToDevice, st);
+      model_in = p->stage_f32;
+    }
+    g.a_kind = A_F32; g.a_f32 = model_in; g.lda = F;
+  }
   op_gemm(h, g, st);
   SeqInfo si;
   ActBuf x = run_stack(h, h->den, p->ws.x0, p->mem, p->ws, si, st);
@@ -1201,7 +1165,6 @@ static int check_ready(mldb_handle* h, bool need_sched) {
   if (!h) FAIL(MLDB_ERR_INVALID, "null handle");
   if (!h->finalized) FAIL(MLDB_ERR_STATE, "weights not finalized");
   if (need_sched && h->timesteps.empty()) FAIL(MLDB_ERR_STATE, "call mldb_scheduler_set_timesteps first");
-  CK(cudaSetDevice(h->device));
   return MLDB_OK;
 }
 
@@ -1210,6 +1173,7 @@ extern "C" int mldb_denoise(mldb_handle* h, const float* sample, int64_t timeste
                             void* stream) {
   (void)lengths; (void)T;
   TRY(check_ready(h, false));
+  DeviceGuard guard(h->device);
   if (!sample || !cond || !out || Bx <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
   const mldb_config& c = h->cfg;
   if (c.num_layers == 0) FAIL(MLDB_ERR_STATE, "this handle has no denoiser");
@@ -1228,7 +1192,7 @@ extern "C" int mldb_denoise(mldb_handle* h, const float* sample, int64_t timeste
     float* hid = feats + tdim;
     float* tt = hid + std::max(tdim, d);
     TRY(time_tokens(h, nullptr, timestep, 1, h->mem_pe, tt, feats, hid, st));
-    denoiser_pass_dec(h, p, sample, tt, out, st);
+    denoiser_pass_dec(h, p, sample, 1, tt, nullptr, out, st);
     CK(cudaGetLastError());
     return MLDB_OK;
   }
@@ -1263,24 +1227,32 @@ static int run_reverse(mldb_handle* h, const void* cond, const float* init_noise
     const int64_t per = (int64_t)T * c.nfeats;
     TRY(place_condition_dec(h, p, cond, st));
     k_dup_lengths<<<nblk(Bx), 256, 0, st>>>(lengths, p->lengths, B, Bx);
-    count_launch(h);
+    kcount(h, MLDB_KSTAT_MISC);
     CK(cudaMemcpyAsync(p->latents, init_noise, (size_t)B * per * sizeof(float), cudaMemcpyDeviceToDevice, st));
     const int nsteps = (int)h->timesteps.size();
+    bool needs_noise = false;
+    for (int i = 0; i < nsteps; ++i) needs_noise |= h->coefs_host[i].kind == 1 && h->coefs_host[i].sigma != 0.0f;
+    if (needs_noise && !step_noise) FAIL(MLDB_ERR_INVALID, "DDPM needs step_noise [n_steps, B, T, F]");
+    // ONE captured step, replayed n_steps times: the step index lives on the device (k_step_inc), the
+    // kernels that depend on it (time token, scheduler coefficients, noise slice) read it through p->d_step.
+    // The graph holds the caller's noise pointer: a different buffer re-captures.
+    if (p->noise_ptr != step_noise && p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
+    p->noise_ptr = step_noise;
+    k_step_set<<<1, 1, 0, st>>>(p->d_step, 0);
+    kcount(h, MLDB_KSTAT_MISC);
     for (int i = 0; i < nsteps; ++i) {
-      for (int rep = 0; rep < (cfg_on ? 2 : 1); ++rep)        // torch.cat([latents] * 2), mld.py:325
-        CK(cudaMemcpyAsync(p->stage_f32 + (size_t)rep * B * per, p->latents, (size_t)B * per * sizeof(float),
-                           cudaMemcpyDeviceToDevice, st));
-      denoiser_pass_dec(h, p, p->stage_f32, h->d_tt + (size_t)i * c.latent_dim, p->eps, st);
-      const float* nz = step_noise ? step_noise + (size_t)i * B * per : nullptr;
-      if (!nz && h->coefs_host[i].kind == 1 && h->coefs_host[i].sigma != 0.0f)
-        FAIL(MLDB_ERR_INVALID, "DDPM needs step_noise [n_steps, B, T, F]");
-      k_cfg_sched<<<nblk(B * per), 256, 0, st>>>(p->eps, p->latents, nz, B * per, cfg_on ? 1 : 0, c.guidance_scale,
-                                               h->d_coefs, i);
-      count_launch(h);
+      TRY(run_graphed(h, p, st, [&](cudaStream_t s) {
+        denoiser_pass_dec(h, p, p->latents, cfg_on ? 2 : 1, h->d_tt, p->d_step, p->eps, s);
+        k_cfg_sched<<<nblk(B * per), 256, 0, s>>>(p->eps, p->latents, needs_noise ? step_noise : nullptr, B * per,
+                                                cfg_on ? 1 : 0, c.guidance_scale, h->d_coefs, 0, p->d_step);
+        kcount(h, MLDB_KSTAT_MISC);
+        k_step_inc<<<1, 1, 0, s>>>(p->d_step);
+        kcount(h, MLDB_KSTAT_MISC);
+      }));
     }
     if (latents_out) {                                        // [T, B, F] (mld.py:359)
       k_permute_01<<<nblk(B * per), 256, 0, st>>>(p->latents, latents_out, B, T, c.nfeats);
-      count_launch(h);
+      kcount(h, MLDB_KSTAT_MISC);
     }
     CK(cudaGetLastError());
     if (plan_out) *plan_out = p;
@@ -1290,52 +1262,36 @@ static int run_reverse(mldb_handle* h, const void* cond, const float* init_noise
   TRY(enc_plan(h, 0, B, Bx, S, &p));
   const int d = c.latent_dim;
   const int64_t per = (int64_t)c.n_lat * d;
-  const int lanes = reverse_lanes(h, p, B);
-  TRY(place_condition(h, p, cond, st, lanes));
+  TRY(place_condition(h, p, cond, st));
   // latents = init_noise * init_noise_sigma (== 1 for DDIM/DDPM), mld.py:310
   CK(cudaMemcpyAsync(p->latents, init_noise, (size_t)B * per * sizeof(float), cudaMemcpyDeviceToDevice, st));
   const int nsteps = (int)h->timesteps.size();
-  TRY(run_graphed(h, p, st, [&](cudaStream_t s) {
-    if (lanes > 1) {
-      // one dependency chain per lane for the whole loop (fork once, join once): a lane's kernel tails,
-      // its small kernels (token assembly, final norm, guidance + scheduler step) and its kernel
-      // boundaries are filled by the other lanes' GEMMs, and the lanes drift out of lockstep
-      const int X = Bx / B;
-      cudaEventRecord(h->ev_fork, s);
-      for (int k = 0; k < lanes; ++k) {
-        cudaStream_t sk = k == 0 ? s : h->br_stream[k - 1];
-        if (k) cudaStreamWaitEvent(sk, h->ev_fork, 0);
-        const int b0 = (int)((int64_t)B * k / lanes), nb = (int)((int64_t)B * (k + 1) / lanes) - b0;
-        const StackWs wk = ws_slice(p->ws, X * b0, X * nb);
-        float* const eps_k = p->eps + (size_t)X * b0 * per;
-        float* const lat_k = p->latents + (size_t)b0 * per;
-        for (int i = 0; i < nsteps; ++i) {                                       // mld.py:323
-          launch_pdl(k_assemble_tokens, dim3(nblk((int64_t)X * nb * (c.n_lat + 1) * d)), dim3(256), 0, sk, wk.x0, p->Ntok,
-                     X * nb, nb, c.n_lat, d, (const float*)lat_k, (const float*)h->query_pe,
-                     (const float*)(h->d_tt + (size_t)i * d));
-          count_launch(h);
-          denoiser_range(h, p, wk, X * nb, eps_k, sk);
-          launch_pdl(k_cfg_sched, dim3(nblk((int64_t)nb * per)), dim3(256), 0, sk, (const float*)eps_k, lat_k,
-                     (const float*)nullptr, (int64_t)nb * per, cfg_on ? 1 : 0, c.guidance_scale,
-                     (const StepCoef*)h->d_coefs, i);
-          count_launch(h);
-        }
-        if (k) cudaEventRecord(h->ev_join[k - 1], sk);
-      }
-      for (int k = 1; k < lanes; ++k) cudaStreamWaitEvent(s, h->ev_join[k - 1], 0);
-      return;
+  // DDPM draws noise at every step with t > 0 (diffusers DDPMScheduler.step): the caller injects it
+  const float* nz_all = nullptr;
+  bool needs_noise = false;
+  for (int i = 0; i < nsteps; ++i) needs_noise |= h->coefs_host[i].kind == 1 && h->coefs_host[i].sigma != 0.0f;
+  if (needs_noise) {
+    if (!step_noise) FAIL(MLDB_ERR_INVALID, "the DDPM scheduler needs step_noise [n_steps, B, n_lat, d] (injected N(0,1) per step)");
+    if (p->noise_cap < (size_t)nsteps * B * per) {
+      TRY(dev_alloc(h, (void**)&p->step_noise, (size_t)nsteps * B * per * sizeof(float)));
+      p->noise_cap = (size_t)nsteps * B * per;
+      if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }   // the graph holds the old pointer
     }
+    CK(cudaMemcpyAsync(p->step_noise, step_noise, (size_t)nsteps * B * per * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    nz_all = p->step_noise;
+  }
+  TRY(run_graphed(h, p, st, [&](cudaStream_t s) {
     for (int i = 0; i < nsteps; ++i) {                                           // mld.py:323
       denoiser_pass(h, p, p->latents, B, h->d_tt + (size_t)i * d, p->eps, s);
       launch_pdl(k_cfg_sched, dim3(nblk(B * per)), dim3(256), 0, s, (const float*)p->eps, p->latents,
-                 (const float*)nullptr, (int64_t)(B * per), cfg_on ? 1 : 0, c.guidance_scale,
-                 (const StepCoef*)h->d_coefs, i);
-      count_launch(h);
+                 nz_all, (int64_t)(B * per), cfg_on ? 1 : 0, c.guidance_scale, (const StepCoef*)h->d_coefs, i,
+                 (const int*)nullptr);
+      kcount(h, MLDB_KSTAT_MISC);
     }
   }));
   if (latents_out) {                                                             // mld.py:359
     k_permute_01<<<nblk(B * per), 256, 0, st>>>(p->latents, latents_out, B, c.n_lat, d);
-    count_launch(h);
+    kcount(h, MLDB_KSTAT_MISC);
   }
   CK(cudaGetLastError());
   if (plan_out) *plan_out = p;
@@ -1346,9 +1302,8 @@ extern "C" int mldb_diffusion_reverse(mldb_handle* h, const void* cond, const fl
                                       const float* step_noise, const int32_t* lengths, int32_t B,
                                       int32_t S_ctx, int32_t T, float* latents_out, void* stream) {
   TRY(check_ready(h, true));
+  DeviceGuard guard(h->device);
   if (!cond || !init_noise || !latents_out || B <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
-  if (step_noise && h->cfg.arch != MLDB_ARCH_TRANS_DEC)
-    FAIL(MLDB_ERR_UNSUPPORTED, "per-step noise is only used by the no-VAE DDPM model");
   return run_reverse(h, cond, init_noise, step_noise, lengths, B, S_ctx, T, latents_out, (cudaStream_t)stream, nullptr);
 }
 
@@ -1397,10 +1352,10 @@ static int run_decode(mldb_handle* h, const float* z, const int32_t* lengths, in
   float* fout = feats_out ? feats_out : p->feats;
   TRY(run_graphed(h, p, st, [&](cudaStream_t s) {
     k_mem_tokens<<<nblk((int64_t)c.n_lat * B * d), 256, 0, s>>>(p->mem, p->latents, c.n_lat, B, d);
-    count_launch(h);
+    kcount(h, MLDB_KSTAT_MISC);
     // queries = zeros + PE rows (mld_vae.py:190,224; actor_vae.py:219-225)
     k_rows_to_split<<<nblk((int64_t)B * T * d), 256, 0, s>>>(p->ws.x0, nullptr, 0, B * T, d, T, T, 0, 0, h->vae_dec_pe);
-    count_launch(h);
+    kcount(h, MLDB_KSTAT_MISC);
     SeqInfo si; si.lengths = p->lengths; si.kv_prefix = 0;
     ActBuf x = run_stack(h, h->vdec, p->ws.x0, p->mem, p->ws, si, s);
     if (h->vdec.norm.g) {
@@ -1422,6 +1377,7 @@ static int run_decode(mldb_handle* h, const float* z, const int32_t* lengths, in
 extern "C" int mldb_vae_decode(mldb_handle* h, const float* z, const int32_t* lengths, int32_t B,
                                int32_t T, float* feats_out, void* stream) {
   TRY(check_ready(h, false));
+  DeviceGuard guard(h->device);
   if (!z || !lengths || !feats_out || B <= 0 || T <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
   return run_decode(h, z, lengths, B, T, feats_out, (cudaStream_t)stream, nullptr);
 }
@@ -1442,6 +1398,7 @@ __global__ void k_rows_out_permuted(const float* __restrict__ src, float* __rest
 extern "C" int mldb_vae_encode(mldb_handle* h, const float* feats, const int32_t* lengths, int32_t B,
                                int32_t T, float* mu, float* logvar, void* stream) {
   TRY(check_ready(h, false));
+  DeviceGuard guard(h->device);
   if (!feats || !lengths || !mu || !logvar || B <= 0 || T <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
   const mldb_config& c = h->cfg;
   if (c.vae_kind != MLDB_VAE_MLD) FAIL(MLDB_ERR_UNSUPPORTED, "encode is built for MldVae only");
@@ -1454,15 +1411,24 @@ extern "C" int mldb_vae_encode(mldb_handle* h, const float* feats, const int32_t
     TRY(alloc_stack_ws(h, h->venc, B, L, 0, &p->ws, h->venc.layers >= 3 ? G : 0));
     TRY(dev_alloc(h, (void**)&p->lengths, (size_t)B * sizeof(int32_t)));
     TRY(dev_alloc(h, (void**)&p->stage_f32, (size_t)B * G * d * sizeof(float)));
+    if (h->skel_emb.K % 64 == 0) TRY(alloc_act(h, B * T, h->skel_emb.K, &p->in_split));
   }
   CK(cudaMemcpyAsync(p->lengths, lengths, (size_t)B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-  // skel_embedding rows -> token rows (b, G + t) + PE (mld_vae.py:139-161)
-  GemmArgs g; g.a_kind = A_F32; g.a_f32 = feats; g.lda = c.vae_nfeats; g.M = B * T; g.w = h->skel_emb;
+  // skel_embedding rows -> token rows (b, G + t) + PE (mld_vae.py:139-161); the 263 features are
+  // zero-padded to the packed K so that the embedding runs on the tensor cores
+  GemmArgs g; g.M = B * T; g.w = h->skel_emb;
   g.out = p->ws.x0; g.in_group = T; g.out_group = L; g.out_off = G; g.addtab = h->vae_enc_pe;
+  if (h->use_tc && p->in_split.hi) {
+    k_f32_to_split_pad<<<nblk((int64_t)B * T * p->in_split.cols), 256, 0, st>>>(p->in_split, feats, c.vae_nfeats, B * T, c.vae_nfeats, 1);
+    kcount(h, MLDB_KSTAT_MISC);
+    g.a1 = p->in_split; g.K1 = p->in_split.cols;
+  } else {
+    g.a_kind = A_F32; g.a_f32 = feats; g.lda = c.vae_nfeats;
+  }
   op_gemm(h, g, st);
   // global motion tokens (b, 0..G-1) = token + PE (mld_vae.py:146,157)
   k_rows_to_split<<<nblk((int64_t)B * G * d), 256, 0, st>>>(p->ws.x0, h->global_token, d, B * G, d, G, L, 0, 1, h->vae_enc_pe);
-  count_launch(h);
+  kcount(h, MLDB_KSTAT_MISC);
   SeqInfo si; si.lengths = p->lengths; si.kv_prefix = G;
   ActBuf x = run_stack(h, h->venc, p->ws.x0, ActBuf{}, p->ws, si, st);
   LnArgs l; l.res = x; l.gamma = h->venc.norm.g; l.beta = h->venc.norm.b; l.M = B * G; l.d = d;
@@ -1470,7 +1436,7 @@ extern "C" int mldb_vae_encode(mldb_handle* h, const float* feats, const int32_t
   l.out_f32 = p->stage_f32; l.ld_out = d;
   op_ln(h, l, st);
   k_rows_out_permuted<<<nblk((int64_t)B * G * d), 256, 0, st>>>(p->stage_f32, mu, logvar, B, c.n_lat, d);
-  count_launch(h);
+  kcount(h, MLDB_KSTAT_MISC);
   CK(cudaGetLastError());
   return MLDB_OK;
 }
@@ -1482,13 +1448,14 @@ static int run_f2j(mldb_handle* h, const float* feats, int B, int T, float* join
   if (!h->mean || h->nstat != F) FAIL(MLDB_ERR_STATE, "call mldb_set_mean_std with %d features first", F);
   if (F < 4 + (c.njoints - 1) * 3) FAIL(MLDB_ERR_UNSUPPORTED, "feats2joints needs the HumanML3D/KIT layout");
   k_feats2joints<<<B, 256, (size_t)4 * T * sizeof(float), st>>>(feats, h->mean, h->stdv, T, F, c.njoints, joints);
-  count_launch(h);
+  kcount(h, MLDB_KSTAT_MISC);
   CK(cudaGetLastError());
   return MLDB_OK;
 }
 extern "C" int mldb_feats2joints(mldb_handle* h, const float* feats, int32_t B, int32_t T,
                                  float* joints_out, void* stream) {
   TRY(check_ready(h, false));
+  DeviceGuard guard(h->device);
   if (!feats || !joints_out || B <= 0 || T <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
   return run_f2j(h, feats, B, T, joints_out, (cudaStream_t)stream);
 }
@@ -1498,6 +1465,7 @@ extern "C" int mldb_sample(mldb_handle* h, const void* cond, const float* init_n
                            const int32_t* lengths, int32_t B, int32_t S_ctx, int32_t T,
                            float* latents_out, float* feats_out, float* joints_out, void* stream) {
   TRY(check_ready(h, true));
+  DeviceGuard guard(h->device);
   if (!cond || !init_noise || !lengths || B <= 0 || T <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   Plan *rp = nullptr, *dp = nullptr;
@@ -1516,10 +1484,34 @@ extern "C" int mldb_sample(mldb_handle* h, const void* cond, const float* init_n
   return MLDB_OK;
 }
 
+// Multi-GPU: this rank samples its shard and the finished joints of every rank are gathered into
+// joints_global [nranks * B, T, njoints, 3] (k_feats2joints writes straight into this rank's slot, ONE in-place
+// ncclAllGather on the handle's side stream).  The call returns after enqueue; the gather of this batch
+// overlaps whatever the caller enqueues next on `stream` - call mldb_gather_wait(h, stream) before reading
+// joints_global on `stream`, and alternate (at least) two joints_global buffers between consecutive calls.
+extern "C" int mldb_sample_gather(mldb_handle* h, const void* cond, const float* init_noise,
+                                  const int32_t* lengths, int32_t B, int32_t S_ctx, int32_t T,
+                                  float* joints_global, void* stream) {
+  TRY(check_ready(h, true));
+  DeviceGuard guard(h->device);
+  if (!joints_global) FAIL(MLDB_ERR_INVALID, "bad argument");
+  const int64_t count = (int64_t)B * T * h->cfg.njoints * 3;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!h->nccl_comm) {      // single rank: the gather is the identity
+    return mldb_sample(h, cond, init_noise, lengths, B, S_ctx, T, nullptr, nullptr, joints_global, stream);
+  }
+  TRY(mldb_gather_begin(h, st));
+  TRY(mldb_sample(h, cond, init_noise, lengths, B, S_ctx, T, nullptr, nullptr, joints_global + h->comm_rank * count, stream));
+  return mldb_gather_async(h, joints_global, count, st);
+}
+
+// Host-buffer entry point.  With a communicator attached joints_host receives the GATHERED motions
+// [nranks * B, T, njoints, 3] (every rank holds all of them after the all-gather), else [B, T, njoints, 3].
 extern "C" int mldb_sample_host(mldb_handle* h, const void* cond_host, const float* init_noise_host,
                                 const int32_t* lengths_host, int32_t B, int32_t S_ctx, int32_t T,
                                 float* joints_host, void* stream) {
   TRY(check_ready(h, true));
+  DeviceGuard guard(h->device);
   if (!cond_host || !init_noise_host || !lengths_host || !joints_host || B <= 0 || T <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const mldb_config& c = h->cfg;
@@ -1538,11 +1530,20 @@ extern "C" int mldb_sample_host(mldb_handle* h, const void* cond_host, const flo
     TRY(dev_alloc(h, (void**)&dp->noise_in, noise_bytes));
     TRY(dev_alloc(h, (void**)&dp->cond_i, (size_t)B * sizeof(int32_t)));
   }
+  const int world = h->nccl_comm ? h->comm_world : 1;
+  const size_t joints_elems = (size_t)B * T * c.njoints * 3;
+  if (world > 1 && !dp->joints_all) TRY(dev_alloc(h, (void**)&dp->joints_all, world * joints_elems * sizeof(float)));
   CK(cudaMemcpyAsync(dp->cond_f, cond_host, cond_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dp->noise_in, init_noise_host, noise_bytes, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dp->cond_i, lengths_host, (size_t)B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (world > 1) {
+    TRY(mldb_sample_gather(h, dp->cond_f, dp->noise_in, (const int32_t*)dp->cond_i, B, S_ctx, T, dp->joints_all, stream));
+    TRY(mldb_gather_wait(h, stream));
+    CK(cudaMemcpyAsync(joints_host, dp->joints_all, world * joints_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return MLDB_OK;
+  }
   TRY(mldb_sample(h, dp->cond_f, dp->noise_in, (const int32_t*)dp->cond_i, B, S_ctx, T, nullptr, nullptr, dp->joints, stream));
-  CK(cudaMemcpyAsync(joints_host, dp->joints, (size_t)B * T * c.njoints * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(joints_host, dp->joints, joints_elems * sizeof(float), cudaMemcpyDeviceToHost, st));
   return MLDB_OK;
 }
 
@@ -1553,6 +1554,7 @@ extern "C" int mldb_sample_host(mldb_handle* h, const void* cond_host, const flo
 extern "C" int mldb_profile_op(mldb_handle* h, const char* op, int32_t B, int32_t S_ctx, int32_t iters,
                                float* avg_ms_out) {
   TRY(check_ready(h, false));
+  DeviceGuard guard(h->device);
   if (!op || !avg_ms_out || iters <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
   const mldb_config& c = h->cfg;
   if (c.num_layers == 0 || c.arch != MLDB_ARCH_TRANS_ENC) FAIL(MLDB_ERR_UNSUPPORTED, "needs the trans_enc denoiser");
@@ -1604,6 +1606,42 @@ extern "C" int mldb_profile_op(mldb_handle* h, const char* op, int32_t B, int32_
   return MLDB_OK;
 }
 
+// Per-step device times of the reverse loop: the same kernels as the captured graph, launched eagerly on the
+// internal stream with a CUDA event between scheduler steps (bench.py's step p50).  cond / init_noise as for
+// mldb_diffusion_reverse; ms_out: HOST float[n_steps].  Synchronous.
+extern "C" int mldb_profile_steps(mldb_handle* h, const void* cond, const float* init_noise, int32_t B, int32_t S_ctx,
+                                  float* ms_out) {
+  TRY(check_ready(h, true));
+  DeviceGuard guard(h->device);
+  if (!cond || !init_noise || !ms_out || B <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  const mldb_config& c = h->cfg;
+  if (c.num_layers == 0 || c.arch != MLDB_ARCH_TRANS_ENC) FAIL(MLDB_ERR_UNSUPPORTED, "needs the trans_enc denoiser");
+  if (c.sched_kind != MLDB_SCHED_DDIM) FAIL(MLDB_ERR_UNSUPPORTED, "step profiling is built for the DDIM loop");
+  const bool cfg_on = c.guidance_scale > 1.0f;
+  Plan* p = nullptr;
+  TRY(enc_plan(h, 0, B, cfg_on ? 2 * B : B, S_ctx, &p));
+  cudaStream_t st = h->cap_stream;
+  const int d = c.latent_dim, nsteps = (int)h->timesteps.size();
+  const int64_t per = (int64_t)c.n_lat * d;
+  TRY(place_condition(h, p, cond, st));
+  CK(cudaMemcpyAsync(p->latents, init_noise, (size_t)B * per * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  std::vector<cudaEvent_t> ev(nsteps + 1);
+  for (auto& e : ev) CK(cudaEventCreate(&e));
+  CK(cudaEventRecord(ev[0], st));
+  for (int i = 0; i < nsteps; ++i) {
+    denoiser_pass(h, p, p->latents, B, h->d_tt + (size_t)i * d, p->eps, st);
+    launch_pdl(k_cfg_sched, dim3(nblk(B * per)), dim3(256), 0, st, (const float*)p->eps, p->latents, (const float*)nullptr,
+               (int64_t)(B * per), cfg_on ? 1 : 0, c.guidance_scale, (const StepCoef*)h->d_coefs, i, (const int*)nullptr);
+    kcount(h, MLDB_KSTAT_MISC);
+    CK(cudaEventRecord(ev[i + 1], st));
+  }
+  CK(cudaStreamSynchronize(st));
+  for (int i = 0; i < nsteps; ++i) CK(cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  CK(cudaGetLastError());
+  return check_ops(h);
+}
+
 // ----------------------------------------------------------------------------- debug aid
 // y = act(A W^T + b) or LayerNorm(A W^T + b + R) through the engine's GEMM operators, so tests can
 // compare the tcgen05 kernels with the CUDA-core kernels (and with torch) shape by shape.
@@ -1619,7 +1657,7 @@ extern "C" int mldb_debug_gemm(mldb_handle* h, const float* A, const float* W, c
                                int32_t K, int32_t K1, int32_t act, int32_t use_tc, int32_t split_out, float* out,
                                void* stream) {
   if (!h || !A || !W || !out || M <= 0 || N <= 0 || K <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
-  CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n_alloc0 = h->allocs.size();
   LinW w;
@@ -1672,7 +1710,7 @@ extern "C" int mldb_debug_ffn(mldb_handle* h, const float* X, const float* W1, c
                               int32_t ff, int32_t mode, float* out, void* stream) {
   if (!h || !X || !W1 || !W2 || !gamma || !beta || !out || M <= 0 || d <= 0 || ff <= 0)
     FAIL(MLDB_ERR_INVALID, "bad argument");
-  CK(cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n_alloc0 = h->allocs.size();
   LinW l1, l2;
@@ -1703,29 +1741,50 @@ extern "C" int mldb_debug_ffn(mldb_handle* h, const float* X, const float* W1, c
   return MLDB_OK;
 }
 
-extern "C" int mldb_debug_attention(mldb_handle* h, const float* QKV, const int32_t* lengths, int32_t nseq, int32_t L,
-                                    int32_t heads, int32_t hd, int32_t mode, float* out, void* stream) {
-  if (!h || !QKV || !out || nseq <= 0 || L <= 0 || heads <= 0 || hd <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
-  CK(cudaSetDevice(h->device));
+extern "C" int mldb_debug_attention(mldb_handle* h, const float* Q, const float* KV, const int32_t* lengths,
+                                    int32_t kv_prefix, int32_t nseq, int32_t Lq, int32_t Lk, int32_t heads, int32_t hd,
+                                    int32_t mode, float* out, void* stream) {
+  if (!h || !Q || !out || nseq <= 0 || Lq <= 0 || Lk <= 0 || heads <= 0 || hd <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  if (!KV && Lq != Lk) FAIL(MLDB_ERR_INVALID, "a packed QKV input is self-attention: Lq must equal Lk");
+  DeviceGuard guard(h->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t n_alloc0 = h->allocs.size();
-  const int d = heads * hd, M = nseq * L;
-  ActBuf qkv, o;
-  TRY(alloc_act(h, M, 3 * d, &qkv));
-  TRY(alloc_act(h, M, d, &o));
-  k_rows_to_split<<<nblk((int64_t)M * 3 * d), 256, 0, st>>>(qkv, QKV, 3 * d, M, 3 * d, 1 << 30, 0, 0, 0, nullptr);
-  AttnArgs a; a.q = qkv; a.q_col0 = 0; a.Lq = L; a.kv = qkv; a.k_col0 = d; a.v_col0 = 2 * d; a.Lk = L;
-  a.nseq = nseq; a.heads = heads; a.hd = hd; a.lengths = lengths; a.kv_prefix = 0; a.out = o;
+  const int d = heads * hd, Mq = nseq * Lq, Mk = nseq * Lk;
+  ActBuf qb, kvb, o;
+  TRY(alloc_act(h, Mq, KV ? d : 3 * d, &qb));
+  TRY(alloc_act(h, Mq, d, &o));
+  rows_to_split(h, qb, Q, qb.cols, Mq, qb.cols, 1 << 30, 0, 0, 0, nullptr, 0, st);
+  AttnArgs a; a.q = qb; a.q_col0 = 0; a.Lq = Lq; a.Lk = Lk;
+  if (KV) {
+    TRY(alloc_act(h, Mk, 2 * d, &kvb));
+    rows_to_split(h, kvb, KV, 2 * d, Mk, 2 * d, 1 << 30, 0, 0, 0, nullptr, 0, st);
+    a.kv = kvb; a.k_col0 = 0; a.v_col0 = d;
+  } else {
+    a.kv = qb; a.k_col0 = d; a.v_col0 = 2 * d;
+  }
+  a.nseq = nseq; a.heads = heads; a.hd = hd; a.lengths = lengths; a.kv_prefix = kv_prefix; a.out = o;
   int rc = MLDB_OK;
   if (mode == 0) simt_attention(a, st);
   else if (mode == 1 && mma_attention_supported(a)) mma_attention(a, st);
-  else if (mode == 2 && tc_attention_supported(a)) tc_attention(a, st);
+  else if (mode == 2 && tc_attention_supported(a)) { if (!tc_attention(a, st)) rc = MLDB_ERR_CUDA; }
   else rc = MLDB_ERR_UNSUPPORTED;
-  if (rc == MLDB_OK) k_split_to_f32<<<nblk((int64_t)M * d), 256, 0, st>>>(o, out, (int64_t)M * d);
+  if (rc == MLDB_OK) k_split_to_f32<<<nblk((int64_t)Mq * d), 256, 0, st>>>(o, out, (int64_t)Mq * d);
   cudaError_t e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
   while (h->allocs.size() > n_alloc0) { cudaFree(h->allocs.back()); h->allocs.pop_back(); }
   if (e != cudaSuccess) FAIL(MLDB_ERR_CUDA, "debug attention: %s", cudaGetErrorString(e));
-  if (rc != MLDB_OK) FAIL(rc, "attention mode %d does not support this shape", mode);
+  if (rc == MLDB_ERR_UNSUPPORTED) FAIL(rc, "attention mode %d does not support this shape", mode);
+  return rc;
+}
+
+// ----------------------------------------------------------------------------- introspection
+extern "C" int mldb_kernel_stats(const mldb_handle* h, int64_t* out, int32_t n) {
+  if (!h || !out || n <= 0) FAIL(MLDB_ERR_INVALID, "bad argument");
+  for (int i = 0; i < n; ++i) out[i] = i < MLDB_KSTAT_COUNT ? h->kstat[i] : 0;
+  return MLDB_OK;
+}
+extern "C" int mldb_reset_kernel_stats(mldb_handle* h) {
+  if (!h) FAIL(MLDB_ERR_INVALID, "null handle");
+  for (int i = 0; i < MLDB_KSTAT_COUNT; ++i) h->kstat[i] = 0;
   return MLDB_OK;
 }

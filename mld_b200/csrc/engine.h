@@ -11,8 +11,6 @@
 #include "misc_kernels.cuh"
 #include "ops.cuh"
 
-#define MLDB_PAIR_MAX_TILES 65536
-
 struct LnW { float* g = nullptr; float* b = nullptr; };
 
 struct EncW {  // TransformerEncoderLayer (cross_attention.py:236-257)
@@ -71,8 +69,14 @@ struct Plan {
   size_t cond_cap = 0;
   int64_t* cond_i = nullptr;
   float* noise_in = nullptr;
+  float* step_noise = nullptr; // plan-owned copy of the injected per-step DDPM noise (graph-stable pointer)
+  size_t noise_cap = 0;
+  const float* noise_ptr = nullptr;  // caller noise pointer baked into the step graph (no-VAE loop)
+  int* d_step = nullptr;       // device-side step counter of the replayed step graph
+  ActBuf in_split;             // model input in split16 form, K zero-padded (no-VAE pose embedding)
   int32_t* lengths = nullptr; // device lengths (plan-owned copy)
   float* joints = nullptr;
+  float* joints_all = nullptr;  // gathered joints of every rank (host entry point with a communicator)
   cudaGraphExec_t exec = nullptr;
   int64_t graph_nodes = 0;
   int sched_epoch = -1;
@@ -104,6 +108,8 @@ struct mldb_handle {
   int64_t* d_timesteps = nullptr;
   StepCoef* d_coefs = nullptr;
   float* d_tt = nullptr;             // [nsteps, d] time tokens (time MLP + PE)
+  float* d_tfeats = nullptr;         // time MLP scratch (sin/cos features)
+  float* d_thid = nullptr;           // time MLP scratch (hidden)
   int sched_epoch = 0;
   // execution
   cudaStream_t cap_stream = nullptr;
@@ -113,23 +119,32 @@ struct mldb_handle {
   bool capturing = false;
   bool use_tc = true;        // tcgen05 GEMMs (option gemm=simt switches to the CUDA-core path)
   bool use_graph = true;
-  bool ffn_pair = false;     // FFN1 + FFN2 as one persistent pair launch (gemm_tc.cu pair mode; measured 3% slower, off)
-  int* pair_cnt = nullptr;   // per-m-tile arrival counters of the pair launch
-  bool pair_chunk = false;   // chunk qkv->attention and FFN1->FFN2 pairs through one L2-sized buffer
-  int chunk_seqs = 0;        // sequences per stack pass (0 = whole batch); see denoiser_pass
   // Concurrent sub-batches: the denoiser stack runs as `branches` independent sequence ranges on
   // parallel streams (parallel chains inside the captured graph), each with its own workspace rows,
   // so one range's kernel tails (316 m-tiles on 148 SMs = 2.13 rounds) and kernel boundaries are
   // filled by the other range's kernels.  1 = off.
   int branches = 2;
-  bool attn_tc = false;      // EXPERIMENTAL tcgen05 attention core (attn_tc.cu): not yet validated on hardware
-  bool branch_round = false; // branch ranges sized to whole rounds of m-tiles (+ a small remainder range)
-  bool lanes = false;        // free-running per-lane chains over the whole reverse loop (see reverse_lanes)
+  int attn_kind = 0;         // 0 = tcgen05 (attn_tc.cu), 1 = mma.sync (attn_mma.cu), 2 = CUDA-core; option `attn`
+  // which kernel every operator of the path was ENQUEUED on (recorded launches, incl. graph capture);
+  // read through mldb_kernel_stats so that tests can assert "nothing fell back to CUDA cores"
+  int64_t kstat[MLDB_KSTAT_COUNT] = {};
+  bool op_failed = false;    // an operator could not be enqueued (tensor-map encoding): sticky until reported
   static constexpr int MAX_BRANCHES = 4;
   cudaStream_t br_stream[MAX_BRANCHES - 1] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_BRANCHES - 1] = {};
   TcCtx* tc = nullptr;
+  // the path's one collective (comm.cu): NCCL communicator bound at run time, gathers on a side stream
+  void* nccl_comm = nullptr;
+  bool comm_owned = false;
+  int comm_world = 1, comm_rank = 0;
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_local_done = nullptr, ev_gather_done[2] = {};
+  int64_t gather_count = 0;
 };
 
 // helpers implemented in engine.cu
 void mldb_set_err(const std::string& s);
+// comm.cu
+void mldb_comm_release(mldb_handle* h);
+int mldb_gather_begin(mldb_handle* h, cudaStream_t stream);
+int mldb_gather_async(mldb_handle* h, float* global, int64_t count, cudaStream_t stream);

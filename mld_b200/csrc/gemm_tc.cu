@@ -9,200 +9,36 @@
 //
 // CTA = 10 warps, one CTA per SM, persistent over tiles: warp 0 = TMA producer, warp 1 = TMEM
 // allocator + MMA issuer (both walk their loops warp-uniformly, one elect.sync lane issues), warps
-// 2..9 = epilogue (TMEM lane quarter = warp_id % 4, two warps per quarter split the columns).
-// Operands stream through a ring of 128B-swizzled shared-memory tiles (BK = 64 halves = one swizzle
-// row) filled by cp.async.bulk.tensor (TMA) and released by tcgen05.commit; accumulators are
-// double-buffered in TMEM and read back with tcgen05.ld.  CG = 2 runs CTA pairs (cta_group::2,
-// M = 256 MMAs issued by the leader, each CTA stages its own A rows and half of the W tile).
-// Epilogues: bias (+ positional table) + activation -> split16 (TMA bulk stores on the pair kernels,
-// st.global through a warp transpose otherwise) / fp32 store, or bias + residual + LayerNorm over
-// the full row (BN == N == 256) -> split16 store, with the row's pre-norm values parked in TMEM
-// between the statistics and the normalise pass.
+// 2..9 = epilogue.  Operands stream through a ring of 128B-swizzled shared-memory tiles (BK = 64
+// halves = one swizzle row) filled by cp.async.bulk.tensor (TMA) and released by tcgen05.commit;
+// accumulators are double-buffered in TMEM and read back with tcgen05.ld.  CG = 2 runs CTA pairs
+// (cta_group::2, M = 256 MMAs issued by the leader, each CTA stages its own A rows and half of the
+// W tile).
+// Epilogues:
+//   plain (LN = false): two warps per TMEM lane quarter split the columns; bias (+ positional
+//       table) + activation -> split16 (TMA bulk stores on the pair kernels, st.global through a
+//       warp transpose otherwise) / fp32 store.
+//   LayerNorm (LN = true, BN == N == 256): the eight epilogue warps form two groups of four that
+//       take alternate tiles (group g drains accumulator stage g), so a thread owns a COMPLETE row:
+//       bias + residual (coalesced loads through a warp transpose, prefetched two 32-column chunks
+//       ahead) + one-pass shifted statistics with the pre-norm row parked in TMEM, then normalise
+//       -> split16 -> TMA bulk stores.  No cross-warp exchange, rolled loops (the round-1 unrolled
+//       epilogue spent ~30 % of its stall samples on instruction fetch).
 #include "gemm_tc.h"
 
-#include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
 
 #include <string>
 
+#include "tc_common.cuh"
+
 void mldb_set_err(const std::string& s);
 
 namespace {
+using namespace tc;
 
 constexpr int BM = 128, BK = 64;
-
-// ------------------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  long long t0 = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && (++spins & 1023u) == 0) {         // a lost arrival must not hang the GPU
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();  // ~2 s
-    }
-  } while (!done);
-}
-// wait on an mbarrier that receives arrivals from the peer CTA (cluster-scope acquire)
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  long long t0 = 0;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && (++spins & 1023u) == 0) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000ll) __trap();
-    }
-  } while (!done);
-}
-
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-// 2-SM (cta_group::2) variant, executed by both CTAs of a pair: the box lands in the executing CTA's
-// shared memory, the bytes are counted on `bar`, a shared::cluster address of the LEADER's mbarrier
-// (cute::SM100_TMA_2SM_LOAD_2D).
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-  return r;
-}
-// Arrive on an mbarrier of another CTA of the cluster.  Deliberately the unqualified form (release at CTA
-// scope, like cutlass::arch::ClusterBarrier::arrive): `.release.cluster` compiles to MEMBAR.ALL.GPU +
-// ERRBAR + CGAERRBAR, i.e. every epilogue warp would wait for its output stores to drain before it
-// may hand the accumulator back (measured: 20 % of all stall samples of the QKV GEMM).  The hazards
-// these arrivals order are TMEM reads (tcgen05.fence::before_thread_sync) and shared-memory writes
-// already made visible to the async proxy (fence.proxy.async), not global memory.
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared -> global bulk tensor store (box given by the map), tracked in the issuing thread's bulk group
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void tma_store_wait_read() {
-  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-// one lane of a fully converged warp (elect.sync): lets ptxas keep the tcgen05 / TMA operands in
-// uniform registers instead of emitting a per-instruction ELECT loop for a lane-id branch
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
-// start address >> 4 | LBO (ignored for swizzled K-major; 1) << 16 | SBO = 1024 B (8 rows x 128 B)
-// << 32 | version 1 << 46 | layout SWIZZLE_128B (2) << 61.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 (bit 4), A = B = F16 (0),
-// both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
-__host__ __device__ constexpr uint32_t make_idesc(int n, int m = BM) {
-  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// 2-SM MMA: D[256 x N] (rows 0-127 in the leader's TMEM, 128-255 in the peer's) += A . B^T with A's
-// 128-row halves and B's N/2-row halves read from the two CTAs' shared memory at the same offsets.
-__device__ __forceinline__ void umma_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-// commit of the pair's MMAs: arrives on the mbarrier at the same offset of both CTAs
-__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"((uint16_t)3) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
-        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
-        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-      : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
 
 // ------------------------------------------------------------------------------ parameters
 struct TcParams {
@@ -217,46 +53,28 @@ struct TcParams {
   int in_group, out_group, out_off;
   const int32_t* zero_lengths;
   // residual + LayerNorm epilogue
-  int ln;
   const __half* res_hi; const __half* res_lo; int ld_res;
-  const float* rowvec; int rv_group;
   const float* gamma; const float* beta;
-  const float* gamma2; const float* beta2;
-  int tma_out;   // fast-path epilogue drains through TMA stores (maps tmOh / tmOl cover out + out_col0)
-  int dbg;   // timing experiments only (MLDB_TC_DBG): 1 = no global stores, 2 = no epilogue math/loads, 4 = no MMA
+  int tma_out;   // the epilogue drains through TMA stores (maps tmOh / tmOl cover out + out_col0)
 };
 
-// Pair mode: one persistent launch runs a producer GEMM (type 0, e.g. FFN1+GELU) and its consumer
-// GEMM (type 1, e.g. FFN2+residual+LayerNorm).  CTA c owns m-tiles c, c+G, c+2G, ... and for each
-// of them runs the n_tiles producer tiles and then the consumer tile, so every dependency is
-// CTA-local: the producer epilogue writes the intermediate tile into this CTA's private 128-row
-// slot of a small scratch buffer (G x 128 rows - it lives in L2 and never travels to HBM), the TMA
-// warp waits on a per-CTA arrival counter (release/acquire + async-proxy fence) before loading the
-// slot as the consumer's A operand, and one kernel boundary disappears.  on == 0: single-GEMM mode.
-struct PairCfg {
-  int on;
-  int* cnt;      // [gridDim.x] arrival counters, zero between launches (the consumer resets them)
-};
-struct WorkItem { int type, m0, n0, s0; };   // s0: first row of this CTA's scratch slot
-
-constexpr int EPI_WARPS = 8;                         // two warps per TMEM lane quarter
+constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;     // producer warp + MMA warp + epilogue warps
 constexpr int MAX_N = 1024;                          // bias staging capacity
 
 template <int BN, int CG = 1>
 struct TileCfg {
-  static constexpr int STAGES = CG == 2 ? (BN == 256 ? 2 : 3) : (BN == 256 ? 2 : 3);
+  static constexpr int STAGES = BN == 256 ? 2 : 3;
   static constexpr int A_BYTES = BM * BK * 2;          // one plane of the A tile (16 KB)
   static constexpr int W_BYTES = BN / CG * BK * 2;     // one plane of this CTA's part of the W tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator
-  // bias[MAX_N] + gamma[256] + beta[256] + LN partials [2][2][128] + barriers
   // per-warp staging: one 32 rows x 64 B transpose buffer (CG = 1: st.global epilogue) or two
-  // {hi, lo} pairs of them (CG = 2: the fast-path epilogue drains through TMA bulk stores)
+  // {hi, lo} pairs of them (CG = 2: the epilogue drains through TMA bulk stores)
   static constexpr int STG_WARP = CG == 2 ? 8192 : 2048;
   static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;
-  // bias[MAX_N] + bias2[256] + gamma[256] + beta[256] + LN partials + staging + barriers
-  static constexpr int AUX_BYTES = MAX_N * 4 + 3 * 256 * 4 + 4 * 128 * 4 + 256 + STG_BYTES;
+  // bias[MAX_N] + gamma[256] + beta[256] + staging + barriers
+  static constexpr int AUX_BYTES = MAX_N * 4 + 2 * 256 * 4 + 256 + STG_BYTES;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;   // + alignment slack
 };
 
@@ -264,13 +82,7 @@ struct TileCfg {
 __device__ __forceinline__ void store_split_chunk(const float (&v)[32], __half* hi, __half* lo) {
   uint32_t ph[16], pl[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    const float2 hf = __half22float2(h2);
-    const __half2 l2 = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
-    ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
-    pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
-  }
+  for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], ph[i], pl[i]);
   uint4* dh = reinterpret_cast<uint4*>(hi);
   uint4* dl = reinterpret_cast<uint4*>(lo);
 #pragma unroll
@@ -284,6 +96,7 @@ __device__ __forceinline__ void store_split_chunk(const float (&v)[32], __half* 
 // A thread owns one tile row (TMEM lane); a 32-column fp16 chunk of that row is 64 B = 4 x 16 B
 // slots.  Staging tile: 32 rows x 64 B, slot index XOR-swizzled with (row >> 1) & 3 (conflict-free
 // for both the row-owner pattern and the coalesced pattern: lane -> row i*8 + lane/4, slot lane%4).
+// The same image is what a SWIZZLE_64B tensor map with a 32 x 32 box reads / writes.
 __device__ __forceinline__ uint32_t stg_off(int row, int slot) {
   return (uint32_t)(row * 64 + ((slot ^ ((row >> 1) & 3)) << 4));
 }
@@ -302,7 +115,7 @@ __device__ __forceinline__ void store_plane_coalesced(uint8_t* stg, const uint32
   }
   __syncwarp();
 }
-// global (coalesced pattern, issued earlier into g[4]) -> registers in row-owner layout
+// global (coalesced pattern: lane -> row i*8 + lane/4, 16-B slot lane%4) -> g[4]
 __device__ __forceinline__ void load_plane_issue(const __half* gbase, int64_t ld, int rows_valid, int lane, uint4 (&g)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -310,6 +123,7 @@ __device__ __forceinline__ void load_plane_issue(const __half* gbase, int64_t ld
     g[i] = (rr < rows_valid) ? *reinterpret_cast<const uint4*>(gbase + (int64_t)rr * ld + qq * 8) : make_uint4(0, 0, 0, 0);
   }
 }
+// g[4] (coalesced pattern) -> rowv[4] (row-owner layout) through a 2 KB staging tile
 __device__ __forceinline__ void plane_to_rows(uint8_t* stg, const uint4 (&g)[4], int lane, uint4 (&rowv)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -321,22 +135,30 @@ __device__ __forceinline__ void plane_to_rows(uint8_t* stg, const uint4 (&g)[4],
   for (int j = 0; j < 4; ++j) rowv[j] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
   __syncwarp();
 }
+// both planes at once (two staging tiles, half the warp barriers)
+__device__ __forceinline__ void planes_to_rows(uint8_t* stg, const uint4 (&gh)[4], const uint4 (&gl)[4], int lane,
+                                               uint4 (&rh)[4], uint4 (&rl)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = i * 8 + (lane >> 2), qq = lane & 3;
+    *reinterpret_cast<uint4*>(stg + stg_off(rr, qq)) = gh[i];
+    *reinterpret_cast<uint4*>(stg + 2048 + stg_off(rr, qq)) = gl[i];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    rh[j] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
+    rl[j] = *reinterpret_cast<const uint4*>(stg + 2048 + stg_off(lane, j));
+  }
+  __syncwarp();
+}
 // fp32 x32 -> packed split16 words (hi and lo planes)
 __device__ __forceinline__ void pack_split(const float (&v)[32], uint32_t (&ph)[16], uint32_t (&pl)[16]) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const __half2 h2 = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    const float2 hf = __half22float2(h2);
-    const __half2 l2 = __floats2half2_rn(v[2 * i] - hf.x, v[2 * i + 1] - hf.y);
-    ph[i] = *reinterpret_cast<const uint32_t*>(&h2);
-    pl[i] = *reinterpret_cast<const uint32_t*>(&l2);
-  }
+  for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], ph[i], pl[i]);
 }
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
 
 // x[i] = act(acc[i] * s + bias[i]) for one 32-column chunk; bias read as float4 broadcasts.
 template <int ACT>
@@ -354,73 +176,116 @@ __device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&
   }
 }
 
-// j-th work item of this CTA.  Single-GEMM mode: CTA pairs (cl = 2, cta_group::2) walk (m-pair, n)
-// items in lockstep - CTA rank r of a pair owns m-tile mp*2 + r and half of the W tile.
-__device__ __forceinline__ WorkItem decode_item(int j, const TcParams& p, int pair, int bn, int cl, int rank) {
-  WorkItem it;
-  it.s0 = blockIdx.x * BM;
-  if (!pair) {
-    const int t = (int)blockIdx.x / cl + j * ((int)gridDim.x / cl);
-    it.type = 0; it.m0 = ((t / p.n_tiles) * cl + rank) * BM; it.n0 = (t % p.n_tiles) * bn;
-    return it;
+// one 32-column chunk of the LayerNorm statistics pass: x = acc * sc + bias + (res_hi + res_lo);
+// accumulates sum(x - K), sum((x - K)^2) and leaves x in r[] (to be parked in TMEM)
+__device__ __forceinline__ void ln_stats_chunk(uint32_t (&r)[32], const uint4 (&rh)[4], const uint4 (&rl)[4],
+                                               const float* bch, float sc, float shiftK, float& s1, float& s2) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t ah[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
+    const uint32_t al[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
+    const float4 b0 = reinterpret_cast<const float4*>(bch)[2 * i], b1 = reinterpret_cast<const float4*>(bch)[2 * i + 1];
+    const float bia[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&ah[j]));
+      const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&al[j]));
+      const int e = i * 8 + j * 2;
+      const float x0 = fmaf(__uint_as_float(r[e]), sc, bia[2 * j]) + (hf2.x + lf2.x);
+      const float x1 = fmaf(__uint_as_float(r[e + 1]), sc, bia[2 * j + 1]) + (hf2.y + lf2.y);
+      const float d0 = x0 - shiftK, d1 = x1 - shiftK;
+      s1 += d0 + d1;
+      s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+      r[e] = __float_as_uint(x0);
+      r[e + 1] = __float_as_uint(x1);
+    }
   }
-  const int per = p.n_tiles + 1;
-  const int k = j / per, r = j - k * per;
-  it.m0 = (blockIdx.x + k * gridDim.x) * BM;
-  if (r < p.n_tiles) { it.type = 0; it.n0 = r * bn; } else { it.type = 1; it.n0 = 0; }
-  return it;
 }
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// first pre-norm value of a row (column 0 of chunk 0): the shift of the one-pass variance
+__device__ __forceinline__ float ln_first_x(const uint32_t (&r)[32], const uint4 (&rh)[4], const uint4 (&rl)[4],
+                                            const float* bch, float sc) {
+  const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&rh[0].x));
+  const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&rl[0].x));
+  return fmaf(__uint_as_float(r[0]), sc, bch[0]) + (hf2.x + lf2.x);
+}
+// y = (x * a + b) * gamma + beta for one parked 32-column chunk
+__device__ __forceinline__ void ln_norm_chunk(const uint32_t (&r)[32], float (&v)[32], const float* g, const float* be,
+                                              float a, float b) {
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const float4* e4 = reinterpret_cast<const float4*>(be);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 gg = g4[i], bb = e4[i];
+    v[4 * i + 0] = fmaf(fmaf(__uint_as_float(r[4 * i + 0]), a, b), gg.x, bb.x);
+    v[4 * i + 1] = fmaf(fmaf(__uint_as_float(r[4 * i + 1]), a, b), gg.y, bb.y);
+    v[4 * i + 2] = fmaf(fmaf(__uint_as_float(r[4 * i + 2]), a, b), gg.z, bb.z);
+    v[4 * i + 3] = fmaf(fmaf(__uint_as_float(r[4 * i + 3]), a, b), gg.w, bb.w);
+  }
+}
+// row-owner packed chunk -> SWIZZLE_64B staging pair -> two TMA bulk stores (lane 0 owns the warp's
+// bulk groups; at most one older pair in flight per warp: the caller alternates `buf`)
+__device__ __forceinline__ void stage_and_store(uint8_t* sb2, const uint32_t (&ph)[16], const uint32_t (&pl)[16], int lane,
+                                                const CUtensorMap* mh, const CUtensorMap* ml, int col, int row0) {
+  if (lane == 0) tma_store_wait_read<1>();
+  __syncwarp();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    *reinterpret_cast<uint4*>(sb2 + stg_off(lane, j)) = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+    *reinterpret_cast<uint4*>(sb2 + 2048 + stg_off(lane, j)) = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(mh, smem_u32(sb2), col, row0);
+    tma_store_2d(ml, smem_u32(sb2 + 2048), col, row0);
+    tma_store_commit();
+  }
+}
+
+// j-th work item of this CTA: CTA pairs (CG = 2) walk (m-pair, n) items in lockstep - CTA rank r of
+// a pair owns m-tile mp*2 + r and half of the W tile.
+__device__ __forceinline__ void decode_item(int j, const TcParams& p, int bn, int cg, int rank, int& m0, int& n0) {
+  const int t = (int)blockIdx.x / cg + j * ((int)gridDim.x / cg);
+  m0 = ((t / p.n_tiles) * cg + rank) * BM;
+  n0 = (t % p.n_tiles) * bn;
 }
 
 // ------------------------------------------------------------------------------ the kernel
 // Persistent: CTA (pair) c walks items c, c + #CTAs (pairs), ...; item t -> (m = t / n_tiles, n = t % n_tiles).
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the TMA/MMA main loop of tile i + 1.
-template <int BN, int CG>
+template <int BN, int CG, bool LN>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
           const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
-          const __grid_constant__ CUtensorMap tmBh, const __grid_constant__ CUtensorMap tmBl,
-          const __grid_constant__ CUtensorMap tmVh, const __grid_constant__ CUtensorMap tmVl,
           const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
-          const TcParams p, const TcParams p2, const PairCfg pc) {
+          const TcParams p) {
+  static_assert(!LN || BN == 256, "the LayerNorm epilogue covers a full 256-wide row");
   using Cfg = TileCfg<BN, CG>;
-  constexpr int CL = CG;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int EMPTY_ARRIVALS = (LN ? 4 : EPI_WARPS) * CG;   // LN: one group of four warps per accumulator stage
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment by pointer arithmetic (an integer round trip would lose the shared address space
   // and turn every staging access into a generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
   float* s_bias = reinterpret_cast<float*>(aux);              // [MAX_N]
-  float* s_bias2 = s_bias + MAX_N;                            // [256] consumer GEMM bias (pair mode)
-  float* s_gamma = s_bias2 + 256;                             // [256]
+  float* s_gamma = s_bias + MAX_N;                            // [256]
   float* s_beta = s_gamma + 256;                              // [256]
-  float* s_part = s_beta + 256;                               // [2 passes][2 halves][128 rows]
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_part + 4 * 128);   // [EPI_WARPS][2048], 16B aligned
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_beta + 256);   // [EPI_WARPS][STG_WARP], 16B aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + Cfg::STG_BYTES);
-  // bars: full[S], empty[S], tmem_full[2], tmem_empty[2]
-  uint64_t* bar_full = bars;
-  uint64_t* bar_empty = bars + STAGES;
-  uint64_t* bar_tfull = bars + 2 * STAGES;
-  uint64_t* bar_tempty = bars + 2 * STAGES + 2;
+  uint64_t* bar_full = bars;                    // [STAGES]
+  uint64_t* bar_empty = bars + STAGES;          // [STAGES]
+  uint64_t* bar_tfull = bars + 2 * STAGES;      // [2]
+  uint64_t* bar_tempty = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
-  const bool pair = pc.on != 0;
-  // number of work items of this CTA
-  const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
-  const int ncl = (int)gridDim.x / CL, cid = (int)blockIdx.x / CL;          // clusters, this CTA's cluster
-  const int ngroups = ((p.m_tiles + CL - 1) / CL) * p.n_tiles;               // (m-group, n) items
-  const int nlocal = pair ? ((p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * (p.n_tiles + 1)
-                          : (ngroups - cid + ncl - 1) / ncl;
-  const TcParams& pl = pair ? p2 : p;                         // the GEMM whose epilogue is the LayerNorm
-  const int nst = (p.dbg & 8) ? 2 : STAGES;                   // timing experiment: use two ring stages only
+  const int rank = CG > 1 ? (int)cluster_ctarank() : 0;
+  const int ncl = (int)gridDim.x / CG, cid = (int)blockIdx.x / CG;          // clusters, this CTA's cluster
+  const int ngroups = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;               // (m-group, n) items
+  const int nlocal = (ngroups - cid + ncl - 1) / ncl;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -429,28 +294,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_tfull[s]), 1);
-      mbar_init(smem_u32(&bar_tempty[s]), EPI_WARPS * CG);  // 2-SM: the leader's barrier collects both CTAs' warps
+      mbar_init(smem_u32(&bar_tempty[s]), EMPTY_ARRIVALS);    // 2-SM: the leader's barrier collects both CTAs' warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmA1h); tma_prefetch_desc(&tmA1l); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
   }
   if (CG > 1) { __syncthreads(); cluster_sync_all(); }   // 2-SM TMEM allocation needs both CTAs of the pair resident
-  if (warp == 1) {
-    if (CG == 1) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-  }
+  if (warp == 1) tmem_alloc<CG>(smem_u32(tmem_slot), Cfg::TMEM_COLS);
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.0f;
-    if (pl.ln)
-      for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) {
-        s_gamma[i] = pl.gamma[i]; s_beta[i] = pl.beta[i];
-        s_bias2[i] = (pair && p2.bias) ? p2.bias[i] : 0.0f;
-      }
+    if (LN)
+      for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) { s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
   }
   pdl_trigger();               // let the next kernel's prologue overlap our tail
   tc_fence_before();
@@ -461,34 +315,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   pdl_wait();                  // everything below touches activations of the previous kernel
 
   if (warp == 0) {
-    {
-      // ---------------------------------------------------------------- TMA producer
-      // The whole warp walks the loop (uniform control flow), one elected lane issues: ptxas then keeps
-      // the TMA / MMA operands in uniform registers instead of wrapping every instruction in an ELECT loop.
-      int kbg = 0;                                   // k-block counter across tiles (ring position)
-      for (int j = 0; j < nlocal; ++j) {
-        const WorkItem wi = decode_item(j, p, pair, BN, CL, rank);
-        const TcParams& q = wi.type ? p2 : p;
-        const int m0 = wi.m0, n0 = wi.n0;
-        if (wi.type && lane == 0) {
-          // consumer tile: wait until every producer-epilogue warp has published its part of the slot
-          const int mt = blockIdx.x, target = EPI_WARPS * p.n_tiles;
-          long long t0 = 0; unsigned spins = 0;
-          while (ld_acquire_gpu(pc.cnt + mt) < target) {
-            if ((++spins & 255u) == 0) {
-              const long long now = clock64();
-              if (t0 == 0) t0 = now; else if (now - t0 > 4000000000ll) __trap();
-            }
-          }
-          pc.cnt[mt] = 0;                                   // ready for the next launch
-          asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes -> TMA reads
-        }
-        __syncwarp();
-        for (int kb = 0; kb < q.kblocks; ++kb, ++kbg) {
-          const int s = kbg % nst;
-          const uint32_t ph = (uint32_t)(kbg / nst) & 1u;
-          mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
-          if (elect_one()) {
+    // ---------------------------------------------------------------- TMA producer
+    // The whole warp walks the loop (uniform control flow), one elected lane issues: ptxas then keeps
+    // the TMA / MMA operands in uniform registers instead of wrapping every instruction in an ELECT loop.
+    int kbg = 0;                                   // k-block counter across tiles (ring position)
+    for (int j = 0; j < nlocal; ++j) {
+      int m0, n0;
+      decode_item(j, p, BN, CG, rank, m0, n0);
+      for (int kb = 0; kb < p.kblocks; ++kb, ++kbg) {
+        const int s = kbg % STAGES;
+        const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
+        mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
+        if (elect_one()) {
           uint32_t full = smem_u32(&bar_full[s]);
           if (CG == 1) {
             mbar_expect_tx(full, Cfg::STAGE_BYTES);
@@ -498,55 +336,47 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           }
           const uint32_t sAh = smem_u32(smem + s * Cfg::STAGE_BYTES), sAl = sAh + Cfg::A_BYTES;
           const uint32_t sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
-          if (wi.type) {
-            tma_load_2d(sAh, &tmBh, full, kb * BK, wi.s0);
-            tma_load_2d(sAl, &tmBl, full, kb * BK, wi.s0);
-            tma_load_2d(sWh, &tmVh, full, kb * BK, n0);
-            tma_load_2d(sWl, &tmVl, full, kb * BK, n0);
-          } else {
-            if (CG == 1) {
-              if (kb < q.kb1) {
-                tma_load_2d(sAh, &tmA1h, full, kb * BK, m0);
-                tma_load_2d(sAl, &tmA1l, full, kb * BK, m0);
-              } else {
-                tma_load_2d(sAh, &tmA2h, full, (kb - q.kb1) * BK, m0);
-                tma_load_2d(sAl, &tmA2l, full, (kb - q.kb1) * BK, m0);
-              }
-              tma_load_2d(sWh, &tmWh, full, kb * BK, n0);
-              tma_load_2d(sWl, &tmWl, full, kb * BK, n0);
+          if (CG == 1) {
+            if (kb < p.kb1) {
+              tma_load_2d(sAh, &tmA1h, full, kb * BK, m0);
+              tma_load_2d(sAl, &tmA1l, full, kb * BK, m0);
             } else {
-              // this CTA's own 128 rows of A and rows [rank*BN/2, (rank+1)*BN/2) of the W tile
-              if (kb < q.kb1) {
-                tma_load_2d_2sm(sAh, &tmA1h, full, kb * BK, m0);
-                tma_load_2d_2sm(sAl, &tmA1l, full, kb * BK, m0);
-              } else {
-                tma_load_2d_2sm(sAh, &tmA2h, full, (kb - q.kb1) * BK, m0);
-                tma_load_2d_2sm(sAl, &tmA2l, full, (kb - q.kb1) * BK, m0);
-              }
-              tma_load_2d_2sm(sWh, &tmWh, full, kb * BK, n0 + rank * (BN / 2));
-              tma_load_2d_2sm(sWl, &tmWl, full, kb * BK, n0 + rank * (BN / 2));
+              tma_load_2d(sAh, &tmA2h, full, (kb - p.kb1) * BK, m0);
+              tma_load_2d(sAl, &tmA2l, full, (kb - p.kb1) * BK, m0);
             }
+            tma_load_2d(sWh, &tmWh, full, kb * BK, n0);
+            tma_load_2d(sWl, &tmWl, full, kb * BK, n0);
+          } else {
+            // this CTA's own 128 rows of A and rows [rank*BN/2, (rank+1)*BN/2) of the W tile
+            if (kb < p.kb1) {
+              tma_load_2d_2sm(sAh, &tmA1h, full, kb * BK, m0);
+              tma_load_2d_2sm(sAl, &tmA1l, full, kb * BK, m0);
+            } else {
+              tma_load_2d_2sm(sAh, &tmA2h, full, (kb - p.kb1) * BK, m0);
+              tma_load_2d_2sm(sAl, &tmA2l, full, (kb - p.kb1) * BK, m0);
+            }
+            tma_load_2d_2sm(sWh, &tmWh, full, kb * BK, n0 + rank * (BN / 2));
+            tma_load_2d_2sm(sWl, &tmWl, full, kb * BK, n0 + rank * (BN / 2));
           }
-          }
-          __syncwarp();
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
     if (rank == 0) {
       // ---------------------------------------------------------------- MMA issuer (2-SM: the leader CTA)
       constexpr uint32_t idesc = make_idesc(BN, BM * CG);
-      int kbg = 0, it = 0;
-      for (; it < nlocal; ++it) {
+      int kbg = 0;
+      for (int it = 0; it < nlocal; ++it) {
         const int as = it & 1;
         if (CG == 1) mbar_wait(smem_u32(&bar_tempty[as]), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained it
         else mbar_wait_cluster(smem_u32(&bar_tempty[as]), (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
-        const int nkb = decode_item(it, p, pair, BN, CL, rank).type ? p2.kblocks : p.kblocks;
+        const int nkb = p.kblocks;
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
-          const int s = kbg % nst;
-          const uint32_t ph = (uint32_t)(kbg / nst) & 1u;
+          const int s = kbg % STAGES;
+          const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
           mbar_wait(smem_u32(&bar_full[s]), ph);
           tc_fence_after();
           if (elect_one()) {
@@ -554,20 +384,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
             const uint32_t sWh = sAl + Cfg::A_BYTES, sWl = sWh + Cfg::W_BYTES;
             // descriptors of the k-block's first 16-wide slice; +2 (32 B >> 4) per further slice
             uint64_t ah = make_desc(sAh), al = make_desc(sAl), wh = make_desc(sWh), wl = make_desc(sWl);
-            if (!(p.dbg & 4)) {
 #pragma unroll
-              for (int kk = 0; kk < BK / 16; ++kk) {
-                if (CG == 1) {
-                  umma(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
-                  umma(tacc, ah, wl, idesc, 1u);
-                  umma(tacc, ah, wh, idesc, 1u);
-                } else {
-                  umma_2sm(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
-                  umma_2sm(tacc, ah, wl, idesc, 1u);
-                  umma_2sm(tacc, ah, wh, idesc, 1u);
-                }
-                ah += 2; al += 2; wh += 2; wl += 2;
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              if (CG == 1) {
+                umma(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
+                umma(tacc, ah, wl, idesc, 1u);
+                umma(tacc, ah, wh, idesc, 1u);
+              } else {
+                umma_2sm(tacc, al, wh, idesc, (kb | kk) != 0 ? 1u : 0u);
+                umma_2sm(tacc, ah, wl, idesc, 1u);
+                umma_2sm(tacc, ah, wh, idesc, 1u);
               }
+              ah += 2; al += 2; wh += 2; wl += 2;
             }
             if (CG == 1) umma_commit(smem_u32(&bar_empty[s]));      // frees the stage when these MMAs retire
             else umma_commit_2sm(smem_u32(&bar_empty[s]));          // ... in both CTAs of the pair
@@ -580,236 +408,199 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9)
+  } else if constexpr (!LN) {
+    // ------------------------------------------------------------------ plain epilogue (warps 2..9)
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int hf = (warp - 2) >> 2;                  // which half of the tile's columns
     const int row = q * 32 + lane;
     constexpr int CH = BN / 64;                      // 32-column chunks per warp
     uint32_t r[32];
     float v[32];
-    int it = 0;
     int tbuf = 0;                                    // staging pair for the next TMA store
-    for (; it < nlocal; ++it) {
+    uint8_t* const stg = s_stage + (warp - 2) * Cfg::STG_WARP;
+    for (int it = 0; it < nlocal; ++it) {
       const int as = it & 1;
-      const WorkItem wi = decode_item(it, p, pair, BN, CL, rank);
-      const TcParams& pp = wi.type ? p2 : p;
-      const float* const sb = wi.type ? s_bias2 : s_bias;
-      const int m0 = wi.m0, n0 = wi.n0;
+      int m0, n0;
+      decode_item(it, p, BN, CG, rank, m0, n0);
       const int m = m0 + row;
-      const bool row_ok = m < pp.M;
+      const bool row_ok = m < p.M;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + hf * (BN / 2));
-      uint8_t* const stg = s_stage + (warp - 2) * Cfg::STG_WARP;
-      const bool to_slot = pair && wi.type == 0;             // producer tile: write into the CTA's slot
-      const int wrow0 = (to_slot ? wi.s0 : m0) + q * 32;     // first output row owned by this warp
-      const int rows_valid = to_slot ? 32 : min(32, pp.M - wrow0);   // <= 0: nothing to write
-      if (!pp.ln) {
-        mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
-        tc_fence_after();
-        int seq = 0, pos = m;
-        if (row_ok && pp.in_group < pp.M) { seq = m / pp.in_group; pos = m - seq * pp.in_group; }
-        const int64_t orow = (int64_t)seq * pp.out_group + pp.out_off + pos;
-        const bool zero = row_ok && pp.zero_lengths != nullptr && pos >= pp.zero_lengths[seq];
-        const float* tab = pp.addtab ? pp.addtab + (int64_t)(pp.out_off + pos) * pp.N : nullptr;
-        // fast path: identity row mapping, split16 output, no table / masking (warp-uniform)
-        const bool fast = pp.addtab == nullptr && pp.zero_lengths == nullptr && pp.out_hi != nullptr &&
-                          pp.out_f32 == nullptr && pp.in_group >= pp.M && pp.out_group == 0 && pp.out_off == 0;
-        const float inv_scale = pp.inv_scale;
-        const int act = pp.act, N = pp.N;
-        __half* const ohi = pp.out_hi;
-        __half* const olo = pp.out_lo;
-        const int64_t obase = orow * pp.ld_out + pp.out_col0;
+      const int wrow0 = m0 + q * 32;                 // first output row owned by this warp
+      const int rows_valid = min(32, p.M - wrow0);   // <= 0: nothing to write
+      mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      int seq = 0, pos = m;
+      if (row_ok && p.in_group < p.M) { seq = m / p.in_group; pos = m - seq * p.in_group; }
+      const int64_t orow = (int64_t)seq * p.out_group + p.out_off + pos;
+      const bool zero = row_ok && p.zero_lengths != nullptr && pos >= p.zero_lengths[seq];
+      const float* tab = p.addtab ? p.addtab + (int64_t)(p.out_off + pos) * p.N : nullptr;
+      // fast path: identity row mapping, split16 output, no table / masking (warp-uniform)
+      const bool fast = p.addtab == nullptr && p.zero_lengths == nullptr && p.out_hi != nullptr &&
+                        p.out_f32 == nullptr && p.in_group >= p.M && p.out_group == 0 && p.out_off == 0;
+      const float inv_scale = p.inv_scale;
+      const int act = p.act, N = p.N;
+      __half* const ohi = p.out_hi;
+      __half* const olo = p.out_lo;
+      const int64_t obase = orow * p.ld_out + p.out_col0;
 #pragma unroll 1
-        for (int c = 0; c < ((p.dbg & 2) ? 0 : CH); ++c) {
-          tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
-          const int nb = n0 + hf * (BN / 2) + c * 32;
-          if (fast && nb + 32 <= N) {               // warp-uniform branch: all lanes take part
-            switch (act) {                          // once per chunk
-              case ACT_NONE: epi_chunk_fast<ACT_NONE>(r, v, sb + nb, inv_scale); break;
-              case ACT_GELU: epi_chunk_fast<ACT_GELU>(r, v, sb + nb, inv_scale); break;
-              case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, sb + nb, inv_scale); break;
-              default:       epi_chunk_fast<ACT_SILU>(r, v, sb + nb, inv_scale); break;
-            }
-            uint32_t ph[16], pl[16];
-            pack_split(v, ph, pl);
-            if (CG == 2 && p.tma_out) {
-              // row-owner writes into a SWIZZLE_64B staging pair, then two bulk tensor stores (the map
-              // clips rows >= M); lane 0 owns the warp's bulk groups, at most one older pair in flight
-              if (lane == 0) tma_store_wait_read<1>();
-              __syncwarp();
-              uint8_t* const sb2 = stg + tbuf * 4096;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                *reinterpret_cast<uint4*>(sb2 + stg_off(lane, j)) = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-                *reinterpret_cast<uint4*>(sb2 + 2048 + stg_off(lane, j)) = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-              }
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              __syncwarp();
-              if (lane == 0 && !(p.dbg & 1)) {
-                tma_store_2d(&tmOh, smem_u32(sb2), nb, wrow0);
-                tma_store_2d(&tmOl, smem_u32(sb2 + 2048), nb, wrow0);
-                tma_store_commit();
-              }
-              tbuf ^= 1;
-            } else if (!(p.dbg & 1)) {
-              const int64_t o = (int64_t)wrow0 * pp.ld_out + pp.out_col0 + nb;
-              store_plane_coalesced(stg, ph, ohi + o, pp.ld_out, rows_valid, lane);
-              store_plane_coalesced(stg, pl, olo + o, pp.ld_out, rows_valid, lane);
-            }
-          } else if (row_ok && nb < N) {
-            const bool full = nb + 32 <= N;
-            {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float x = __uint_as_float(r[i]) * inv_scale + sb[min(nb + i, MAX_N - 1)];
-                if (tab && (full || nb + i < N)) x += tab[nb + i];
-                x = apply_act(x, act);
-                v[i] = zero ? 0.0f : x;
-              }
-              if (ohi) {
-                const int64_t o = obase + nb;
-                if (full) {
-                  store_split_chunk(v, ohi + o, olo + o);
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) {
-                    if (nb + i < N) {
-                      __half h, l;
-                      split_f32(v[i], h, l);
-                      ohi[o + i] = h; olo[o + i] = l;
-                    }
-                  }
-                }
-              }
-              if (pp.out_f32) {
-                float* dst = pp.out_f32 + orow * pp.ldc + nb;
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                  if (full || nb + i < N) dst[i] = v[i];
-              }
-            }
-          }
-          __syncwarp();
-        }
-        if (pair && wi.type == 0) {              // publish this warp's part of the intermediate tile
-          __threadfence();
-          __syncwarp();
-          if (lane == 0) atomicAdd(pc.cnt + blockIdx.x, 1);
-        }
-      } else {
-        // x = acc*s + bias + residual (+ rowvec); y = LayerNorm(x) over the 256-wide row, eps 1e-5.
-        // Two warps share a row (column halves) and exchange partial sums through shared memory; the
-        // pre-norm row is parked in TMEM between the statistics pass and the normalise pass.
-        // Statistics in one pass with a per-row shift K (the row's first residual value) so that
-        // var = E[(x-K)^2] - E[x-K]^2 does not cancel.  The residual chunk c+1 is fetched while
-        // chunk c is processed (the loop is fully unrolled), chunk 0 before the accumulator is ready.
-        if (p.dbg & 32) {                          // timing experiment: no LayerNorm epilogue work
-          mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
-          tc_fence_after();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) { if (CG == 1) mbar_arrive(smem_u32(&bar_tempty[as])); else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[as]), 0)); }
-          continue;
-        }
-        const float* rv = (row_ok && pp.rowvec) ? pp.rowvec + (int64_t)(m / pp.rv_group) * BN : nullptr;
-        const int cb = hf * (BN / 2);
-        const bool has_res = pp.res_hi != nullptr;                       // warp-uniform
-        const float shiftK = (has_res && row_ok) ? join_f32(pp.res_hi[(int64_t)m * pp.ld_res], pp.res_lo[(int64_t)m * pp.ld_res]) : 0.0f;
-        const __half* rbh = pp.res_hi + (int64_t)wrow0 * pp.ld_res + cb;   // this warp's 32 rows, its column half
-        const __half* rbl = pp.res_lo + (int64_t)wrow0 * pp.ld_res + cb;
-        uint4 gh[4], gl[4];                       // residual chunk in the coalesced (4 lanes per row) pattern
-        if (has_res) {
-          load_plane_issue(rbh, pp.ld_res, rows_valid, lane, gh);
-          load_plane_issue(rbl, pp.ld_res, rows_valid, lane, gl);
-        }
-        mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
-        tc_fence_after();
-        float s1 = 0.0f, s2 = 0.0f;
-        const float sc = pp.inv_scale;
-#pragma unroll
-        for (int c = 0; c < CH; ++c) {
-          uint4 rh[4], rl[4];                     // the same chunk, row-owner layout
-          if (has_res) {
-            plane_to_rows(stg, gh, lane, rh);
-            plane_to_rows(stg, gl, lane, rl);
-            if (c + 1 < CH) {                     // fetch the next chunk under this one's math
-              load_plane_issue(rbh + (c + 1) * 32, pp.ld_res, rows_valid, lane, gh);
-              load_plane_issue(rbl + (c + 1) * 32, pp.ld_res, rows_valid, lane, gl);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
-          }
-          tmem_ld32(trow + c * 32, r);
-          const float* bch = sb + cb + c * 32;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t ah[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
-            const uint32_t al[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
-            const float4 b0 = reinterpret_cast<const float4*>(bch)[2 * i], b1 = reinterpret_cast<const float4*>(bch)[2 * i + 1];
-            const float bia[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&ah[j]));
-              const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&al[j]));
-              const int e = i * 8 + j * 2;
-              float x0 = fmaf(__uint_as_float(r[e]), sc, bia[2 * j]) + (hf2.x + lf2.x);
-              float x1 = fmaf(__uint_as_float(r[e + 1]), sc, bia[2 * j + 1]) + (hf2.y + lf2.y);
-              if (rv) { x0 += rv[cb + c * 32 + e]; x1 += rv[cb + c * 32 + e + 1]; }
-              const float d0 = x0 - shiftK, d1 = x1 - shiftK;
-              s1 += d0 + d1;
-              s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
-              r[e] = __float_as_uint(x0);
-              r[e + 1] = __float_as_uint(x1);
-            }
-          }
-          tmem_st32(trow + c * 32, r);
-        }
-        s_part[hf * 128 + row] = s1;
-        s_part[256 + hf * 128 + row] = s2;
-        epi_bar_sync();
-        const float e1 = (s_part[row] + s_part[128 + row]) * (1.0f / BN);
-        const float e2 = (s_part[256 + row] + s_part[256 + 128 + row]) * (1.0f / BN);
-        const float mean = shiftK + e1;
-        const float rstd = rsqrtf(fmaxf(e2 - e1 * e1, 0.0f) + 1e-5f);
-#pragma unroll 1
-        for (int c = 0; c < CH; ++c) {
-          tmem_ld32(trow + c * 32, r);
-          {
-            const float4* g4 = reinterpret_cast<const float4*>(s_gamma + cb + c * 32);
-            const float4* e4 = reinterpret_cast<const float4*>(s_beta + cb + c * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 gg = g4[i], bb = e4[i];
-              v[4 * i + 0] = fmaf((__uint_as_float(r[4 * i + 0]) - mean) * rstd, gg.x, bb.x);
-              v[4 * i + 1] = fmaf((__uint_as_float(r[4 * i + 1]) - mean) * rstd, gg.y, bb.y);
-              v[4 * i + 2] = fmaf((__uint_as_float(r[4 * i + 2]) - mean) * rstd, gg.z, bb.z);
-              v[4 * i + 3] = fmaf((__uint_as_float(r[4 * i + 3]) - mean) * rstd, gg.w, bb.w);
-            }
+      for (int c = 0; c < CH; ++c) {
+        tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
+        const int nb = n0 + hf * (BN / 2) + c * 32;
+        if (fast && nb + 32 <= N) {               // warp-uniform branch: all lanes take part
+          switch (act) {                          // once per chunk
+            case ACT_NONE: epi_chunk_fast<ACT_NONE>(r, v, s_bias + nb, inv_scale); break;
+            case ACT_GELU: epi_chunk_fast<ACT_GELU>(r, v, s_bias + nb, inv_scale); break;
+            case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, s_bias + nb, inv_scale); break;
+            default:       epi_chunk_fast<ACT_SILU>(r, v, s_bias + nb, inv_scale); break;
           }
           uint32_t ph[16], pl[16];
           pack_split(v, ph, pl);
-          const int64_t o = (int64_t)wrow0 * pp.ld_out + cb + c * 32;
-          store_plane_coalesced(stg, ph, pp.out_hi + o, pp.ld_out, rows_valid, lane);
-          store_plane_coalesced(stg, pl, pp.out_lo + o, pp.ld_out, rows_valid, lane);
+          if (CG == 2 && p.tma_out) {
+            stage_and_store(stg + tbuf * 4096, ph, pl, lane, &tmOh, &tmOl, nb, wrow0);   // the map clips rows >= M
+            tbuf ^= 1;
+          } else {
+            const int64_t o = (int64_t)wrow0 * p.ld_out + p.out_col0 + nb;
+            store_plane_coalesced(stg, ph, ohi + o, p.ld_out, rows_valid, lane);
+            store_plane_coalesced(stg, pl, olo + o, p.ld_out, rows_valid, lane);
+          }
+        } else if (row_ok && nb < N) {
+          const bool full = nb + 32 <= N;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(r[i]) * inv_scale + s_bias[min(nb + i, MAX_N - 1)];
+            if (tab && (full || nb + i < N)) x += tab[nb + i];
+            x = apply_act(x, act);
+            v[i] = zero ? 0.0f : x;
+          }
+          if (ohi) {
+            const int64_t o = obase + nb;
+            if (full) {
+              store_split_chunk(v, ohi + o, olo + o);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (nb + i < N) {
+                  __half h, l;
+                  split_f32(v[i], h, l);
+                  ohi[o + i] = h; olo[o + i] = l;
+                }
+              }
+            }
+          }
+          if (p.out_f32) {
+            float* dst = p.out_f32 + orow * p.ldc + nb;
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (full || nb + i < N) dst[i] = v[i];
+          }
         }
-        // the partial sums of this tile may be overwritten only after everyone has read them
-        epi_bar_sync();
+        __syncwarp();
       }
       // this warp is done reading the accumulator stage: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { if (CG == 1) mbar_arrive(smem_u32(&bar_tempty[as])); else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[as]), 0)); }
     }
+    if (CG == 2 && lane == 0) tma_store_wait_read<0>();   // staging fully read by the TMA engine
+  } else {
+    // ------------------------------------------------------------------ LayerNorm epilogue (warps 2..9)
+    // y = LayerNorm(acc * s + bias + residual) over the 256-wide row, eps 1e-5.  Group g = (warp - 2) / 4
+    // drains the accumulator stages of tiles it = g, g + 2, ...; a thread owns the whole row: statistics
+    // in one pass with the row's first value as the shift (var = E[(x-K)^2] - E[x-K]^2 does not cancel),
+    // the pre-norm row parked in TMEM between the two passes.
+    const int q = warp & 3;
+    const int g = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    constexpr int NCH = 8;                           // 32-column chunks per row
+    uint8_t* const stg = s_stage + (warp - 2) * Cfg::STG_WARP;
+    uint32_t r[32];
+    float v[32];
+    int tbuf = 0;
+    for (int it = g; it < nlocal; it += 2) {
+      const int as = it & 1;                         // == g
+      int m0, n0;
+      decode_item(it, p, BN, CG, rank, m0, n0);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const int wrow0 = m0 + q * 32;
+      const int rows_valid = min(32, p.M - wrow0);
+      const bool has_res = p.res_hi != nullptr;      // warp-uniform
+      const __half* rbh = p.res_hi + (int64_t)wrow0 * p.ld_res;
+      const __half* rbl = p.res_lo + (int64_t)wrow0 * p.ld_res;
+      uint4 gAh[4], gAl[4], gBh[4], gBl[4];          // two residual chunks in flight (coalesced pattern)
+      if (CG == 2 && lane == 0) tma_store_wait_read<0>();   // the staging tiles double as transpose buffers
+      __syncwarp();
+      if (has_res) {
+        load_plane_issue(rbh, p.ld_res, rows_valid, lane, gAh);
+        load_plane_issue(rbl, p.ld_res, rows_valid, lane, gAl);
+        load_plane_issue(rbh + 32, p.ld_res, rows_valid, lane, gBh);
+        load_plane_issue(rbl + 32, p.ld_res, rows_valid, lane, gBl);
+      }
+      mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
+      tc_fence_after();
+      float s1 = 0.0f, s2 = 0.0f, shiftK = 0.0f;
+      const float sc = p.inv_scale;
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        uint4 rh[4], rl[4];
+        // ---- chunk c (buffers A)
+        if (has_res) {
+          if (CG == 2) planes_to_rows(stg, gAh, gAl, lane, rh, rl);
+          else { plane_to_rows(stg, gAh, lane, rh); plane_to_rows(stg, gAl, lane, rl); }
+          if (c + 2 < NCH) {
+            load_plane_issue(rbh + (c + 2) * 32, p.ld_res, rows_valid, lane, gAh);
+            load_plane_issue(rbl + (c + 2) * 32, p.ld_res, rows_valid, lane, gAl);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
+        }
+        tmem_ld32(trow + c * 32, r);
+        if (c == 0) shiftK = ln_first_x(r, rh, rl, s_bias, sc);
+        ln_stats_chunk(r, rh, rl, s_bias + c * 32, sc, shiftK, s1, s2);
+        tmem_st32(trow + c * 32, r);
+        // ---- chunk c + 1 (buffers B)
+        if (has_res) {
+          if (CG == 2) planes_to_rows(stg, gBh, gBl, lane, rh, rl);
+          else { plane_to_rows(stg, gBh, lane, rh); plane_to_rows(stg, gBl, lane, rl); }
+          if (c + 3 < NCH) {
+            load_plane_issue(rbh + (c + 3) * 32, p.ld_res, rows_valid, lane, gBh);
+            load_plane_issue(rbl + (c + 3) * 32, p.ld_res, rows_valid, lane, gBl);
+          }
+        }
+        tmem_ld32(trow + (c + 1) * 32, r);
+        ln_stats_chunk(r, rh, rl, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
+        tmem_st32(trow + (c + 1) * 32, r);
+      }
+      const float e1 = s1 * (1.0f / 256), e2 = s2 * (1.0f / 256);
+      const float rstd = rsqrtf(fmaxf(e2 - e1 * e1, 0.0f) + 1e-5f);
+      const float nb_ = -(shiftK + e1) * rstd;       // y = x * rstd + nb_
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        tmem_ld32(trow + c * 32, r);
+        ln_norm_chunk(r, v, s_gamma + c * 32, s_beta + c * 32, rstd, nb_);
+        uint32_t ph[16], pl[16];
+        pack_split(v, ph, pl);
+        if (CG == 2 && p.tma_out) {
+          stage_and_store(stg + tbuf * 4096, ph, pl, lane, &tmOh, &tmOl, c * 32, wrow0);
+          tbuf ^= 1;
+        } else {
+          const int64_t o = (int64_t)wrow0 * p.ld_out + c * 32;
+          store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
+          store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (CG == 1) mbar_arrive(smem_u32(&bar_tempty[as])); else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[as]), 0)); }
+    }
+    if (CG == 2 && lane == 0) tma_store_wait_read<0>();
   }
-  if (CG == 2 && warp >= 2 && lane == 0) tma_store_wait_read<0>();   // staging fully read by the TMA engine
   tc_fence_before();
   __syncthreads();
   if (CG > 1) cluster_sync_all();   // nobody exits while the peer may still signal its barriers / read its smem
   if (warp == 1) {
     tc_fence_after();
-    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -830,6 +621,7 @@ struct FfnParams {
   const float* b1; const float* b2; const float* gamma; const float* beta;
   const __half* res_hi; const __half* res_lo; int ld_res;
   __half* out_hi; __half* out_lo; int ld_out;
+  int tma_out;
 };
 template <int CG>
 struct FfnCfg {
@@ -857,7 +649,8 @@ template <int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
          const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW1l,
-         const __grid_constant__ CUtensorMap tmW2h, const __grid_constant__ CUtensorMap tmW2l, const FfnParams p) {
+         const __grid_constant__ CUtensorMap tmW2h, const __grid_constant__ CUtensorMap tmW2l,
+         const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl, const FfnParams p) {
   using Cfg = FfnCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -868,7 +661,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   float* s_b2 = s_b1 + MAX_N;                                 // [256]
   float* s_gamma = s_b2 + 256;
   float* s_beta = s_gamma + 256;
-  float* s_part = s_beta + 256;                               // [2][2][128]
+  float* s_part = s_beta + 256;                               // [2 halves][2 values][128 rows]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 4 * 128);
   uint64_t* bar_full = bars;                  // [STAGES] ring stage filled (TMA tx; 2-SM: the leader's)
   uint64_t* bar_empty = bars + 4;             // [STAGES] ring stage consumed (MMA commit, both CTAs)
@@ -905,15 +698,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
     tma_prefetch_desc(&tmW1l); tma_prefetch_desc(&tmW2h); tma_prefetch_desc(&tmW2l);
   }
   if (CG > 1) { __syncthreads(); cluster_sync_all(); }
-  if (warp == 1) {
-    if (CG == 1) {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    } else {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS) : "memory");
-      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-    }
-  }
+  if (warp == 1) tmem_alloc<CG>(smem_u32(tmem_slot), Cfg::TMEM_COLS);
   if (warp >= 2) {
     for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_b1[i] = (p.b1 && i < NC * Cfg::CHUNK) ? p.b1[i] : 0.0f;
     for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) {
@@ -935,53 +720,51 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   };
 
   if (warp == 0) {
-    {
-      // ---------------------------------------------------------------- TMA producer (both CTAs)
-      // whole warp walks the loop, one elected lane issues (operands stay in uniform registers)
-      int kbg = 0;
-      auto stage_begin = [&](uint32_t bytes, uint32_t& full) -> uint32_t {   // elected lane: arm the barrier
-        const int s = kbg % STAGES;
-        full = smem_u32(&bar_full[s]);
-        if (CG == 1) {
-          mbar_expect_tx(full, bytes);
-        } else {
-          if (rank == 0) mbar_expect_tx(full, 2 * bytes);  // both CTAs' boxes are counted on the leader's barrier
-          full = mapa_u32(full, 0);
-        }
-        return smem_u32(smem + s * Cfg::STAGE_BYTES);
-      };
-      auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t full, int c0, int c1) {
-        if (CG == 1) tma_load_2d(dst, map, full, c0, c1);
-        else tma_load_2d_2sm(dst, map, full, c0, c1);
-      };
-      for (int j = 0; j < nlocal; ++j) {
-        const int m0 = ((cid + j * ncl) * CG + rank) * BM;
-        for (int i = 0; i <= NC; ++i) {
-          if (i < NC) {
-            for (int kb = 0; kb < 4; ++kb, ++kbg) {
-              mbar_wait(smem_u32(&bar_empty[kbg % STAGES]), (((uint32_t)(kbg / STAGES)) & 1u) ^ 1u);
-              if (elect_one()) {
-                uint32_t full;
-                const uint32_t dst = stage_begin(Cfg::F1_BYTES, full);
-                load(dst, &tmXh, full, kb * BK, m0);
-                load(dst + 16384, &tmXl, full, kb * BK, m0);
-                load(dst + 32768, &tmW1h, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
-                load(dst + 32768 + Cfg::W1_BYTES, &tmW1l, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
-              }
-              __syncwarp();
+    // ---------------------------------------------------------------- TMA producer (both CTAs)
+    // whole warp walks the loop, one elected lane issues (operands stay in uniform registers)
+    int kbg = 0;
+    auto stage_begin = [&](uint32_t bytes, uint32_t& full) -> uint32_t {   // elected lane: arm the barrier
+      const int s = kbg % STAGES;
+      full = smem_u32(&bar_full[s]);
+      if (CG == 1) {
+        mbar_expect_tx(full, bytes);
+      } else {
+        if (rank == 0) mbar_expect_tx(full, 2 * bytes);  // both CTAs' boxes are counted on the leader's barrier
+        full = mapa_u32(full, 0);
+      }
+      return smem_u32(smem + s * Cfg::STAGE_BYTES);
+    };
+    auto load = [&](uint32_t dst, const CUtensorMap* map, uint32_t full, int c0, int c1) {
+      if (CG == 1) tma_load_2d(dst, map, full, c0, c1);
+      else tma_load_2d_2sm(dst, map, full, c0, c1);
+    };
+    for (int j = 0; j < nlocal; ++j) {
+      const int m0 = ((cid + j * ncl) * CG + rank) * BM;
+      for (int i = 0; i <= NC; ++i) {
+        if (i < NC) {
+          for (int kb = 0; kb < 4; ++kb, ++kbg) {
+            mbar_wait(smem_u32(&bar_empty[kbg % STAGES]), (((uint32_t)(kbg / STAGES)) & 1u) ^ 1u);
+            if (elect_one()) {
+              uint32_t full;
+              const uint32_t dst = stage_begin(Cfg::F1_BYTES, full);
+              load(dst, &tmXh, full, kb * BK, m0);
+              load(dst + 16384, &tmXl, full, kb * BK, m0);
+              load(dst + 32768, &tmW1h, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
+              load(dst + 32768 + Cfg::W1_BYTES, &tmW1l, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
             }
+            __syncwarp();
           }
-          if (i >= 1) {
-            for (int kb = 0; kb < 2; ++kb, ++kbg) {
-              mbar_wait(smem_u32(&bar_empty[kbg % STAGES]), (((uint32_t)(kbg / STAGES)) & 1u) ^ 1u);
-              if (elect_one()) {
-                uint32_t full;
-                const uint32_t dst = stage_begin(Cfg::F2_BYTES, full);
-                load(dst, &tmW2h, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
-                load(dst + Cfg::W2_BYTES, &tmW2l, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
-              }
-              __syncwarp();
+        }
+        if (i >= 1) {
+          for (int kb = 0; kb < 2; ++kb, ++kbg) {
+            mbar_wait(smem_u32(&bar_empty[kbg % STAGES]), (((uint32_t)(kbg / STAGES)) & 1u) ^ 1u);
+            if (elect_one()) {
+              uint32_t full;
+              const uint32_t dst = stage_begin(Cfg::F2_BYTES, full);
+              load(dst, &tmW2h, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
+              load(dst + Cfg::W2_BYTES, &tmW2l, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
             }
+            __syncwarp();
           }
         }
       }
@@ -1060,7 +843,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
     const int q = warp & 3;                          // TMEM lane quarter
     const int hf = (warp - 2) >> 2;                  // column half of a chunk / of the output row
     const int row = q * 32 + lane;
-    uint8_t* const stg = hs + (warp - 2) * 2048;     // LayerNorm staging lives in the (then idle) Hs buffer
+    uint8_t* const stg = hs + (warp - 2) * 8192;     // LayerNorm staging lives in the (then idle) Hs buffer
     uint32_t r[32];
     float v[32];
     int g = 0;                                       // hidden chunks handled so far
@@ -1093,95 +876,82 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
             *reinterpret_cast<uint4*>(hrow + sl) = make_uint4(PH[cc][4 * jj], PH[cc][4 * jj + 1], PH[cc][4 * jj + 2], PH[cc][4 * jj + 3]);
             *reinterpret_cast<uint4*>(hrow + 32768 + sl) = make_uint4(PL[cc][4 * jj], PL[cc][4 * jj + 1], PL[cc][4 * jj + 2], PL[cc][4 * jj + 3]);
           }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tcgen05.mma reads
+        fence_proxy_async_smem();                    // generic-proxy writes -> tcgen05.mma reads
         __syncwarp();
         if (lane == 0) arrive_leader(bar_hfull);
       }
-      // ---- residual + LayerNorm on acc2 (same scheme as k_gemm_tc's LN epilogue)
-      const int m = m0 + row;
-      const bool row_ok = m < p.M;
+      // ---- residual + LayerNorm on acc2.  Two warps share a row (column halves of 128): each keeps
+      // one-pass statistics shifted by ITS first value and the halves are merged with the pairwise
+      // (Chan) update through shared memory; the pre-norm row is parked in TMEM between the passes.
+      // The residual is prefetched two 32-column chunks ahead (the first two before the accumulator is awaited).
       const int wrow0 = m0 + q * 32;
       const int rows_valid = min(32, p.M - wrow0);
       const int cb = hf * 128;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * Cfg::CHUNK + cb);
       const bool has_res = p.res_hi != nullptr;
-      const float shiftK = (has_res && row_ok) ? join_f32(p.res_hi[(int64_t)m * p.ld_res], p.res_lo[(int64_t)m * p.ld_res]) : 0.0f;
       const __half* rbh = p.res_hi + (int64_t)wrow0 * p.ld_res + cb;
       const __half* rbl = p.res_lo + (int64_t)wrow0 * p.ld_res + cb;
-      uint4 gh[4], gl[4];
+      uint4 gh[2][4], gl[2][4];                      // two residual chunks in flight
       if (has_res) {
-        load_plane_issue(rbh, p.ld_res, rows_valid, lane, gh);
-        load_plane_issue(rbl, p.ld_res, rows_valid, lane, gl);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          load_plane_issue(rbh + c * 32, p.ld_res, rows_valid, lane, gh[c]);
+          load_plane_issue(rbl + c * 32, p.ld_res, rows_valid, lane, gl[c]);
+        }
       }
       mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);      // all F2 MMAs retired: acc2 complete, Hs idle
       tc_fence_after();
-      float s1 = 0.0f, s2 = 0.0f;
+      float s1 = 0.0f, s2 = 0.0f, shiftK = 0.0f;
       const float sc = p.inv_s2;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 rh[4], rl[4];
         if (has_res) {
-          plane_to_rows(stg, gh, lane, rh);
-          plane_to_rows(stg, gl, lane, rl);
-          if (c + 1 < 4) {
-            load_plane_issue(rbh + (c + 1) * 32, p.ld_res, rows_valid, lane, gh);
-            load_plane_issue(rbl + (c + 1) * 32, p.ld_res, rows_valid, lane, gl);
+          planes_to_rows(stg, gh[c & 1], gl[c & 1], lane, rh, rl);
+          if (c + 2 < 4) {
+            load_plane_issue(rbh + (c + 2) * 32, p.ld_res, rows_valid, lane, gh[c & 1]);
+            load_plane_issue(rbl + (c + 2) * 32, p.ld_res, rows_valid, lane, gl[c & 1]);
           }
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
         }
         tmem_ld32(trow + c * 32, r);
-        const float* bch = s_b2 + cb + c * 32;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint32_t ah[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
-          const uint32_t al[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
-          const float4 b0 = reinterpret_cast<const float4*>(bch)[2 * i], b1 = reinterpret_cast<const float4*>(bch)[2 * i + 1];
-          const float bia[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&ah[jj]));
-            const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&al[jj]));
-            const int e = i * 8 + jj * 2;
-            const float x0 = fmaf(__uint_as_float(r[e]), sc, bia[2 * jj]) + (hf2.x + lf2.x);
-            const float x1 = fmaf(__uint_as_float(r[e + 1]), sc, bia[2 * jj + 1]) + (hf2.y + lf2.y);
-            const float d0 = x0 - shiftK, d1 = x1 - shiftK;
-            s1 += d0 + d1;
-            s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
-            r[e] = __float_as_uint(x0);
-            r[e + 1] = __float_as_uint(x1);
-          }
-        }
+        if (c == 0) shiftK = ln_first_x(r, rh, rl, s_b2 + cb, sc);
+        ln_stats_chunk(r, rh, rl, s_b2 + cb + c * 32, sc, shiftK, s1, s2);
         tmem_st32(trow + c * 32, r);
       }
-      s_part[hf * 128 + row] = s1;
-      s_part[256 + hf * 128 + row] = s2;
+      // this half: mean_h = K + s1/128, M2_h = s2 - s1^2/128
+      const float mean_h = shiftK + s1 * (1.0f / 128), m2_h = fmaxf(s2 - s1 * s1 * (1.0f / 128), 0.0f);
+      s_part[hf * 256 + row] = mean_h;
+      s_part[hf * 256 + 128 + row] = m2_h;
       epi_bar_sync();
-      const float e1 = (s_part[row] + s_part[128 + row]) * (1.0f / 256);
-      const float e2 = (s_part[256 + row] + s_part[256 + 128 + row]) * (1.0f / 256);
-      const float mean = shiftK + e1;
-      const float rstd = rsqrtf(fmaxf(e2 - e1 * e1, 0.0f) + 1e-5f);
+      const float mean_o = s_part[(hf ^ 1) * 256 + row], m2_o = s_part[(hf ^ 1) * 256 + 128 + row];
+      const float dm = mean_h - mean_o;
+      const float mean = 0.5f * (mean_h + mean_o);
+      const float var = (m2_h + m2_o + dm * dm * 64.0f) * (1.0f / 256);
+      const float rstd = rsqrtf(var + 1e-5f);
+      const float nb_ = -mean * rstd;
+      int tbuf = 0;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         tmem_ld32(trow + c * 32, r);
-        const float4* g4 = reinterpret_cast<const float4*>(s_gamma + cb + c * 32);
-        const float4* e4 = reinterpret_cast<const float4*>(s_beta + cb + c * 32);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 gg = g4[i], bb = e4[i];
-          v[4 * i + 0] = fmaf((__uint_as_float(r[4 * i + 0]) - mean) * rstd, gg.x, bb.x);
-          v[4 * i + 1] = fmaf((__uint_as_float(r[4 * i + 1]) - mean) * rstd, gg.y, bb.y);
-          v[4 * i + 2] = fmaf((__uint_as_float(r[4 * i + 2]) - mean) * rstd, gg.z, bb.z);
-          v[4 * i + 3] = fmaf((__uint_as_float(r[4 * i + 3]) - mean) * rstd, gg.w, bb.w);
-        }
+        ln_norm_chunk(r, v, s_gamma + cb + c * 32, s_beta + cb + c * 32, rstd, nb_);
         uint32_t ph[16], pl[16];
         pack_split(v, ph, pl);
-        const int64_t o = (int64_t)wrow0 * p.ld_out + cb + c * 32;
-        store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
-        store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
+        if (p.tma_out) {
+          stage_and_store(stg + tbuf * 4096, ph, pl, lane, &tmOh, &tmOl, cb + c * 32, wrow0);
+          tbuf ^= 1;
+        } else {
+          const int64_t o = (int64_t)wrow0 * p.ld_out + cb + c * 32;
+          store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
+          store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
+        }
       }
-      epi_bar_sync();                              // s_part / the staging rows are reused by the next tile
+      // Hs (the staging) is rewritten by the next tile's E1 and s_part by its LayerNorm: the TMA engine
+      // must have read the staging and everyone must have read the partial statistics
+      if (p.tma_out && lane == 0) tma_store_wait_read<0>();
+      epi_bar_sync();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) arrive_leader(bar_a2empty);
@@ -1192,31 +962,18 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   if (CG > 1) cluster_sync_all();
   if (warp == 1) {
     tc_fence_after();
-    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+    tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
 }  // namespace
 
 // ------------------------------------------------------------------------------ host side
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                        CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                        CUtensorMapFloatOOBfill);
-
-static int g_force_bn = 0;   // MLDB_TC_BN=128: experiment knob (3-stage BN=128 tiles everywhere)
-
 struct TcCtx {
-  int ffn_2sm = 1;   // fused FFN on CTA pairs (cta_group::2); MLDB_FFN_2SM=0: one CTA per tile
-  int ffn_fused = 1; // FFN1 + GELU + FFN2 + residual + LayerNorm as one launch (MLDB_FFN_FUSED=0: off)
-  int no_tma_store = 0;   // MLDB_TC_TMA_STORE=0: 2-SM kernels keep the st.global epilogue
-  int cluster = 2;   // 2 = CTA pairs (cta_group::2 MMA, each CTA loads half of the W tile); MLDB_TC_2SM
-  int dbg = 0;
   int device = 0;
   int sm_count = 148;
-  PFN_tmapEncodeTiled encode = nullptr;
-  bool ok = true;
+  int ffn_fused = 1;          // FFN1 + GELU + FFN2 + residual + LayerNorm as one launch (option ffn_fused)
+  tc::PFN_tmapEncodeTiled encode = nullptr;
 };
 
 TcCtx* tc_create(int device) {
@@ -1230,20 +987,15 @@ TcCtx* tc_create(int device) {
     delete c;
     return nullptr;
   }
-  c->encode = (PFN_tmapEncodeTiled)fn;
-  if (const char* e = getenv("MLDB_TC_DBG")) c->dbg = atoi(e);
-  if (const char* e = getenv("MLDB_TC_BN")) g_force_bn = atoi(e);
-  if (const char* e = getenv("MLDB_FFN_FUSED")) c->ffn_fused = atoi(e);
-  if (const char* e = getenv("MLDB_FFN_2SM")) c->ffn_2sm = atoi(e);
-  if (const char* e = getenv("MLDB_TC_2SM")) c->cluster = atoi(e) ? 2 : 1;
-  if (const char* e = getenv("MLDB_TC_TMA_STORE")) c->no_tma_store = atoi(e) ? 0 : 1;
+  c->encode = (tc::PFN_tmapEncodeTiled)fn;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
   e = cudaSuccess;
   auto opt_in = [&](auto kernel, int bytes) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   };
-  opt_in(k_gemm_tc<256, 1>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1>, TileCfg<128, 1>::SMEM_BYTES);
-  opt_in(k_gemm_tc<256, 2>, TileCfg<256, 2>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2>, TileCfg<128, 2>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 1, false>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1, false>, TileCfg<128, 1>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 2, false>, TileCfg<256, 2>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2, false>, TileCfg<128, 2>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 1, true>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<256, 2, true>, TileCfg<256, 2>::SMEM_BYTES);
   opt_in(k_ffn_tc<1>, FfnCfg<1>::SMEM_BYTES); opt_in(k_ffn_tc<2>, FfnCfg<2>::SMEM_BYTES);
   if (e != cudaSuccess) {
     mldb_set_err(std::string("cudaFuncSetAttribute(k_gemm_tc): ") + cudaGetErrorString(e));
@@ -1280,10 +1032,10 @@ static bool make_map_out(const TcCtx* c, CUtensorMap* m, const __half* base, int
   return r == CUDA_SUCCESS;
 }
 
-static int pick_bn(const GemmArgs& g) { return (g.w.N % 256 == 0 && g_force_bn != 128) ? 256 : 128; }
+static int pick_bn(const GemmArgs& g) { return (g.w.N % 256 == 0) ? 256 : 128; }
 
 bool tc_gemm_supported(const TcCtx* c, const GemmArgs& g) {
-  if (!c || !c->ok) return false;
+  if (!c) return false;
   if (g.a_kind != A_SPLIT || g.M < 1 || g.w.N > MAX_N) return false;
   if (g.K1 <= 0 || g.K1 % BK || g.K2 % BK || g.a1.cols != g.K1) return false;
   if (g.K2 > 0 && g.a2.cols != g.K2) return false;
@@ -1298,99 +1050,72 @@ bool tc_gemm_ln_supported(const TcCtx* c, const GemmArgs& g, const LnArgs& l) {
   if (g.w.N != 256 || l.d != 256 || g.act != ACT_NONE) return false;
   if (l.in_group != 0 || l.c != nullptr || l.out_f32 != nullptr || !l.out.hi) return false;
   if (l.out.cols != 256 || (l.res.hi && l.res.cols != 256)) return false;
-  if (l.gamma2) return false;
+  if (l.gamma2 || l.rowvec) return false;
+  if (g.addtab || g.zero_lengths || g.in_group < g.M || g.out_group != 0 || g.out_off != 0) return false;
   return true;
 }
 
-static void fill_params(const TcCtx* c, const GemmArgs& g, const LnArgs* ln, int bn, TcParams* out) {
+static void fill_params(const GemmArgs& g, const LnArgs* ln, int bn, TcParams* out) {
   TcParams p{};
   p.M = g.M; p.N = g.w.N; p.kblocks = g.w.K / BK; p.kb1 = g.K1 / BK;
   p.inv_scale = g.w.inv_scale; p.bias = g.w.bias; p.addtab = g.addtab; p.act = g.act;
   p.in_group = g.in_group; p.out_group = g.out_group; p.out_off = g.out_off; p.zero_lengths = g.zero_lengths;
   if (ln) {
-    p.ln = 1;
     p.out_hi = ln->out.hi; p.out_lo = ln->out.lo(); p.ld_out = ln->out.cols; p.out_col0 = 0;
     p.res_hi = ln->res.hi; p.res_lo = ln->res.hi ? ln->res.lo() : nullptr; p.ld_res = ln->res.cols;
-    p.rowvec = ln->rowvec; p.rv_group = ln->rv_group > 0 ? ln->rv_group : 1;
-    p.gamma = ln->gamma; p.beta = ln->beta; p.gamma2 = ln->gamma2; p.beta2 = ln->beta2;
+    p.gamma = ln->gamma; p.beta = ln->beta;
   } else {
     p.out_hi = g.out.hi; p.out_lo = g.out.hi ? g.out.lo() : nullptr; p.ld_out = g.out.cols; p.out_col0 = g.out_col0;
     p.out_f32 = g.out_f32; p.ldc = g.ldc;
   }
-  p.dbg = c->dbg;
   p.m_tiles = (g.M + BM - 1) / BM;
   p.n_tiles = (g.w.N + bn - 1) / bn;
   *out = p;
 }
 
-void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
+static bool map_fail(const char* what, int M, int N, int K) {
+  char buf[160];
+  snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%s M=%d N=%d K=%d)", what, M, N, K);
+  mldb_set_err(buf);
+  return false;
+}
+
+bool tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   CUtensorMap mA1h, mA1l, mA2h, mA2l, mWh, mWl;
   const int bn = ln ? 256 : pick_bn(g);
   bool ok = make_map(c, &mA1h, g.a1.hi, g.M, g.K1, BM) && make_map(c, &mA1l, g.a1.lo(), g.M, g.K1, BM);
   if (g.K2 > 0) ok = ok && make_map(c, &mA2h, g.a2.hi, g.M, g.K2, BM) && make_map(c, &mA2l, g.a2.lo(), g.M, g.K2, BM);
   else { mA2h = mA1h; mA2l = mA1l; }
   const int m_tiles_ = (g.M + BM - 1) / BM;
-  const int cl = (c->cluster == 2 && m_tiles_ >= 4 && c->sm_count % 2 == 0) ? 2 : 1;   // small problems: no pairs
+  const int cl = (m_tiles_ >= 4 && c->sm_count % 2 == 0) ? 2 : 1;   // small problems: no pairs
   ok = ok && make_map(c, &mWh, g.w.w, g.w.N, g.w.K, bn / cl) &&
        make_map(c, &mWl, g.w.w + g.w.plane_stride, g.w.N, g.w.K, bn / cl);
-  if (!ok) {
-    fprintf(stderr, "libmldb200: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d)\n", g.M, g.w.N, g.w.K);
-    c->ok = false;
-    return;
-  }
-  TcParams p, p2{};
-  fill_params(c, g, ln, bn, &p);
+  if (!ok) return map_fail("gemm", g.M, g.w.N, g.w.K);
+  TcParams p;
+  fill_params(g, ln, bn, &p);
   CUtensorMap mOh = mA1h, mOl = mA1l;
-  if (cl == 2 && !ln && g.out.hi && !g.out_f32 && !g.addtab && !g.zero_lengths && g.in_group >= g.M &&
-      g.out_group == 0 && g.out_off == 0 && !c->no_tma_store) {
-    if (make_map_out(c, &mOh, g.out.hi + g.out_col0, g.M, g.w.N, g.out.cols) &&
-        make_map_out(c, &mOl, g.out.lo() + g.out_col0, g.M, g.w.N, g.out.cols))
-      p.tma_out = 1;
+  if (cl == 2 && ln) {
+    if (!make_map_out(c, &mOh, ln->out.hi, g.M, 256, ln->out.cols) || !make_map_out(c, &mOl, ln->out.lo(), g.M, 256, ln->out.cols))
+      return map_fail("gemm ln out", g.M, g.w.N, g.w.K);
+    p.tma_out = 1;
+  } else if (cl == 2 && g.out.hi && !g.out_f32 && !g.addtab && !g.zero_lengths && g.in_group >= g.M &&
+             g.out_group == 0 && g.out_off == 0) {
+    if (!make_map_out(c, &mOh, g.out.hi + g.out_col0, g.M, g.w.N, g.out.cols) ||
+        !make_map_out(c, &mOl, g.out.lo() + g.out_col0, g.M, g.w.N, g.out.cols))
+      return map_fail("gemm out", g.M, g.w.N, g.w.K);
+    p.tma_out = 1;
   }
-  const PairCfg pc{0, nullptr};
   const int ngroups = ((p.m_tiles + cl - 1) / cl) * p.n_tiles;
   const int ncl = ngroups < c->sm_count / cl ? ngroups : c->sm_count / cl;
   dim3 grid(ncl * cl);
-#define MLDB_LAUNCH(BN_, CL_)                                                                                   \
-  launch_pdl_cluster(k_gemm_tc<BN_, CL_>, grid, dim3(NUM_THREADS), TileCfg<BN_, CL_>::SMEM_BYTES, st, CL_, mA1h, \
-                     mA1l, mA2h, mA2l, mWh, mWl, mA1h, mA1l, mWh, mWl, mOh, mOl, p, p2, pc)
-  if (bn == 256) { if (cl == 2) MLDB_LAUNCH(256, 2); else MLDB_LAUNCH(256, 1); }
-  else           { if (cl == 2) MLDB_LAUNCH(128, 2); else MLDB_LAUNCH(128, 1); }
+#define MLDB_LAUNCH(BN_, CL_, LN_)                                                                                   \
+  launch_pdl_cluster(k_gemm_tc<BN_, CL_, LN_>, grid, dim3(NUM_THREADS), TileCfg<BN_, CL_>::SMEM_BYTES, st, CL_, mA1h, \
+                     mA1l, mA2h, mA2l, mWh, mWl, mOh, mOl, p)
+  if (ln)             { if (cl == 2) MLDB_LAUNCH(256, 2, true); else MLDB_LAUNCH(256, 1, true); }
+  else if (bn == 256) { if (cl == 2) MLDB_LAUNCH(256, 2, false); else MLDB_LAUNCH(256, 1, false); }
+  else                { if (cl == 2) MLDB_LAUNCH(128, 2, false); else MLDB_LAUNCH(128, 1, false); }
 #undef MLDB_LAUNCH
-}
-
-// Producer GEMM g1 (plain epilogue, N a multiple of 256, e.g. FFN1+GELU) and consumer GEMM g2
-// (+ residual + LayerNorm, A operand == g1's output) in ONE persistent launch (pair mode).
-bool tc_gemm_pair_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2) {
-  if (!tc_gemm_supported(c, g1) || !tc_gemm_ln_supported(c, g2, l2)) return false;
-  if (g1.w.N % 256 || g1.K2 > 0 || g2.K2 > 0 || g1.M != g2.M) return false;
-  if (!g1.out.hi || g1.out.hi != g2.a1.hi || g1.out_col0 != 0 || g1.out_f32) return false;
-  if (g1.out.rows < (g1.M < c->sm_count * BM ? ((g1.M + BM - 1) / BM) * BM : c->sm_count * BM) && g1.out.rows < g1.M) return false;
-  if (g1.addtab || g1.zero_lengths || g1.in_group < g1.M || g1.out_group != 0 || g1.out_off != 0) return false;
   return true;
-}
-
-void tc_gemm_pair(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, int* counters,
-                  cudaStream_t st) {
-  CUtensorMap mAh, mAl, mWh, mWl, mBh, mBl, mVh, mVl;
-  const int m_tiles = (g1.M + BM - 1) / BM;
-  const int grid = m_tiles < c->sm_count ? m_tiles : c->sm_count;
-  // the intermediate (g1.out == g2.a1) is used as grid x 128 scratch rows
-  bool ok = make_map(c, &mAh, g1.a1.hi, g1.M, g1.K1, BM) && make_map(c, &mAl, g1.a1.lo(), g1.M, g1.K1, BM) &&
-            make_map(c, &mWh, g1.w.w, g1.w.N, g1.w.K, 256) && make_map(c, &mWl, g1.w.w + g1.w.plane_stride, g1.w.N, g1.w.K, 256) &&
-            make_map(c, &mBh, g2.a1.hi, grid * BM, g2.K1, BM) && make_map(c, &mBl, g2.a1.lo(), grid * BM, g2.K1, BM) &&
-            make_map(c, &mVh, g2.w.w, g2.w.N, g2.w.K, 256) && make_map(c, &mVl, g2.w.w + g2.w.plane_stride, g2.w.N, g2.w.K, 256);
-  if (!ok) {
-    fprintf(stderr, "libmldb200: cuTensorMapEncodeTiled failed (pair M=%d)\n", g1.M);
-    c->ok = false;
-    return;
-  }
-  TcParams p, p2;
-  fill_params(c, g1, nullptr, 256, &p);
-  fill_params(c, g2, &l2, 256, &p2);
-  const PairCfg pc{1, counters};
-  launch_pdl(k_gemm_tc<256, 1>, dim3(grid), dim3(NUM_THREADS), TileCfg<256, 1>::SMEM_BYTES, st, mAh, mAl, mAh, mAl, mWh, mWl,
-             mBh, mBl, mVh, mVl, mAh, mAl, p, p2, pc);
 }
 
 // FFN block (linear1 + GELU + linear2 + residual + LayerNorm) as one launch, d = 256.
@@ -1406,34 +1131,35 @@ bool tc_ffn_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, co
   if (g1.K1 != 256 || g1.K2 > 0 || g2.K2 > 0 || g1.M != g2.M) return false;
   if (g1.w.N % FfnCfg<1>::CHUNK || g1.w.N > MAX_N || g1.w.N != g2.K1) return false;
   if (g1.act != ACT_GELU || g1.out_f32 || g1.addtab || g1.zero_lengths) return false;
-  if (g1.in_group < g1.M || g1.out_group != 0 || g1.out_off != 0 || l2.rowvec) return false;
+  if (g1.in_group < g1.M || g1.out_group != 0 || g1.out_off != 0) return false;
   return true;
 }
-void tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, cudaStream_t st) {
-  CUtensorMap mXh, mXl, mW1h, mW1l, mW2h, mW2l;
+bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, cudaStream_t st) {
+  CUtensorMap mXh, mXl, mW1h, mW1l, mW2h, mW2l, mOh, mOl;
   const int m_tiles = (g1.M + BM - 1) / BM;
-  const int cg = (c->ffn_2sm && m_tiles >= 2 && c->sm_count % 2 == 0) ? 2 : 1;
+  const int cg = (m_tiles >= 2 && c->sm_count % 2 == 0) ? 2 : 1;
   const bool ok = make_map(c, &mXh, g1.a1.hi, g1.M, g1.K1, BM) && make_map(c, &mXl, g1.a1.lo(), g1.M, g1.K1, BM) &&
                   make_map(c, &mW1h, g1.w.w, g1.w.N, g1.w.K, FfnCfg<1>::CHUNK / cg) &&
                   make_map(c, &mW1l, g1.w.w + g1.w.plane_stride, g1.w.N, g1.w.K, FfnCfg<1>::CHUNK / cg) &&
                   make_map(c, &mW2h, g2.w.w, g2.w.N, g2.w.K, 256 / cg) &&
-                  make_map(c, &mW2l, g2.w.w + g2.w.plane_stride, g2.w.N, g2.w.K, 256 / cg);
-  if (!ok) {
-    fprintf(stderr, "libmldb200: cuTensorMapEncodeTiled failed (ffn M=%d)\n", g1.M);
-    c->ok = false;
-    return;
-  }
+                  make_map(c, &mW2l, g2.w.w + g2.w.plane_stride, g2.w.N, g2.w.K, 256 / cg) &&
+                  make_map_out(c, &mOh, l2.out.hi, g1.M, 256, l2.out.cols) &&
+                  make_map_out(c, &mOl, l2.out.lo(), g1.M, 256, l2.out.cols);
+  if (!ok) return map_fail("ffn", g1.M, g1.w.N, g1.w.K);
   FfnParams p{};
   p.M = g1.M; p.m_tiles = m_tiles; p.n_chunks = g1.w.N / FfnCfg<1>::CHUNK;
   p.inv_s1 = g1.w.inv_scale; p.inv_s2 = g2.w.inv_scale;
   p.b1 = g1.w.bias; p.b2 = g2.w.bias; p.gamma = l2.gamma; p.beta = l2.beta;
   p.res_hi = l2.res.hi; p.res_lo = l2.res.hi ? l2.res.lo() : nullptr; p.ld_res = l2.res.cols;
   p.out_hi = l2.out.hi; p.out_lo = l2.out.lo(); p.ld_out = l2.out.cols;
+  p.tma_out = 1;
   const int groups = (m_tiles + cg - 1) / cg;
   const int ncl = groups < c->sm_count / cg ? groups : c->sm_count / cg;
   if (cg == 2)
     launch_pdl_cluster(k_ffn_tc<2>, dim3(ncl * 2), dim3(NUM_THREADS), FfnCfg<2>::SMEM_BYTES, st, 2, mXh, mXl, mW1h, mW1l,
-                       mW2h, mW2l, p);
+                       mW2h, mW2l, mOh, mOl, p);
   else
-    launch_pdl(k_ffn_tc<1>, dim3(ncl), dim3(NUM_THREADS), FfnCfg<1>::SMEM_BYTES, st, mXh, mXl, mW1h, mW1l, mW2h, mW2l, p);
+    launch_pdl(k_ffn_tc<1>, dim3(ncl), dim3(NUM_THREADS), FfnCfg<1>::SMEM_BYTES, st, mXh, mXl, mW1h, mW1l, mW2h, mW2l,
+               mOh, mOl, p);
+  return true;
 }

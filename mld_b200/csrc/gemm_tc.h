@@ -7,14 +7,12 @@ TcCtx* tc_create(int device);
 void tc_destroy(TcCtx* c);
 // can this GEMM run on the tensor-core kernel (shape / alignment constraints)?
 bool tc_gemm_supported(const TcCtx* c, const GemmArgs& g);
-// ... with the residual + LayerNorm epilogue fused (the tile must cover a full row)?
+// ... with the residual + LayerNorm epilogue fused (the tile must cover a full 256-wide row)?
 bool tc_gemm_ln_supported(const TcCtx* c, const GemmArgs& g, const LnArgs& l);
-// enqueue; ln == nullptr for the plain epilogue
-void tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st);
-// producer GEMM + consumer GEMM(+LN) as one persistent launch; counters: int[m_tiles], zeroed once
-bool tc_gemm_pair_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2);
-void tc_gemm_pair(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, int* counters, cudaStream_t st);
+// enqueue; ln == nullptr for the plain epilogue.  false: tensor-map encoding failed, nothing was
+// launched and mldb_last_error() says why.
+bool tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st);
 // FFN block linear1 + GELU + linear2 + residual + LayerNorm as one launch (hidden stays on the SM)
 bool tc_ffn_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2);
-void tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, cudaStream_t st);
+bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, cudaStream_t st);
 int tc_set_ffn_fused(TcCtx* c, int on);   // returns the previous setting

@@ -71,10 +71,10 @@ void simt_attention(const AttnArgs& a, cudaStream_t st);
 bool mma_attention_supported(const AttnArgs& a);
 void mma_attention_init();
 void mma_attention(const AttnArgs& a, cudaStream_t st);
-// attn_tc.cu: tcgen05 attention core (EXPERIMENTAL, not yet validated on hardware; engine option attn_tc)
-bool tc_attention_init(int device);
+// attn_tc.cu: tcgen05 attention core (Lq, Lk <= 256, head_dim 64 / 128)
+bool tc_attention_init(int device);                       // once per process, outside stream capture
 bool tc_attention_supported(const AttnArgs& a);
-void tc_attention(const AttnArgs& a, cudaStream_t st);
+bool tc_attention(const AttnArgs& a, cudaStream_t st);    // false: tensor-map encoding failed, nothing launched
 void simt_init();
 // --- tcgen05 implementations (gemm_tc.cu) ---
 struct TcCtx;

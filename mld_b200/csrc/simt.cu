@@ -19,6 +19,7 @@ __device__ __forceinline__ float load_a(const GemmArgs& a, int m, int k) {
     int64_t o = (int64_t)m * a.a2.cols + (k - a.K1);
     return join_f32(a.a2.hi[o], a.a2.lo()[o]);
   }
+  if (k >= a.lda) return 0.0f;               // weights packed with a zero-padded K (odd feature counts)
   float v = a.a_f32[(int64_t)m * a.lda + k];
   return a.a_kind == A_F32_RELU ? fmaxf(v, 0.0f) : v;
 }

@@ -57,3 +57,20 @@ def sample_sharded(run_local: Callable[[torch.Tensor, torch.Tensor, Sequence[int
     if world * cmax == B:
         return out
     return torch.cat([out[r * cmax: r * cmax + (c[1] - c[0])] for r, c in enumerate(counts)], 0)
+
+
+def sample_sharded_engine(engine, cond: torch.Tensor, init_noise: torch.Tensor, lengths: Sequence[int],
+                          group=None) -> torch.Tensor:
+    """The product multi-GPU path: this rank's contiguous shard of the GLOBAL batch through
+    ``Engine.sample_gather`` (C ABI: k_feats2joints writes into this rank's slot of the gathered buffer, one
+    in-place ncclAllGather on a side stream).  The engine must have a communicator (``engine.comm_init``).
+    Returns joints ``[B, T_max, J, 3]`` identical on every rank and bit-identical to a single-GPU run on the
+    whole batch.  The batch must split evenly (the reference's loaders drop the last partial batch)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B = init_noise.shape[0]
+    if B % world:
+        raise ValueError(f"batch {B} does not split evenly over {world} ranks; use sample_sharded for ragged splits")
+    lo, hi = shard_range(B, rank, world)
+    return engine.sample_gather(shard_cfg_condition(cond, B, lo, hi, engine.cfg_on), init_noise[lo:hi],
+                                list(lengths[lo:hi]), T=int(max(lengths)))

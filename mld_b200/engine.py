@@ -72,6 +72,18 @@ class Engine:
         check(self.lib.mldb_profile_op(self._h, op.encode(), B, S_ctx, iters, C.byref(ms)), "mldb_profile_op")
         return float(ms.value)
 
+    def profile_steps(self, cond: torch.Tensor, init_noise: torch.Tensor):
+        """Device time (ms) of every scheduler step of the reverse loop, launched eagerly (mldb_profile_steps)."""
+        c, z0 = self._cond(cond), _f32c(init_noise, self.device)
+        B = z0.shape[0]
+        self._check_latent(z0, B, "init_noise")
+        self._check_cond(c, 2 * B if self.cfg_on else B)
+        S = c.shape[1] if c.dim() == 3 else 1
+        n = 0 if self.timesteps is None else len(self.timesteps)
+        ms = (C.c_float * n)()
+        check(self.lib.mldb_profile_steps(self._h, _ptr(c), _ptr(z0), B, S, ms), "mldb_profile_steps")
+        return [float(v) for v in ms]
+
     def debug_gemm(self, A, W, bias=None, gamma=None, beta=None, R=None, K1=0, act=0, use_tc=True, split_out=False):
         """Kernel unit-test hook (mldb_debug_gemm): A [M,K] (device), W [N,K] / bias / gamma / beta (host)."""
         A = _f32c(A, self.device)
@@ -98,16 +110,30 @@ class Engine:
                                       self._stream()), "mldb_debug_ffn")
         return out
 
-    def debug_attention(self, qkv, nseq, L, heads, lengths=None, mode=1):
-        """Kernel unit-test hook (mldb_debug_attention): qkv [nseq*L, 3*heads*hd] (device), mode 0 CUDA-core,
-        1 mma.sync (product), 2 tcgen05 (experimental).  Returns [nseq*L, heads*hd]."""
-        qkv = _f32c(qkv, self.device)
-        d = qkv.shape[1] // 3
+    def debug_attention(self, q, nseq, Lq, heads, lengths=None, mode=2, kv=None, Lk=None, kv_prefix=0):
+        """Kernel unit-test hook (mldb_debug_attention).  ``kv is None``: ``q`` is a packed qkv
+        [nseq*Lq, 3*heads*hd] tensor (self-attention, the layout the stacks use); else ``q`` [nseq*Lq, d] and
+        ``kv`` [nseq*Lk, 2*d] (cross-attention).  mode 0 CUDA-core, 1 mma.sync, 2 tcgen05 (product).
+        Returns [nseq*Lq, heads*hd]."""
+        q = _f32c(q, self.device)
+        kvd = None if kv is None else _f32c(kv, self.device)
+        d = q.shape[1] // 3 if kv is None else q.shape[1]
+        Lk = Lq if Lk is None else Lk
+        if q.shape[0] != nseq * Lq or (kvd is not None and tuple(kvd.shape) != (nseq * Lk, 2 * d)):
+            raise ValueError("debug_attention: shape mismatch")
         ln = None if lengths is None else torch.as_tensor(lengths, dtype=torch.int32, device=self.device).contiguous()
-        out = torch.empty((nseq * L, d), dtype=torch.float32, device=self.device)
-        check(self.lib.mldb_debug_attention(self._h, _ptr(qkv), _ptr(ln), nseq, L, heads, d // heads, int(mode), _ptr(out),
-                                            self._stream()), "mldb_debug_attention")
+        out = torch.empty((nseq * Lq, d), dtype=torch.float32, device=self.device)
+        check(self.lib.mldb_debug_attention(self._h, _ptr(q), _ptr(kvd), _ptr(ln), int(kv_prefix), nseq, Lq, Lk, heads,
+                                            d // heads, int(mode), _ptr(out), self._stream()), "mldb_debug_attention")
         return out
+
+    def kernel_stats(self, reset: bool = False) -> Dict[str, int]:
+        """Which kernel each operator was enqueued on since the last reset (mldb_kernel_stats)."""
+        arr = (C.c_int64 * len(_lib.KSTAT_NAMES))()
+        check(self.lib.mldb_kernel_stats(self._h, arr, len(_lib.KSTAT_NAMES)), "mldb_kernel_stats")
+        if reset:
+            check(self.lib.mldb_reset_kernel_stats(self._h), "mldb_reset_kernel_stats")
+        return {k: int(v) for k, v in zip(_lib.KSTAT_NAMES, arr)}
 
     @property
     def launch_count(self) -> int:
@@ -132,6 +158,36 @@ class Engine:
                                            sa.numel(), _ptr(out), self._stream()), "mldb_scheduler_step")
         return out
 
+    # ------------------------------------------------------------------ argument checks
+    # The C ABI takes raw pointers: a wrong shape would be a silent out-of-bounds access on the device.
+    @property
+    def cfg_on(self) -> bool:
+        return self.cfg.guidance_scale > 1.0
+
+    def _check_cond(self, c: torch.Tensor, Bx: int):
+        if self.cfg.cond_kind == _lib.COND_TEXT:
+            if c.dim() != 3 or c.shape[0] != Bx or c.shape[2] != self.cfg.text_dim or c.shape[1] < 1:
+                raise ValueError(f"condition must be [{Bx}, S, {self.cfg.text_dim}] (uncond half first when guidance "
+                                 f"is on), got {tuple(c.shape)}")
+        elif c.numel() != Bx:
+            raise ValueError(f"action condition must hold {Bx} class ids ([{Bx}, 1]), got {tuple(c.shape)}")
+
+    def _check_latent(self, x: torch.Tensor, rows: int, what: str):
+        cfg = self.cfg
+        want = (rows, x.shape[1], cfg.nfeats) if cfg.diffusion_only else (rows, cfg.n_lat, cfg.latent_dim)
+        if x.dim() != 3 or tuple(x.shape) != want:
+            raise ValueError(f"{what} must be {list(want)}, got {tuple(x.shape)}")
+
+    def _check_lengths(self, ln: Optional[torch.Tensor], B: int, T: Optional[int] = None):
+        if ln is None:
+            return
+        if ln.numel() != B:
+            raise ValueError(f"lengths must have {B} entries, got {ln.numel()}")
+        if T is not None and not isinstance(T, bool):
+            host = ln if ln.device.type == "cpu" else None
+            if host is not None and (int(host.max()) > T or int(host.min()) < 1):
+                raise ValueError(f"lengths must lie in [1, {T}]")
+
     # ------------------------------------------------------------------ denoiser
     def _cond(self, cond: torch.Tensor) -> torch.Tensor:
         if self.cfg.cond_kind == _lib.COND_TEXT:
@@ -150,6 +206,9 @@ class Engine:
         x, c = _f32c(sample, self.device), self._cond(cond)
         ln = self._lengths(lengths)
         Bx = x.shape[0]
+        self._check_latent(x, Bx, "sample")
+        self._check_cond(c, Bx)
+        self._check_lengths(ln, Bx)
         S = c.shape[1] if c.dim() == 3 else 1
         T = x.shape[1] if self.cfg.diffusion_only else 0
         out = torch.empty_like(x)
@@ -162,10 +221,17 @@ class Engine:
         c, z0 = self._cond(cond), _f32c(init_noise, self.device)
         ln = self._lengths(lengths)
         B = z0.shape[0]
+        self._check_latent(z0, B, "init_noise")
+        self._check_cond(c, 2 * B if self.cfg_on else B)
+        self._check_lengths(ln, B)
         S = c.shape[1] if c.dim() == 3 else 1
         T = z0.shape[1] if self.cfg.diffusion_only else 0
         out = torch.empty((z0.shape[1], B, z0.shape[2]), dtype=torch.float32, device=self.device)
         sn = None if step_noise is None else _f32c(step_noise, self.device)
+        if sn is not None:
+            n_steps = 0 if self.timesteps is None else len(self.timesteps)
+            if tuple(sn.shape) != (n_steps, *z0.shape):
+                raise ValueError(f"step_noise must be [{n_steps}, {', '.join(map(str, z0.shape))}], got {tuple(sn.shape)}")
         check(self.lib.mldb_diffusion_reverse(self._h, _ptr(c), _ptr(z0), _ptr(sn), _ptr(ln), B, S, T,
                                               _ptr(out), self._stream()), "mldb_diffusion_reverse")
         return out
@@ -174,7 +240,10 @@ class Engine:
     def vae_decode(self, z: torch.Tensor, lengths) -> torch.Tensor:
         zz = _f32c(z, self.device)
         ln = self._lengths(lengths)
+        if zz.dim() != 3 or zz.shape[0] != self.cfg.n_lat or zz.shape[2] != self.cfg.latent_dim:
+            raise ValueError(f"z must be [{self.cfg.n_lat}, B, {self.cfg.latent_dim}], got {tuple(zz.shape)}")
         B = zz.shape[1]
+        self._check_lengths(ln, B)
         T = int(max(lengths)) if not isinstance(lengths, torch.Tensor) else int(lengths.max())
         out = torch.empty((B, T, self.cfg.vae_nfeats), dtype=torch.float32, device=self.device)
         check(self.lib.mldb_vae_decode(self._h, _ptr(zz), _ptr(ln), B, T, _ptr(out), self._stream()),
@@ -184,7 +253,10 @@ class Engine:
     def vae_encode(self, feats: torch.Tensor, lengths):
         f = _f32c(feats, self.device)
         ln = self._lengths(lengths)
+        if f.dim() != 3 or f.shape[2] != self.cfg.vae_nfeats:
+            raise ValueError(f"feats must be [B, T, {self.cfg.vae_nfeats}], got {tuple(f.shape)}")
         B, T = f.shape[0], f.shape[1]
+        self._check_lengths(ln, B)
         shape = (self.cfg.n_lat, B, self.cfg.latent_dim)
         mu = torch.empty(shape, dtype=torch.float32, device=self.device)
         logvar = torch.empty(shape, dtype=torch.float32, device=self.device)
@@ -194,6 +266,9 @@ class Engine:
 
     def feats2joints(self, feats: torch.Tensor) -> torch.Tensor:
         f = _f32c(feats, self.device)
+        F = self.cfg.vae_nfeats if self.cfg.vae_kind != _lib.VAE_NONE else self.cfg.nfeats
+        if f.dim() != 3 or f.shape[2] != F:
+            raise ValueError(f"feats must be [B, T, {F}], got {tuple(f.shape)}")
         B, T = f.shape[0], f.shape[1]
         out = torch.empty((B, T, self.cfg.njoints, 3), dtype=torch.float32, device=self.device)
         check(self.lib.mldb_feats2joints(self._h, _ptr(f), B, T, _ptr(out), self._stream()),
@@ -207,8 +282,13 @@ class Engine:
         c, z0 = self._cond(cond), _f32c(init_noise, self.device)
         ln = self._lengths(lengths)
         B = z0.shape[0]
+        self._check_latent(z0, B, "init_noise")
+        self._check_cond(c, 2 * B if self.cfg_on else B)
+        self._check_lengths(ln, B)
         S = c.shape[1] if c.dim() == 3 else 1
         T = int(max(lengths)) if not isinstance(lengths, torch.Tensor) else int(lengths.max())
+        if T < 1 or int(min(lengths)) < 1:
+            raise ValueError("lengths must be >= 1")
         cfg = self.cfg
         out = {}
         lat = fe = jo = None
@@ -222,13 +302,81 @@ class Engine:
                                    _ptr(jo), self._stream()), "mldb_sample")
         return out
 
+    # ------------------------------------------------------------------ multi-GPU (one process per GPU)
+    def comm_init(self, group=None):
+        """Build the handle's NCCL communicator over the ranks of ``group`` (default: the world): rank 0 of
+        the group draws the unique id inside the library, torch.distributed only ships its 128 bytes."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        uid = (C.c_ubyte * 128)()
+        if rank == 0:
+            check(self.lib.mldb_comm_unique_id(uid), "mldb_comm_unique_id")
+        box = [bytes(uid)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        buf = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        check(self.lib.mldb_comm_init(self._h, buf, world, rank), "mldb_comm_init")
+        return world, rank
+
+    def comm_info(self):
+        n, r = C.c_int32(), C.c_int32()
+        check(self.lib.mldb_comm_info(self._h, C.byref(n), C.byref(r)), "mldb_comm_info")
+        return int(n.value), int(r.value)
+
+    def allgather(self, local: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """ncclAllGather through the C ABI on the current stream: [n, ...] per rank -> [world * n, ...]."""
+        world, _ = self.comm_info()
+        x = _f32c(local, self.device)
+        if out is None:
+            out = torch.empty((world * x.shape[0], *x.shape[1:]), dtype=torch.float32, device=self.device)
+        check(self.lib.mldb_allgather(self._h, _ptr(x), _ptr(out), x.numel(), self._stream()), "mldb_allgather")
+        return out
+
+    def sample_gather(self, cond: torch.Tensor, init_noise: torch.Tensor, lengths, T: Optional[int] = None,
+                      out: Optional[torch.Tensor] = None, wait: bool = True) -> torch.Tensor:
+        """This rank's shard through ``mldb_sample_gather``: joints of ALL ranks ``[world * B, T, J, 3]``.
+        ``T`` must be the same on every rank (pad to the global max length).  ``wait=False`` leaves the gather
+        running on the side stream (call :meth:`gather_wait` before reading ``out``; alternate two ``out``
+        buffers between consecutive calls)."""
+        c, z0 = self._cond(cond), _f32c(init_noise, self.device)
+        ln = self._lengths(lengths)
+        B = z0.shape[0]
+        self._check_latent(z0, B, "init_noise")
+        self._check_cond(c, 2 * B if self.cfg_on else B)
+        self._check_lengths(ln, B)
+        S = c.shape[1] if c.dim() == 3 else 1
+        if T is None:
+            T = int(max(lengths)) if not isinstance(lengths, torch.Tensor) else int(lengths.max())
+        world, _ = self.comm_info()
+        shape = (world * B, T, self.cfg.njoints, 3)
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float32, device=self.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError(f"out must be a contiguous float32 {list(shape)} tensor")
+        check(self.lib.mldb_sample_gather(self._h, _ptr(c), _ptr(z0), _ptr(ln), B, S, T, _ptr(out), self._stream()),
+              "mldb_sample_gather")
+        if wait:
+            self.gather_wait()
+        return out
+
+    def gather_wait(self):
+        check(self.lib.mldb_gather_wait(self._h, self._stream()), "mldb_gather_wait")
+
     def sample_host(self, cond_cpu: torch.Tensor, noise_cpu: torch.Tensor, lengths_cpu: torch.Tensor,
                     joints_cpu: torch.Tensor, T: int):
         """End-to-end through HOST buffers (pinned recommended); asynchronous on the current
         stream - synchronise before reading ``joints_cpu``."""
         B = noise_cpu.shape[0]
         S = cond_cpu.shape[1] if cond_cpu.dim() == 3 else 1
-        assert lengths_cpu.dtype == torch.int32 and joints_cpu.dtype == torch.float32
+        for t, dt in ((cond_cpu, torch.float32 if self.cfg.cond_kind == _lib.COND_TEXT else torch.int64),
+                      (noise_cpu, torch.float32), (lengths_cpu, torch.int32), (joints_cpu, torch.float32)):
+            if t.device.type != "cpu" or t.dtype != dt or not t.is_contiguous():
+                raise ValueError("sample_host takes contiguous HOST tensors (cond f32/int64, noise f32, lengths int32, joints f32)")
+        self._check_latent(noise_cpu, B, "init_noise")
+        self._check_cond(cond_cpu, 2 * B if self.cfg_on else B)
+        self._check_lengths(lengths_cpu, B, T)
+        world, _ = self.comm_info()
+        if joints_cpu.numel() != world * B * T * self.cfg.njoints * 3:
+            raise ValueError(f"joints buffer must hold [{world * B}, {T}, {self.cfg.njoints}, 3] floats")
         check(self.lib.mldb_sample_host(self._h, _ptr(cond_cpu), _ptr(noise_cpu), _ptr(lengths_cpu), B, S, T,
                                         _ptr(joints_cpu), self._stream()), "mldb_sample_host")
         return joints_cpu

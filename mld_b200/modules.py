@@ -39,18 +39,18 @@ class _EngineModule(nn.Module):
     def __init__(self):
         super().__init__()
         self._engine: Optional[Engine] = None
-        self._engine_version = -1
-        self._version = 0
+        self._engine_epoch = -1
+        self._weights_epoch = 0
 
     def _make_config(self):
         raise NotImplementedError
 
     def _load_from_state_dict(self, *args, **kwargs):   # weights changed -> rebuild engine
-        self._version += 1
+        self._weights_epoch += 1
         return super()._load_from_state_dict(*args, **kwargs)
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        self._version += 1
+        self._weights_epoch += 1
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def engine(self) -> Engine:
@@ -58,11 +58,11 @@ class _EngineModule(nn.Module):
         if dev.type != "cuda":
             raise RuntimeError(f"{type(self).__name__} runs on a B200 only: move it with .cuda() "
                                "(no CPU/PyTorch fallback exists)")
-        if self._engine is None or self._engine_version != self._version or self._engine.device != dev:
+        if self._engine is None or self._engine_epoch != self._weights_epoch or self._engine.device != dev:
             eng = Engine(self._make_config(), dev)
             eng.load_state_dict(self.state_dict(), self._prefix)
             eng.finalize()
-            self._engine, self._engine_version = eng, self._version
+            self._engine, self._engine_epoch = eng, self._weights_epoch
         return self._engine
 
 

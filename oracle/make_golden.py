@@ -52,7 +52,70 @@ def build_text_denoiser(MldDenoiser, sd):
     return m.eval()
 
 
+def golden_nlat2():
+    """latent_dim = [2, 256] (two latent tokens): denoiser forward, MldVae decode (2 memory tokens: the
+    cross-attention is a real softmax, not the 1-token collapse) and encode (4 distribution tokens)."""
+    from mld_b200 import synth
+    from oracle import mld_oracle as O
+    MldDenoiser, MldVae, _, _ = _ref_modules()
+    torch.set_grad_enabled(False)
+    dsd = synth.denoiser_state_dict(seed=5678)
+    den = MldDenoiser(ablation=abl(), nfeats=263, condition="text", latent_dim=[2, 256], ff_size=1024,
+                      num_layers=9, num_heads=4, arch="trans_enc", text_encoded_dim=768)
+    den.load_state_dict(dsd, strict=True)
+    den.eval()
+    ctx = synth.text_context(2, 77, seed=111)
+    x = synth.init_noise(2, n_lat=2, seed=112).repeat(2, 1, 1)
+    y = den(sample=x, timestep=torch.tensor(501), encoder_hidden_states=ctx, lengths=[196, 100] * 2)[0]
+    yo = O.denoiser_forward(dsd, O.DenoiserCfg(n_lat=2), x, torch.tensor(501), ctx, [196, 100] * 2)
+    print(f"n_lat=2 denoiser: oracle-vs-ref max abs {float((y - yo).abs().max()):.3e}")
+    vsd = synth.mld_vae_state_dict(seed=8765, n_lat=2)
+    vae = MldVae(ablation=abl(), nfeats=263, latent_dim=[2, 256], ff_size=1024, num_layers=9, num_heads=4,
+                 dropout=0.1, arch="encoder_decoder", normalize_before=False, activation="gelu",
+                 position_embedding="learned")
+    vae.load_state_dict(vsd, strict=True)
+    vae.eval()
+    lengths = [196, 120, 8]
+    z = synth.init_noise(3, n_lat=2, seed=141).permute(1, 0, 2).contiguous()      # [2, B, 256]
+    feats = vae.decode(z, lengths)
+    fo = O.vae_decode(vsd, O.VaeCfg(n_lat=2), z, lengths)
+    print(f"n_lat=2 vae decode: oracle-vs-ref max abs {float((feats - fo).abs().max()):.3e}")
+    g = torch.Generator().manual_seed(142)
+    motion = torch.randn(3, 196, 263, generator=g)
+    _, dist = vae.encode(motion, lengths)
+    mo, lvo = O.vae_encode(vsd, O.VaeCfg(n_lat=2), motion, lengths)
+    print(f"n_lat=2 vae encode: oracle-vs-ref mu {float((dist.loc - mo).abs().max()):.3e}")
+    np.savez(os.path.join(OUT, "nlat2.npz"), y=y.numpy(), feats=feats.numpy(), mu=dist.loc.numpy(),
+             std=dist.scale.numpy())
+
+
+def golden_novae196():
+    """The no-VAE denoiser at its BASELINE shape: 196 frames x 263 features, d = 512 (head 128), ragged lengths."""
+    from mld_b200 import synth
+    from oracle import mld_oracle as O
+    MldDenoiser, _, _, _ = _ref_modules()
+    torch.set_grad_enabled(False)
+    nsd = synth.denoiser_state_dict(seed=3456, arch="trans_dec", d=512, diffusion_only=True)
+    nden = MldDenoiser(ablation=abl("no"), nfeats=263, condition="text", latent_dim=[1, 512], ff_size=1024,
+                       num_layers=9, num_heads=4, arch="trans_dec", text_encoded_dim=768)
+    nden.load_state_dict(nsd, strict=True)
+    nden.eval()
+    lengths = [196, 132]
+    g = torch.Generator().manual_seed(231)
+    x = torch.randn(2, 196, 263, generator=g).repeat(2, 1, 1)
+    ctx = synth.text_context(2, 1, seed=232)
+    y = nden(sample=x, timestep=torch.tensor(777), encoder_hidden_states=ctx, lengths=lengths * 2)[0]
+    ncfg = O.DenoiserCfg(arch="trans_dec", latent_dim=512, diffusion_only=True)
+    yo = O.denoiser_forward(nsd, ncfg, x, torch.tensor(777), ctx, lengths * 2)
+    print(f"denoiser no-VAE T=196: oracle-vs-ref max abs {float((y - yo).abs().max()):.3e}")
+    np.savez(os.path.join(OUT, "denoiser_novae_T196.npz"), y=y.numpy())
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "nlat2":
+        return golden_nlat2()
+    if len(sys.argv) > 1 and sys.argv[1] == "novae196":
+        return golden_novae196()
     from mld_b200 import synth
     from oracle import mld_oracle as O
     MldDenoiser, MldVae, ActorVae, recover_from_ric = _ref_modules()
@@ -179,6 +242,8 @@ def main():
               f"(|z|max {float(z.abs().max()):.3f})")
         np.savez(os.path.join(OUT, f"loop_S{S}.npz"), latents=np.stack(lat_trace),
                  feats=feats.numpy(), joints=joints.numpy())
+    golden_nlat2()
+    golden_novae196()
     print("golden written to", OUT)
 
 

@@ -21,7 +21,7 @@ def _fake_sampler(cond, noise, lengths):
     return out
 
 
-def _worker(rank, world, port, B, q):
+def _worker(rank, world, port, B, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = torch.Generator().manual_seed(0)
@@ -30,20 +30,29 @@ def _worker(rank, world, port, B, q):
     lengths = (torch.randint(3, 12, (B,), generator=g)).tolist()
     out = sample_sharded(_fake_sampler, cond, noise, lengths, cfg_on=True)
     if rank == 0:
-        q.put(out)
+        torch.save(out, out_path)          # a file, not a queue: nothing to drain while a rank exits
+    dist.barrier()
     dist.destroy_process_group()
 
 
-def _run(B, port):
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run(B, tmp_path):
     ctx = mp.get_context("spawn")
-    q = ctx.SimpleQueue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, q)) for r in range(2)]
+    out_path = str(tmp_path / "gathered.pt")
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, out_path)) for r in range(2)]
     for p in procs:
         p.start()
-    out = q.get()
     for p in procs:
-        p.join(60)
+        p.join(120)
         assert p.exitcode == 0
+    out = torch.load(out_path)
     g = torch.Generator().manual_seed(0)
     cond = torch.randn(2 * B, 4, 8, generator=g)
     noise = torch.randn(B, 1, 16, generator=g)
@@ -62,9 +71,9 @@ def test_shard_ranges_cover_batch():
     assert shard_cfg_condition(c, 4, 1, 3, True).flatten().tolist() == [1, 2, 5, 6]
 
 
-def test_two_rank_gather_even():
-    _run(8, 29511)
+def test_two_rank_gather_even(tmp_path):
+    _run(8, tmp_path)
 
 
-def test_two_rank_gather_uneven():
-    _run(7, 29512)
+def test_two_rank_gather_uneven(tmp_path):
+    _run(7, tmp_path)

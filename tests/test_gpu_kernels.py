@@ -1,8 +1,6 @@
 """GPU kernel unit tests (pytest -m gpu): each GEMM epilogue of the tcgen05 kernel against a
 float64 torch reference of the same op, and against the CUDA-core kernel, through the C ABI's
 debug hook.  Tolerance 5e-6 relative-to-max: the split-fp16 3-product scheme keeps ~22 bits."""
-import os
-
 import pytest
 import torch
 import torch.nn.functional as F
@@ -104,10 +102,9 @@ def test_whole_path_tc_equals_cuda_core_path(built_lib):
 
 
 def test_scheduling_options_do_not_change_results(built_lib):
-    """Engine scheduling options only reorder independent work: the fused FFN pair launch (one
-    persistent kernel running FFN1 -> FFN2 chains per CTA), the L2-sized producer/consumer chunking,
-    the sequence chunking and the number of concurrent sub-batch branches must give bit-identical
-    motions."""
+    """Engine scheduling options only reorder independent work: the number of concurrent sub-batch branches
+    and CUDA-graph replay vs eager launches must give bit-identical motions; the unfused FFN (same math, the
+    hidden activations round-trip HBM) and the other attention cores agree to fp32 re-association noise."""
     from mld_b200 import synth
     from mld_b200.engine import Engine, make_config
     eng = Engine(make_config(), 0)
@@ -119,27 +116,103 @@ def test_scheduling_options_do_not_change_results(built_lib):
     B = 300                                   # 600 sequences x 79 tokens = 371 m-tiles: > 2 waves + ragged tail
     ctx, noise = synth.text_context(B, 77, seed=15), synth.init_noise(B, seed=16)
     lengths = [196] * B
-    fused = eng.sample(ctx, noise, lengths, want=("latents",))["latents"].clone()
-    eng.set_option("ffn_fused", "0")          # the two-launch FFN: same math, hidden round-trips HBM
     base = eng.sample(ctx, noise, lengths, want=("latents",))["latents"].clone()
-    assert _rel(fused, base) < 1e-5
-    for name, value in (("branches", "1"), ("branches", "3"), ("ffn_pair", "1"), ("pair_chunk", "1"), ("chunk", "96")):
+    assert torch.isfinite(base).all()
+    for name, value, restore in (("branches", "1", "2"), ("branches", "3", "2"), ("graph", "0", "1")):
         eng.set_option(name, value)
         out = eng.sample(ctx, noise, lengths, want=("latents",))["latents"]
         assert torch.equal(out, base), f"option {name}={value} changed the result"
-        eng.set_option(name, "0")
-    # free-running per-lane chains (each lane holds the uncond + cond copies of its motions contiguously)
-    eng.set_option("branches", "3")
-    eng.set_option("lanes", "1")
+        eng.set_option(name, restore)
+    eng.set_option("ffn_fused", "0")
     out = eng.sample(ctx, noise, lengths, want=("latents",))["latents"]
-    assert torch.equal(out, base), "lanes changed the result"
+    assert _rel(out, base) < 1e-5
+    eng.set_option("ffn_fused", "1")
+    for kind in ("mma", "simt"):
+        eng.set_option("attn", kind)
+        out = eng.sample(ctx, noise, lengths, want=("latents",))["latents"]
+        assert _rel(out, base) < 1e-5, kind
+    eng.set_option("attn", "tc")
 
 
-@pytest.mark.skipif(os.environ.get("MLDB_EXPERIMENTAL") != "1",
-                    reason="attn_tc.cu has not been validated on hardware yet (set MLDB_EXPERIMENTAL=1)")
-def test_tc_attention_matches_mma(built_lib):
-    """The experimental tcgen05 attention core (option attn_tc) against the product mma.sync kernel on
-    the whole sampling path (ragged lengths exercise the key mask in the VAE decoder's fallback)."""
+def _attention_ref(q, k, v, nseq, Lq, Lk, heads, nk=None):
+    """float64 reference: q [nseq*Lq, d], k / v [nseq*Lk, d]; nk[s] valid keys of sequence s."""
+    d = q.shape[1]
+    hd = d // heads
+    qh = q.reshape(nseq, Lq, heads, hd).permute(0, 2, 1, 3).double()
+    kh = k.reshape(nseq, Lk, heads, hd).permute(0, 2, 1, 3).double()
+    vh = v.reshape(nseq, Lk, heads, hd).permute(0, 2, 1, 3).double()
+    s = qh @ kh.transpose(-1, -2) / hd ** 0.5
+    if nk is not None:
+        mask = torch.arange(Lk)[None, :] >= torch.as_tensor(nk)[:, None]
+        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    return (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(nseq * Lq, d)
+
+
+SELF_ATTN_CASES = [
+    # nseq, L, hd, masked        (heads = 4)
+    (3, 79, 64, False),          # denoiser sequence: 2 key blocks (64 + 16), two score buffers
+    (5, 79, 64, True),
+    (300, 79, 64, False),        # > 148 CTAs x several items: persistent loop, both softmax groups, ring wrap
+    (7, 3, 64, False),           # action model / pooled context: 3 tokens
+    (2, 128, 64, False),         # exactly one query tile, two full key blocks
+    (4, 33, 64, True),
+    (8, 196, 64, True),          # VAE decoder: two query tiles, 4 key blocks (208 keys), one score buffer
+    (5, 198, 64, True),          # VAE encoder: 2 distribution tokens + 196 frames
+    (3, 60, 64, True),           # ActorVae
+    (6, 196, 128, False),        # no-VAE denoiser (d = 512): two 64-wide slices of the head, one Q buffer
+    (3, 79, 128, True),
+    (2, 256, 64, False),         # the largest key count the score row fits (256 TMEM columns)
+]
+
+
+@pytest.mark.parametrize("nseq,L,hd,masked", SELF_ATTN_CASES)
+def test_self_attention_kernels(eng, nseq, L, hd, masked):
+    """The attention cores in isolation on the packed q|k|v layout of the stacks, against float64: tcgen05
+    (product), mma.sync and CUDA cores.  5e-6 relative-to-max: the split-fp16 scheme keeps ~22 bits."""
+    heads = 4
+    d = heads * hd
+    g = torch.Generator().manual_seed(nseq * 131 + L + hd)
+    qkv = torch.randn(nseq * L, 3 * d, generator=g)
+    lengths = [max(1, (7 * i + 5) % L) for i in range(nseq)] if masked else None
+    ref = _attention_ref(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], nseq, L, L, heads, lengths)
+    for mode, name in ((2, "tcgen05"), (1, "mma.sync"), (0, "cuda-core")):
+        if mode == 1 and (hd == 128 and L > 128 or L < 8):
+            continue                       # outside the mma.sync kernel's shared-memory budget / tile shape
+        y = eng.debug_attention(qkv, nseq, L, heads, lengths, mode=mode).cpu().double()
+        assert torch.isfinite(y).all(), name
+        assert _rel(y, ref) < 5e-6, name
+
+
+CROSS_ATTN_CASES = [
+    # nseq, Lq, Lk, hd, kv_prefix, masked
+    (300, 1, 79, 64, 0, False),   # trimmed last denoiser layer: one query row per sequence
+    (4, 2, 198, 64, 2, True),     # trimmed last VAE-encoder layer: 2 queries, 2 always-on tokens + masked frames
+    (5, 196, 2, 128, 0, False),   # no-VAE denoiser cross-attention: 2 memory tokens (time, text)
+    (3, 60, 1, 64, 0, False),     # one memory token
+    (2, 130, 70, 64, 0, True),
+]
+
+
+@pytest.mark.parametrize("nseq,Lq,Lk,hd,prefix,masked", CROSS_ATTN_CASES)
+def test_cross_attention_kernels(eng, nseq, Lq, Lk, hd, prefix, masked):
+    heads = 4
+    d = heads * hd
+    g = torch.Generator().manual_seed(nseq * 17 + Lq * 3 + Lk)
+    q = torch.randn(nseq * Lq, d, generator=g)
+    kv = torch.randn(nseq * Lk, 2 * d, generator=g)
+    lengths = [max(1, (11 * i + 3) % (Lk - prefix)) for i in range(nseq)] if masked else None
+    nk = None if lengths is None else [min(Lk, prefix + n) for n in lengths]
+    ref = _attention_ref(q, kv[:, :d], kv[:, d:], nseq, Lq, Lk, heads, nk)
+    for mode, name in ((2, "tcgen05"), (0, "cuda-core")):
+        y = eng.debug_attention(q, nseq, Lq, heads, lengths, mode=mode, kv=kv, Lk=Lk, kv_prefix=prefix).cpu().double()
+        assert torch.isfinite(y).all(), name
+        assert _rel(y, ref) < 5e-6, name
+
+
+def test_product_path_runs_on_tcgen05(built_lib):
+    """Kernel-choice introspection (mldb_kernel_stats): the text-to-motion path enqueues its GEMMs, FFN blocks
+    and attention on the tcgen05 kernels - no CUDA-core attention, no LayerNorm split off a GEMM - and the
+    CTA-pair variants the benchmark runs are the ones a medium batch exercises."""
     from mld_b200 import synth
     from mld_b200.engine import Engine, make_config
     eng = Engine(make_config(), 0)
@@ -147,40 +220,12 @@ def test_tc_attention_matches_mma(built_lib):
     eng.load_state_dict(synth.mld_vae_state_dict(4321), "vae.")
     eng.finalize()
     eng.set_mean_std(*synth.mean_std())
-    eng.set_timesteps(4)
-    ctx, noise = synth.text_context(5, 77, seed=25), synth.init_noise(5, seed=26)
-    lengths = [196, 64, 120, 33, 196]
-    a = eng.sample(ctx, noise, lengths, want=("latents", "joints"))
-    a = {k: v.clone() for k, v in a.items()}
-    eng.set_option("attn_tc", "1")
-    b = eng.sample(ctx, noise, lengths, want=("latents", "joints"))
-    assert torch.isfinite(b["latents"]).all()
-    assert _rel(b["latents"], a["latents"]) < 1e-4
-    assert _rel(b["joints"], a["joints"]) < 1e-4
-
-
-def _attention_ref(qkv, nseq, L, heads, lengths=None):
-    d = qkv.shape[1] // 3
-    hd = d // heads
-    q, k, v = (t.reshape(nseq, L, heads, hd).permute(0, 2, 1, 3).double() for t in qkv.split(d, dim=1))
-    s = q @ k.transpose(-1, -2) / hd ** 0.5
-    if lengths is not None:
-        mask = torch.arange(L)[None, :] >= torch.as_tensor(lengths)[:, None]
-        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
-    return (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(nseq * L, d)
-
-
-@pytest.mark.skipif(os.environ.get("MLDB_EXPERIMENTAL") != "1",
-                    reason="debug hook + attn_tc.cu not validated on hardware yet (set MLDB_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("nseq,L,masked", [(3, 79, False), (5, 79, True), (2, 128, False), (4, 33, True), (300, 79, False)])
-def test_attention_kernels_unit(eng, nseq, L, masked):
-    """Attention cores in isolation against float64: CUDA-core, mma.sync (product) and tcgen05 (experimental)."""
-    heads, hd = 4, 64
-    g = torch.Generator().manual_seed(nseq * 131 + L)
-    qkv = torch.randn(nseq * L, 3 * heads * hd, generator=g)
-    lengths = [max(1, (7 * i + 5) % L) for i in range(nseq)] if masked else None
-    ref = _attention_ref(qkv, nseq, L, heads, lengths)
-    for mode, name in ((0, "cuda-core"), (1, "mma.sync"), (2, "tcgen05")):
-        y = eng.debug_attention(qkv, nseq, L, heads, lengths, mode=mode).cpu().double()
-        assert torch.isfinite(y).all(), name
-        assert _rel(y, ref) < 5e-6, name
+    eng.set_timesteps(2)
+    ctx, noise = synth.text_context(8, 77, seed=5), synth.init_noise(8, seed=6)
+    eng.kernel_stats(reset=True)
+    eng.sample(ctx, noise, [196, 64, 120, 33, 196, 100, 7, 150], want=("joints",))
+    st = eng.kernel_stats()
+    assert st["attn_tc"] > 0 and st["ffn_tc"] > 0 and st["gemm_ln_tc"] > 0 and st["gemm_tc"] > 0
+    assert st["attn_simt"] == 0 and st["attn_mma"] == 0 and st["ln_unfused"] == 0, st
+    # CUDA-core GEMMs: only the time MLP (2 per set_timesteps) - nothing on the per-step path
+    assert st["gemm_simt"] == 0, st

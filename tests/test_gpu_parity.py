@@ -301,3 +301,105 @@ def test_action_to_motion_loop_vs_oracle(built_lib):
     assert _rel(out["latents"], zo) < 1e-3
     assert _rel(out["feats"], fo) < 1e-3
     assert float(out["feats"][4, 20:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ latent_dim = [2, 256]
+def test_two_latent_tokens_vs_reference_golden(built_lib):
+    """n_lat = 2: denoiser forward (the trimmed last layer selects two rows per sequence), MldVae decode with
+    TWO memory tokens (a real cross-attention softmax, not the one-token collapse) and encode (4 distribution
+    tokens), against the reference's own modules."""
+    from mld_b200.engine import Engine, make_config
+    g = golden("nlat2.npz")
+    dsd, vsd = synth.denoiser_state_dict(seed=5678), synth.mld_vae_state_dict(seed=8765, n_lat=2)
+    eng = Engine(make_config(latent_dim=(2, 256)), 0)
+    eng.load_state_dict(dsd, "denoiser.")
+    eng.load_state_dict(vsd, "vae.")
+    eng.finalize()
+    ctx = synth.text_context(2, 77, seed=111)
+    x = synth.init_noise(2, n_lat=2, seed=112).repeat(2, 1, 1)
+    y = eng.denoise(x, 501, ctx, [196, 100] * 2)
+    assert y.shape == (4, 2, 256)
+    assert _rel(y, g["y"]) < 2e-4
+    lengths = [196, 120, 8]
+    z = synth.init_noise(3, n_lat=2, seed=141).permute(1, 0, 2).contiguous()
+    eng.kernel_stats(reset=True)
+    feats = eng.vae_decode(z, lengths)
+    st = eng.kernel_stats()
+    assert _rel(feats, g["feats"]) < 2e-4
+    assert float(feats[2, 8:].abs().max()) == 0.0
+    assert st["attn_simt"] == 0 and st["attn_tc"] == 2 * 9, st      # self- and cross-attention of 9 layers
+    gen = torch.Generator().manual_seed(142)
+    motion = torch.randn(3, 196, 263, generator=gen)
+    mu, logvar = eng.vae_encode(motion, lengths)
+    assert mu.shape == (2, 3, 256)
+    assert _rel(mu, g["mu"]) < 2e-4
+    assert _rel(logvar.exp().pow(0.5), g["std"]) < 2e-4
+
+
+# ------------------------------------------------------------------ no-VAE model at its BASELINE shape
+def test_novae_full_shape_vs_reference_golden_and_oracle(novae):
+    """configs[4] shape: 196 frames x 263 features, d = 512 (head_dim 128), ragged lengths.  Single forward
+    against the reference module's output, then 4 guided DDPM steps with injected noise against the oracle;
+    the kernel statistics must show every attention (196 x 196 self-attention, 2-token cross-attention) on
+    the tcgen05 kernel and every stack GEMM on the tensor cores."""
+    eng, nsd = novae
+    g = golden("denoiser_novae_T196.npz")
+    lengths = [196, 132]
+    gen = torch.Generator().manual_seed(231)
+    x = torch.randn(2, 196, 263, generator=gen).repeat(2, 1, 1)
+    ctx = synth.text_context(2, 1, seed=232)
+    eng.kernel_stats(reset=True)
+    y = eng.denoise(x, 777, ctx, lengths * 2)
+    st = eng.kernel_stats()
+    assert _rel(y, g["y"]) < 2e-4
+    assert float(y[1, 132:].abs().max()) == 0.0
+    assert st["attn_tc"] == 2 * 9 and st["attn_simt"] == 0 and st["attn_mma"] == 0, st
+    assert st["gemm_tc"] >= 9 * 5, st                 # qkv, cross q / kv, FFN1 ... of 9 layers + both pose projections
+    steps = 4
+    eng.set_timesteps(steps)
+    gen = torch.Generator().manual_seed(241)
+    x0 = torch.randn(2, 196, 263, generator=gen)
+    nz = torch.randn(steps, 2, 196, 263, generator=gen)
+    z = eng.diffusion_reverse(ctx, x0, lengths, step_noise=nz)
+    cfg = O.DenoiserCfg(arch="trans_dec", latent_dim=512, diffusion_only=True)
+    zo = O.diffusion_reverse(nsd, cfg, O.DDPMScheduler(), steps, ctx, x0, lengths, step_noise=nz)
+    assert z.shape == (196, 2, 263)
+    assert _rel(z, zo) < 1e-3
+    # replaying the captured step graph a second time gives the same motion (device-side step counter reset)
+    assert torch.equal(eng.diffusion_reverse(ctx, x0, lengths, step_noise=nz), z)
+
+
+# ------------------------------------------------------------------ DDPM on the latent model
+def test_latent_ddpm_needs_and_uses_injected_noise(engines):
+    """scheduler='ddpm' with the VAE model: diffusers' DDPMScheduler.step adds variance noise at t > 0; the
+    caller injects it ([n_steps, B, n_lat, d]).  Without it the call fails instead of silently running the
+    deterministic posterior mean."""
+    from mld_b200.engine import Engine, make_config
+    eng = Engine(make_config(scheduler="ddpm", vae="none"), 0)
+    eng.load_state_dict(engines["dsd"], "denoiser.")
+    eng.finalize()
+    steps, B = 6, 3
+    eng.set_timesteps(steps)
+    ctx, noise = synth.text_context(B, 5, seed=301), synth.init_noise(B, seed=302)
+    with pytest.raises(RuntimeError, match="step_noise"):
+        eng.diffusion_reverse(ctx, noise, [196] * B)
+    gen = torch.Generator().manual_seed(303)
+    nz = torch.randn(steps, B, 1, 256, generator=gen)
+    z = eng.diffusion_reverse(ctx, noise, [196] * B, step_noise=nz)
+    zo = O.diffusion_reverse(engines["dsd"], O.DenoiserCfg(), O.DDPMScheduler(), steps, ctx, noise, [196] * B,
+                             step_noise=nz)
+    assert _rel(z, zo) < 1e-3
+
+
+def test_wrapper_rejects_bad_shapes(engines):
+    """The C ABI borrows raw pointers; the torch-side wrapper refuses shapes that would read out of bounds."""
+    eng = engines["text"]
+    ctx, noise = synth.text_context(2, 77, seed=1), synth.init_noise(2, seed=2)
+    with pytest.raises(ValueError):
+        eng.sample(ctx[2:], noise, [196, 196])               # cond without the uncond half
+    with pytest.raises(ValueError):
+        eng.sample(ctx, noise[:, :, :128], [196, 196])       # wrong latent width
+    with pytest.raises(ValueError):
+        eng.sample(ctx, noise, [196])                        # len(lengths) != B
+    with pytest.raises(ValueError):
+        eng.diffusion_reverse(ctx[:, :, :512], noise, [196, 196])

@@ -189,9 +189,12 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
     const uint32_t sP_u = smem_u32(sP);
     int rc = 0;
     auto issue_s = [&](int j) {                       // S(j) = Q K^T, block by block
-      const int qb = j % QB, sb = j % SB;
+      const int qb = j % QB, sb = j % SB, g = j & 1;
       mbar_wait(smem_u32(&q_full[qb]), ((uint32_t)(j / QB)) & 1u);
-      mbar_wait(smem_u32(&s_empty[sb]), (((uint32_t)(j / SB)) & 1u) ^ 1u);
+      // score buffer sb was last read by item j - SB, i.e. by softmax group (j - SB) & 1 as ITS item number
+      // (j - SB) >> 1.  The full / empty barriers are per GROUP (not per buffer): every waiter then sees the
+      // phases of its barrier one by one, whatever SB is (a parity wait must never lag two phases).
+      if (j >= SB) mbar_wait(smem_u32(&s_empty[(j - SB) & 1]), ((uint32_t)(j - SB) >> 1) & 1u);
       tc_fence_after();
       const uint32_t qbase = smem_u32(sQ + qb * q_bytes);
       for (int kb = 0; kb < nkb; ++kb, ++rc) {
@@ -217,7 +220,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
           }
           umma_commit(smem_u32(&r_empty[sl_i]));      // the K block may be overwritten
           if (kb == nkb - 1) {
-            umma_commit(smem_u32(&s_full[sb]));
+            umma_commit(smem_u32(&s_full[g]));
             umma_commit(smem_u32(&q_empty[qb]));      // Q only feeds the scores
           }
         }
@@ -272,6 +275,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float sc = p.scale_log2e;
     const int npad = (nkb - 1) * KBLK + p.rem;          // keys padded to 16
+    const bool fast = npad <= 80;                       // the whole score row fits in 80 registers
     for (int j = g; j < nlocal; j += 2) {
       const Item it = decode_item((int)blockIdx.x + j * (int)gridDim.x, p);
       const int sb = j % SB, ob = j & 1;
@@ -280,82 +284,157 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       int nk = p.Lk;
       if (p.lengths) nk = min(p.Lk, p.kv_prefix + p.lengths[p.len_mod > 0 ? (p.seq0 + it.s) % p.len_mod : it.s]);
       const uint32_t s_addr = tmem_base + lane_addr + (uint32_t)(sb * scols);
-      mbar_wait(smem_u32(&s_full[sb]), ((uint32_t)(j / SB)) & 1u);
+      mbar_wait(smem_u32(&s_full[g]), ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
-      // ---- pass 1: row maximum over the valid keys
-      float mx = -INFINITY;
-      if (active) {
-#pragma unroll 1
-        for (int c = 0; c < npad / 16; ++c) {
-          uint32_t r[16];
-          tmem_ld16(s_addr + (uint32_t)(c * 16), r);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c * 16 + i < nk) ? __uint_as_float(r[i]) : -INFINITY);
-        }
-      }
-      const float mc = (mx == -INFINITY) ? 0.0f : mx * sc;
-      // ---- pass 2: P = exp2(sc * s - sc * max) (unnormalised), fp32 row sum, P -> shared memory
       float sum = 0.0f;
-#pragma unroll 1
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int pseq = j * nkb + kb, pb = pseq & 1;
-        mbar_wait(smem_u32(&p_empty[pb]), (((uint32_t)pseq >> 1) & 1u) ^ 1u);    // PV(pseq - 2) has read the buffer
+      if (fast) {
+        // ---- short rows (<= 80 keys: the denoiser's 79 tokens): ONE TMEM round trip brings the whole row into
+        // registers (a tcgen05.ld + wait costs ~300 cycles, the round-1-style chunk loop paid it 10 times per
+        // item), the score buffer goes back to the MMA warp at once, max / exp2 / P run from registers
+        uint32_t s0[32], s1[32], s2[16];
         if (active) {
-          const int nch = (kb == nkb - 1 ? p.rem : KBLK) / 16;
-          // row `row` of the [128 x 64] K-major SWIZZLE_128B tile: 16-B chunk index XOR (row & 7)
-          uint8_t* const prow = sP + pb * P_BYTES + row * 128;
-#pragma unroll 1
-          for (int c = 0; c < nch; ++c) {
-            uint32_t r[16];
-            tmem_ld16(s_addr + (uint32_t)(kb * KBLK + c * 16), r);
-            uint32_t ph[8], pl[8];
-            const int k0 = kb * KBLK + c * 16;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float e0, e1;
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(r[2 * i]), sc, -mc)));
-              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(r[2 * i + 1]), sc, -mc)));
-              e0 = (k0 + 2 * i < nk) ? e0 : 0.0f;
-              e1 = (k0 + 2 * i + 1 < nk) ? e1 : 0.0f;
-              sum += e0 + e1;
-              split2(e0, e1, ph[i], pl[i]);
-            }
-            const int s0 = ((2 * c) ^ (row & 7)) << 4, s1 = ((2 * c + 1) ^ (row & 7)) << 4;
-            *reinterpret_cast<uint4*>(prow + s0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-            *reinterpret_cast<uint4*>(prow + s1) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-            *reinterpret_cast<uint4*>(prow + 16384 + s0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-            *reinterpret_cast<uint4*>(prow + 16384 + s1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-          }
-          fence_proxy_async_smem();                      // generic-proxy writes -> tcgen05.mma reads
+          tmem_ld32_nowait(s_addr, s0);
+          if (npad > 32) tmem_ld32_nowait(s_addr + 32, s1);
+          if (npad > 64) tmem_ld16_nowait(s_addr + 64, s2);
+          tmem_ld_wait();
         }
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&p_full[pb]));
+        if (lane == 0) mbar_arrive(smem_u32(&s_empty[g]));
+        float mx = -INFINITY;
+        if (active) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            mx = fmaxf(mx, (i < nk) ? __uint_as_float(s0[i]) : -INFINITY);
+            if (npad > 32) mx = fmaxf(mx, (32 + i < nk) ? __uint_as_float(s1[i]) : -INFINITY);
+            if (npad > 64 && i < 16) mx = fmaxf(mx, (64 + i < nk) ? __uint_as_float(s2[i]) : -INFINITY);
+          }
+        }
+        const float mc = (mx == -INFINITY) ? 0.0f : mx * sc;
+        // exp2 of 32 keys starting at key k0 -> two 16-key chunks (c16, c16 + 1) of P row `prow`
+        auto exp_store = [&](const uint32_t* sv, int k0, int c16, int n16, uint8_t* prow) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (h < n16) {
+              uint32_t ph[8], pl[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float e0, e1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(sv[h * 16 + 2 * i]), sc, -mc)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(sv[h * 16 + 2 * i + 1]), sc, -mc)));
+                e0 = (k0 + h * 16 + 2 * i < nk) ? e0 : 0.0f;
+                e1 = (k0 + h * 16 + 2 * i + 1 < nk) ? e1 : 0.0f;
+                sum += e0 + e1;
+                split2(e0, e1, ph[i], pl[i]);
+              }
+              const int c = c16 + h;
+              const int o0 = ((2 * c) ^ (row & 7)) << 4, o1 = ((2 * c + 1) ^ (row & 7)) << 4;
+              *reinterpret_cast<uint4*>(prow + o0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              *reinterpret_cast<uint4*>(prow + o1) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+              *reinterpret_cast<uint4*>(prow + 16384 + o0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              *reinterpret_cast<uint4*>(prow + 16384 + o1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            }
+          }
+        };
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int pseq = j * nkb + kb, pb = pseq & 1;
+          mbar_wait(smem_u32(&p_empty[pb]), (((uint32_t)pseq >> 1) & 1u) ^ 1u);    // PV(pseq - 2) has read the buffer
+          if (active) {
+            uint8_t* const prow = sP + pb * P_BYTES + row * 128;
+            const int n16 = (kb == nkb - 1 ? p.rem : KBLK) / 16;                   // 16-key chunks of this block
+            if (kb == 0) {
+              exp_store(s0, 0, 0, min(n16, 2), prow);
+              if (n16 > 2) exp_store(s1, 32, 2, n16 - 2, prow);
+            } else {
+              exp_store(s2, 64, 0, 1, prow);
+            }
+            fence_proxy_async_smem();                    // generic-proxy writes -> tcgen05.mma reads
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&p_full[pb]));
+        }
+      } else {
+        // ---- long rows (VAE: 196 / 198 frames): two exact passes over the score row in TMEM
+        float mx = -INFINITY;
+        if (active) {
+#pragma unroll 1
+          for (int c = 0; c < npad / 16; ++c) {
+            uint32_t r[16];
+            tmem_ld16(s_addr + (uint32_t)(c * 16), r);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c * 16 + i < nk) ? __uint_as_float(r[i]) : -INFINITY);
+          }
+        }
+        const float mc = (mx == -INFINITY) ? 0.0f : mx * sc;
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb) {
+          const int pseq = j * nkb + kb, pb = pseq & 1;
+          mbar_wait(smem_u32(&p_empty[pb]), (((uint32_t)pseq >> 1) & 1u) ^ 1u);
+          if (active) {
+            const int nch = (kb == nkb - 1 ? p.rem : KBLK) / 16;
+            // row `row` of the [128 x 64] K-major SWIZZLE_128B tile: 16-B chunk index XOR (row & 7)
+            uint8_t* const prow = sP + pb * P_BYTES + row * 128;
+#pragma unroll 1
+            for (int c = 0; c < nch; ++c) {
+              uint32_t r[16];
+              tmem_ld16(s_addr + (uint32_t)(kb * KBLK + c * 16), r);
+              uint32_t ph[8], pl[8];
+              const int k0 = kb * KBLK + c * 16;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float e0, e1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(r[2 * i]), sc, -mc)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(r[2 * i + 1]), sc, -mc)));
+                e0 = (k0 + 2 * i < nk) ? e0 : 0.0f;
+                e1 = (k0 + 2 * i + 1 < nk) ? e1 : 0.0f;
+                sum += e0 + e1;
+                split2(e0, e1, ph[i], pl[i]);
+              }
+              const int o0 = ((2 * c) ^ (row & 7)) << 4, o1 = ((2 * c + 1) ^ (row & 7)) << 4;
+              *reinterpret_cast<uint4*>(prow + o0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+              *reinterpret_cast<uint4*>(prow + o1) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+              *reinterpret_cast<uint4*>(prow + 16384 + o0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+              *reinterpret_cast<uint4*>(prow + 16384 + o1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+            }
+            fence_proxy_async_smem();
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&p_full[pb]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s_empty[g]));     // the score buffer may be overwritten
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&s_empty[sb]));     // the score buffer may be overwritten
-      // ---- O row / sum -> split16 -> global
+      // ---- O row / sum -> split16 -> global: all of the row's TMEM loads in flight, one wait
       mbar_wait(smem_u32(&o_full[ob]), ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
       if (active) {
         const float inv = 1.0f / sum;
         const uint32_t o_addr = tmem_base + lane_addr + (uint32_t)(SB * scols + ob * HD);
         const int64_t o = ((int64_t)it.s * p.Lq + it.qt * 128 + row) * p.ld_out + it.h * HD;
-        uint4* const dh = reinterpret_cast<uint4*>(p.out_hi + o);
-        uint4* const dl = reinterpret_cast<uint4*>(p.out_lo + o);
 #pragma unroll
-        for (int c = 0; c < HD / 16; ++c) {
-          uint32_t r[16];
-          tmem_ld16(o_addr + (uint32_t)(c * 16), r);
-          uint32_t oh[8], ol[8];
+        for (int hh = 0; hh < HD / 64; ++hh) {
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(o_addr + (uint32_t)(hh * 64), r0);
+          tmem_ld32_nowait(o_addr + (uint32_t)(hh * 64 + 32), r1);
+          tmem_ld_wait();
+          uint4* const dh = reinterpret_cast<uint4*>(p.out_hi + o + hh * 64);
+          uint4* const dl = reinterpret_cast<uint4*>(p.out_lo + o + hh * 64);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            split2(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv, oh[i], ol[i]);
-          if (row < rows_valid) {
-            dh[2 * c] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-            dh[2 * c + 1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-            dl[2 * c] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-            dl[2 * c + 1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t (&r)[32] = c < 2 ? r0 : r1;
+            const int b0 = (c & 1) * 16;
+            uint32_t oh[8], ol[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              split2(__uint_as_float(r[b0 + 2 * i]) * inv, __uint_as_float(r[b0 + 2 * i + 1]) * inv, oh[i], ol[i]);
+            if (row < rows_valid) {
+              dh[2 * c] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+              dh[2 * c + 1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+              dl[2 * c] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+              dl[2 * c + 1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+            }
           }
         }
       }

@@ -201,12 +201,25 @@ __device__ __forceinline__ void ln_stats_chunk(uint32_t (&r)[32], const uint4 (&
     }
   }
 }
-// first pre-norm value of a row (column 0 of chunk 0): the shift of the one-pass variance
-__device__ __forceinline__ float ln_first_x(const uint32_t (&r)[32], const uint4 (&rh)[4], const uint4 (&rl)[4],
-                                            const float* bch, float sc) {
-  const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&rh[0].x));
-  const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&rl[0].x));
-  return fmaf(__uint_as_float(r[0]), sc, bch[0]) + (hf2.x + lf2.x);
+// Shift of the one-pass variance: the mean of the row's first 32 pre-norm values.  (A single value - the
+// first element - can sit 3 sigma off the mean and E[(x-K)^2] - E[x-K]^2 then cancels ~3 bits.)
+__device__ __forceinline__ float ln_shift(const uint32_t (&r)[32], const uint4 (&rh)[4], const uint4 (&rl)[4],
+                                          const float* bch, float sc) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t ah[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
+    const uint32_t al[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&ah[j]));
+      const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&al[j]));
+      const int e = i * 8 + j * 2;
+      acc += fmaf(__uint_as_float(r[e]), sc, bch[e]) + (hf2.x + lf2.x);
+      acc += fmaf(__uint_as_float(r[e + 1]), sc, bch[e + 1]) + (hf2.y + lf2.y);
+    }
+  }
+  return acc * (1.0f / 32);
 }
 // y = (x * a + b) * gamma + beta for one parked 32-column chunk
 __device__ __forceinline__ void ln_norm_chunk(const uint32_t (&r)[32], float (&v)[32], const float* g, const float* be,
@@ -414,7 +427,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     const int hf = (warp - 2) >> 2;                  // which half of the tile's columns
     const int row = q * 32 + lane;
     constexpr int CH = BN / 64;                      // 32-column chunks per warp
-    uint32_t r[32];
+    uint32_t r[32], r2[32];
     float v[32];
     int tbuf = 0;                                    // staging pair for the next TMA store
     uint8_t* const stg = s_stage + (warp - 2) * Cfg::STG_WARP;
@@ -442,9 +455,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       __half* const ohi = p.out_hi;
       __half* const olo = p.out_lo;
       const int64_t obase = orow * p.ld_out + p.out_col0;
-#pragma unroll 1
-      for (int c = 0; c < CH; ++c) {
-        tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
+      // one 32-column chunk: accumulator registers -> bias / activation -> split16 -> global
+      auto chunk = [&](const uint32_t (&r)[32], int c) {
         const int nb = n0 + hf * (BN / 2) + c * 32;
         if (fast && nb + 32 <= N) {               // warp-uniform branch: all lanes take part
           switch (act) {                          // once per chunk
@@ -495,6 +507,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           }
         }
         __syncwarp();
+      };
+      // The TMEM load of chunk c + 1 is in flight while chunk c is processed (a tcgen05.ld + wait round
+      // trip costs ~300 cycles; only two epilogue warps share an SM sub-partition to hide it).
+      tmem_ld32_nowait(trow, r);                   // warp-collective: no divergence around it
+#pragma unroll 1
+      for (int c = 0; c < CH; c += 2) {
+        tmem_ld_wait();
+        if (c + 1 < CH) tmem_ld32_nowait(trow + (c + 1) * 32, r2);
+        chunk(r, c);
+        if (c + 1 < CH) {
+          tmem_ld_wait();
+          if (c + 2 < CH) tmem_ld32_nowait(trow + (c + 2) * 32, r);
+          chunk(r2, c + 1);
+        }
       }
       // this warp is done reading the accumulator stage: hand it back to the MMA warp
       tc_fence_before();
@@ -513,7 +539,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     const int row = q * 32 + lane;
     constexpr int NCH = 8;                           // 32-column chunks per row
     uint8_t* const stg = s_stage + (warp - 2) * Cfg::STG_WARP;
-    uint32_t r[32];
+    uint32_t r[32], r2[32];
     float v[32];
     int tbuf = 0;
     for (int it = g; it < nlocal; it += 2) {
@@ -539,10 +565,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       tc_fence_after();
       float s1 = 0.0f, s2 = 0.0f, shiftK = 0.0f;
       const float sc = p.inv_scale;
+      // TMEM loads are issued one chunk ahead of their use and the parking stores are not waited for one by
+      // one: a tcgen05.ld / st + wait round trip costs ~300 cycles and this group has only itself to hide it.
+      tmem_ld32_nowait(trow, r);
 #pragma unroll 1
       for (int c = 0; c < NCH; c += 2) {
         uint4 rh[4], rl[4];
-        // ---- chunk c (buffers A)
+        // ---- chunk c (residual buffers A, accumulator registers r)
         if (has_res) {
           if (CG == 2) planes_to_rows(stg, gAh, gAl, lane, rh, rl);
           else { plane_to_rows(stg, gAh, lane, rh); plane_to_rows(stg, gAl, lane, rl); }
@@ -554,11 +583,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
         }
-        tmem_ld32(trow + c * 32, r);
-        if (c == 0) shiftK = ln_first_x(r, rh, rl, s_bias, sc);
+        tmem_ld_wait();
+        tmem_ld32_nowait(trow + (c + 1) * 32, r2);
+        if (c == 0) shiftK = ln_shift(r, rh, rl, s_bias, sc);
         ln_stats_chunk(r, rh, rl, s_bias + c * 32, sc, shiftK, s1, s2);
-        tmem_st32(trow + c * 32, r);
-        // ---- chunk c + 1 (buffers B)
+        tmem_st32_nowait(trow + c * 32, r);
+        // ---- chunk c + 1 (residual buffers B, accumulator registers r2)
         if (has_res) {
           if (CG == 2) planes_to_rows(stg, gBh, gBl, lane, rh, rl);
           else { plane_to_rows(stg, gBh, lane, rh); plane_to_rows(stg, gBl, lane, rl); }
@@ -567,17 +597,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
             load_plane_issue(rbl + (c + 3) * 32, p.ld_res, rows_valid, lane, gBl);
           }
         }
-        tmem_ld32(trow + (c + 1) * 32, r);
-        ln_stats_chunk(r, rh, rl, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
-        tmem_st32(trow + (c + 1) * 32, r);
+        tmem_ld_wait();
+        if (c + 2 < NCH) tmem_ld32_nowait(trow + (c + 2) * 32, r);
+        ln_stats_chunk(r2, rh, rl, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
+        tmem_st32_nowait(trow + (c + 1) * 32, r2);
       }
+      tmem_st_wait();                                // the parked row is complete before it is read back
       const float e1 = s1 * (1.0f / 256), e2 = s2 * (1.0f / 256);
       const float rstd = rsqrtf(fmaxf(e2 - e1 * e1, 0.0f) + 1e-5f);
       const float nb_ = -(shiftK + e1) * rstd;       // y = x * rstd + nb_
-#pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        tmem_ld32(trow + c * 32, r);
-        ln_norm_chunk(r, v, s_gamma + c * 32, s_beta + c * 32, rstd, nb_);
+      auto norm_store = [&](const uint32_t (&rr)[32], int c) {
+        ln_norm_chunk(rr, v, s_gamma + c * 32, s_beta + c * 32, rstd, nb_);
         uint32_t ph[16], pl[16];
         pack_split(v, ph, pl);
         if (CG == 2 && p.tma_out) {
@@ -588,6 +618,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
           store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
         }
+      };
+      tmem_ld32_nowait(trow, r);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        tmem_ld_wait();
+        tmem_ld32_nowait(trow + (c + 1) * 32, r2);
+        norm_store(r, c);
+        tmem_ld_wait();
+        if (c + 2 < NCH) tmem_ld32_nowait(trow + (c + 2) * 32, r);
+        norm_store(r2, c + 1);
       }
       tc_fence_before();
       __syncwarp();
@@ -844,7 +884,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
     const int hf = (warp - 2) >> 2;                  // column half of a chunk / of the output row
     const int row = q * 32 + lane;
     uint8_t* const stg = hs + (warp - 2) * 8192;     // LayerNorm staging lives in the (then idle) Hs buffer
-    uint32_t r[32];
+    uint32_t r[32], r2[32];
     float v[32];
     int g = 0;                                       // hidden chunks handled so far
     for (int j = 0; j < nlocal; ++j) {
@@ -856,12 +896,14 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         tc_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * Cfg::CHUNK + hf * 64);
         uint32_t PH[2][16], PL[2][16];
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          tmem_ld32(tacc + cc * 32, r);
-          epi_chunk_fast<ACT_GELU>(r, v, s_b1 + c * Cfg::CHUNK + hf * 64 + cc * 32, p.inv_s1);
-          pack_split(v, PH[cc], PL[cc]);
-        }
+        tmem_ld32_nowait(tacc, r);                   // the second 32 columns load while the first get their GELU
+        tmem_ld_wait();
+        tmem_ld32_nowait(tacc + 32, r2);
+        epi_chunk_fast<ACT_GELU>(r, v, s_b1 + c * Cfg::CHUNK + hf * 64, p.inv_s1);
+        pack_split(v, PH[0], PL[0]);
+        tmem_ld_wait();
+        epi_chunk_fast<ACT_GELU>(r2, v, s_b1 + c * Cfg::CHUNK + hf * 64 + 32, p.inv_s1);
+        pack_split(v, PH[1], PL[1]);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(&bar_a1empty[b]);
@@ -903,6 +945,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       tc_fence_after();
       float s1 = 0.0f, s2 = 0.0f, shiftK = 0.0f;
       const float sc = p.inv_s2;
+      tmem_ld32_nowait(trow, r);                     // TMEM loads run one chunk ahead, parking stores are not awaited one by one
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 rh[4], rl[4];
@@ -916,11 +959,15 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
 #pragma unroll
           for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
         }
-        tmem_ld32(trow + c * 32, r);
-        if (c == 0) shiftK = ln_first_x(r, rh, rl, s_b2 + cb, sc);
-        ln_stats_chunk(r, rh, rl, s_b2 + cb + c * 32, sc, shiftK, s1, s2);
-        tmem_st32(trow + c * 32, r);
+        uint32_t (&rc)[32] = (c & 1) ? r2 : r;
+        uint32_t (&rn)[32] = (c & 1) ? r : r2;
+        tmem_ld_wait();
+        if (c + 1 < 4) tmem_ld32_nowait(trow + (c + 1) * 32, rn);
+        if (c == 0) shiftK = ln_shift(rc, rh, rl, s_b2 + cb, sc);
+        ln_stats_chunk(rc, rh, rl, s_b2 + cb + c * 32, sc, shiftK, s1, s2);
+        tmem_st32_nowait(trow + c * 32, rc);
       }
+      tmem_st_wait();
       // this half: mean_h = K + s1/128, M2_h = s2 - s1^2/128
       const float mean_h = shiftK + s1 * (1.0f / 128), m2_h = fmaxf(s2 - s1 * s1 * (1.0f / 128), 0.0f);
       s_part[hf * 256 + row] = mean_h;
@@ -933,10 +980,8 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       const float rstd = rsqrtf(var + 1e-5f);
       const float nb_ = -mean * rstd;
       int tbuf = 0;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld32(trow + c * 32, r);
-        ln_norm_chunk(r, v, s_gamma + cb + c * 32, s_beta + cb + c * 32, rstd, nb_);
+      auto norm_store = [&](const uint32_t (&rr)[32], int c) {
+        ln_norm_chunk(rr, v, s_gamma + cb + c * 32, s_beta + cb + c * 32, rstd, nb_);
         uint32_t ph[16], pl[16];
         pack_split(v, ph, pl);
         if (p.tma_out) {
@@ -947,6 +992,16 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
           store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
           store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
         }
+      };
+      tmem_ld32_nowait(trow, r);
+#pragma unroll 1
+      for (int c = 0; c < 4; c += 2) {
+        tmem_ld_wait();
+        tmem_ld32_nowait(trow + (c + 1) * 32, r2);
+        norm_store(r, c);
+        tmem_ld_wait();
+        if (c + 2 < 4) tmem_ld32_nowait(trow + (c + 2) * 32, r);
+        norm_store(r2, c + 1);
       }
       // Hs (the staging) is rewritten by the next tile's E1 and s_part by its LayerNorm: the TMA engine
       // must have read the staging and everyone must have read the partial statistics

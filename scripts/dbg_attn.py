@@ -6,7 +6,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 CASES = [(3, 79, 79, 64, 0), (5, 79, 79, 64, 1), (2, 16, 16, 64, 0), (2, 64, 64, 64, 0), (2, 128, 128, 64, 0),
          (7, 3, 3, 64, 0), (300, 79, 79, 64, 0), (8, 196, 196, 64, 1), (6, 196, 196, 128, 0), (3, 79, 79, 128, 1),
-         (300, 1, 79, 64, 0), (5, 196, 2, 128, 0), (2, 256, 256, 64, 0)]
+         (300, 1, 79, 64, 0), (5, 196, 2, 128, 0), (2, 256, 256, 64, 0),
+         (256, 196, 196, 64, 1), (100, 196, 196, 128, 0), (200, 198, 198, 64, 1), (400, 130, 130, 64, 1), (512, 3, 3, 64, 0)]
 
 
 def one(nseq, Lq, Lk, hd, masked):

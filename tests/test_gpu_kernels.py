@@ -77,7 +77,7 @@ def test_fused_ffn_block(eng, M, ff):
     for name, y in zip(("cuda-core", "tc unfused", "tc fused"), ys):
         assert torch.isfinite(y).all(), name
         assert _rel(y, ref) < 5e-6, name
-    assert _rel(ys[2], ys[1]) < 2e-6
+    assert _rel(ys[2], ys[1]) < 4e-6
 
 
 def test_whole_path_tc_equals_cuda_core_path(built_lib):
@@ -162,6 +162,9 @@ SELF_ATTN_CASES = [
     (6, 196, 128, False),        # no-VAE denoiser (d = 512): two 64-wide slices of the head, one Q buffer
     (3, 79, 128, True),
     (2, 256, 64, False),         # the largest key count the score row fits (256 TMEM columns)
+    (256, 196, 64, True),        # VAE decode at the benchmark batch: many items per CTA on ONE score buffer
+    (90, 196, 128, False),       # ... and with head_dim 128
+    (400, 130, 64, True),        # three key blocks on two score buffers
 ]
 
 

@@ -14,14 +14,18 @@
 //                                   delivers the [keys x d] box: an MN-major operand, no transpose)
 // every product in the 3-term split-fp16 form (hi.hi + lo.hi + hi.lo, fp32 accumulation in TMEM).
 //
-// Warp roles (10 warps):
-//   warps 0-3 / 4-7  two softmax groups; group g owns items j = g (mod 2); one query row per
-//                    thread (TMEM lane = row): pass 1 max, pass 2 exp2 + row sum + P re-split to
-//                    hi / lo fp16 written to shared memory in the UMMA K-major SWIZZLE_128B layout,
-//                    then O / sum -> split16 -> global
-//   warp 8           TMA producer: Q tile (own double buffer), then K blocks and V blocks through
+// Warp roles (18 warps):
+//   warps 0-7 / 8-15  two softmax groups; group g owns items j = g (mod 2).  One query row per TMEM lane,
+//                    TWO warps per lane quarter that split the key columns (16-key chunks alternate between
+//                    them): pass 1 partial max -> exchanged through shared memory, pass 2 exp2 + partial row
+//                    sum + P re-split to hi / lo fp16 written to shared memory in the UMMA K-major
+//                    SWIZZLE_128B layout, sums exchanged, then each warp normalises and stores half of the
+//                    O row.  (Measured on the first version, one warp per row: the softmax warps were bound
+//                    by exposed instruction latency - one active warp per SM sub-partition, ~7 cycles per
+//                    instruction - not by TMEM or MUFU throughput; twice the warps halve an item's latency.)
+//   warp 16          TMA producer: Q tile (own double buffer), then K blocks and V blocks through
 //                    one ring of 64-key slots, in exactly the order the MMA warp consumes them
-//   warp 9           TMEM allocator + MMA issuer: S(j+1) is issued before PV(j) when two score
+//   warp 17          TMEM allocator + MMA issuer: S(j+1) is issued before PV(j) when two score
 //                    buffers fit in TMEM, so the tensor pipe works on the next item while a softmax
 //                    group is busy with this one
 // TMEM: S buffers (nkb*64 columns each) then two O buffers (head_dim columns each), <= 512 columns.
@@ -34,7 +38,9 @@
 namespace {
 using namespace tc;
 
-constexpr int ATC_THREADS = 320;
+constexpr int ATC_THREADS = 576;
+constexpr int WARP_TMA = 16, WARP_MMA = 17;
+constexpr int RED_BYTES = 2 * 2 * 2 * 128 * 4;   // [group][max | sum][column half][row] exchange buffers
 constexpr int KBLK = 64;                  // keys per block
 constexpr int P_BYTES = 2 * 16384;        // one P block: [128 rows x 64 keys] hi plane + lo plane
 constexpr int MAX_RS = 8;                 // ring slots (K / V blocks)
@@ -78,7 +84,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
   uint8_t* sQ = smem;
   uint8_t* sR = sQ + p.QB * q_bytes;
   uint8_t* sP = sR + p.RS * SLOT_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
+  float* s_red = reinterpret_cast<float*>(sP + 2 * P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES + RED_BYTES);
   uint64_t* q_full = bars;                  // [2]
   uint64_t* q_empty = bars + 2;             // [2]
   uint64_t* r_full = bars + 4;              // [MAX_RS]
@@ -100,15 +107,15 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&q_full[i]), 1);  mbar_init(smem_u32(&q_empty[i]), 1);
-      mbar_init(smem_u32(&s_full[i]), 1);  mbar_init(smem_u32(&s_empty[i]), 4);
-      mbar_init(smem_u32(&p_full[i]), 4);  mbar_init(smem_u32(&p_empty[i]), 1);
-      mbar_init(smem_u32(&o_full[i]), 1);  mbar_init(smem_u32(&o_empty[i]), 4);
+      mbar_init(smem_u32(&s_full[i]), 1);  mbar_init(smem_u32(&s_empty[i]), 8);
+      mbar_init(smem_u32(&p_full[i]), 8);  mbar_init(smem_u32(&p_empty[i]), 1);
+      mbar_init(smem_u32(&o_full[i]), 1);  mbar_init(smem_u32(&o_empty[i]), 8);
     }
     for (int i = 0; i < MAX_RS; ++i) { mbar_init(smem_u32(&r_full[i]), 1); mbar_init(smem_u32(&r_empty[i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmQh); tma_prefetch_desc(&tmQl); tma_prefetch_desc(&tmKh); tma_prefetch_desc(&tmKl);
   }
-  if (warp == 9) tmem_alloc<1>(smem_u32(tmem_slot), 512);
+  if (warp == WARP_MMA) tmem_alloc<1>(smem_u32(tmem_slot), 512);
   pdl_trigger();
   tc_fence_before();
   __syncthreads();
@@ -116,7 +123,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                                         // q|k|v come from the previous kernel
 
-  if (warp == 8) {
+  if (warp == WARP_TMA) {
     // ------------------------------------------------------------------ TMA producer
     int rc = 0;                                       // ring position (K and V blocks, all items)
     auto load_qk = [&](int j) {
@@ -183,7 +190,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       else load_qk(j);
       load_v(j);
     }
-  } else if (warp == 9) {
+  } else if (warp == WARP_MMA) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc_o = make_idesc(64, 128, true);
     const uint32_t sP_u = smem_u32(sP);
@@ -269,13 +276,16 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue groups
-    const int g = warp >> 2;                  // group 0: warps 0-3, group 1: warps 4-7
+    const int g = warp >> 3;                  // group 0: warps 0-7, group 1: warps 8-15
     const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    const int hf = (warp >> 2) & 1;           // which half of the key chunks / of the O columns this warp handles
     const int row = q * 32 + lane;            // query row of this thread inside the tile
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const float sc = p.scale_log2e;
     const int npad = (nkb - 1) * KBLK + p.rem;          // keys padded to 16
-    const bool fast = npad <= 80;                       // the whole score row fits in 80 registers
+    float* const red_max = s_red + g * 512;             // [half][row]
+    float* const red_sum = red_max + 256;
+    auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); };
     for (int j = g; j < nlocal; j += 2) {
       const Item it = decode_item((int)blockIdx.x + j * (int)gridDim.x, p);
       const int sb = j % SB, ob = j & 1;
@@ -286,155 +296,87 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       const uint32_t s_addr = tmem_base + lane_addr + (uint32_t)(sb * scols);
       mbar_wait(smem_u32(&s_full[g]), ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
-      float sum = 0.0f;
-      if (fast) {
-        // ---- short rows (<= 80 keys: the denoiser's 79 tokens): ONE TMEM round trip brings the whole row into
-        // registers (a tcgen05.ld + wait costs ~300 cycles, the round-1-style chunk loop paid it 10 times per
-        // item), the score buffer goes back to the MMA warp at once, max / exp2 / P run from registers
-        uint32_t s0[32], s1[32], s2[16];
-        if (active) {
-          tmem_ld32_nowait(s_addr, s0);
-          if (npad > 32) tmem_ld32_nowait(s_addr + 32, s1);
-          if (npad > 64) tmem_ld16_nowait(s_addr + 64, s2);
-          tmem_ld_wait();
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_empty[g]));
-        float mx = -INFINITY;
-        if (active) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            mx = fmaxf(mx, (i < nk) ? __uint_as_float(s0[i]) : -INFINITY);
-            if (npad > 32) mx = fmaxf(mx, (32 + i < nk) ? __uint_as_float(s1[i]) : -INFINITY);
-            if (npad > 64 && i < 16) mx = fmaxf(mx, (64 + i < nk) ? __uint_as_float(s2[i]) : -INFINITY);
-          }
-        }
-        const float mc = (mx == -INFINITY) ? 0.0f : mx * sc;
-        // exp2 of 32 keys starting at key k0 -> two 16-key chunks (c16, c16 + 1) of P row `prow`
-        auto exp_store = [&](const uint32_t* sv, int k0, int c16, int n16, uint8_t* prow) {
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (h < n16) {
-              uint32_t ph[8], pl[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float e0, e1;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(sv[h * 16 + 2 * i]), sc, -mc)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(sv[h * 16 + 2 * i + 1]), sc, -mc)));
-                e0 = (k0 + h * 16 + 2 * i < nk) ? e0 : 0.0f;
-                e1 = (k0 + h * 16 + 2 * i + 1 < nk) ? e1 : 0.0f;
-                sum += e0 + e1;
-                split2(e0, e1, ph[i], pl[i]);
-              }
-              const int c = c16 + h;
-              const int o0 = ((2 * c) ^ (row & 7)) << 4, o1 = ((2 * c + 1) ^ (row & 7)) << 4;
-              *reinterpret_cast<uint4*>(prow + o0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-              *reinterpret_cast<uint4*>(prow + o1) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-              *reinterpret_cast<uint4*>(prow + 16384 + o0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-              *reinterpret_cast<uint4*>(prow + 16384 + o1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-            }
-          }
-        };
+      // ---- pass 1: maximum over this warp's 16-key chunks (c = hf, hf + 2, ...), then over both halves
+      float mx = -INFINITY;
+      if (active) {
 #pragma unroll 1
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int pseq = j * nkb + kb, pb = pseq & 1;
-          mbar_wait(smem_u32(&p_empty[pb]), (((uint32_t)pseq >> 1) & 1u) ^ 1u);    // PV(pseq - 2) has read the buffer
-          if (active) {
-            uint8_t* const prow = sP + pb * P_BYTES + row * 128;
-            const int n16 = (kb == nkb - 1 ? p.rem : KBLK) / 16;                   // 16-key chunks of this block
-            if (kb == 0) {
-              exp_store(s0, 0, 0, min(n16, 2), prow);
-              if (n16 > 2) exp_store(s1, 32, 2, n16 - 2, prow);
-            } else {
-              exp_store(s2, 64, 0, 1, prow);
-            }
-            fence_proxy_async_smem();                    // generic-proxy writes -> tcgen05.mma reads
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&p_full[pb]));
-        }
-      } else {
-        // ---- long rows (VAE: 196 / 198 frames): two exact passes over the score row in TMEM
-        float mx = -INFINITY;
-        if (active) {
-#pragma unroll 1
-          for (int c = 0; c < npad / 16; ++c) {
-            uint32_t r[16];
-            tmem_ld16(s_addr + (uint32_t)(c * 16), r);
+        for (int c = hf; c < npad / 16; c += 2) {
+          uint32_t r[16];
+          tmem_ld16(s_addr + (uint32_t)(c * 16), r);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c * 16 + i < nk) ? __uint_as_float(r[i]) : -INFINITY);
-          }
+          for (int i = 0; i < 16; ++i) mx = fmaxf(mx, (c * 16 + i < nk) ? __uint_as_float(r[i]) : -INFINITY);
         }
-        const float mc = (mx == -INFINITY) ? 0.0f : mx * sc;
-#pragma unroll 1
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int pseq = j * nkb + kb, pb = pseq & 1;
-          mbar_wait(smem_u32(&p_empty[pb]), (((uint32_t)pseq >> 1) & 1u) ^ 1u);
-          if (active) {
-            const int nch = (kb == nkb - 1 ? p.rem : KBLK) / 16;
-            // row `row` of the [128 x 64] K-major SWIZZLE_128B tile: 16-B chunk index XOR (row & 7)
-            uint8_t* const prow = sP + pb * P_BYTES + row * 128;
-#pragma unroll 1
-            for (int c = 0; c < nch; ++c) {
-              uint32_t r[16];
-              tmem_ld16(s_addr + (uint32_t)(kb * KBLK + c * 16), r);
-              uint32_t ph[8], pl[8];
-              const int k0 = kb * KBLK + c * 16;
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float e0, e1;
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(r[2 * i]), sc, -mc)));
-                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(r[2 * i + 1]), sc, -mc)));
-                e0 = (k0 + 2 * i < nk) ? e0 : 0.0f;
-                e1 = (k0 + 2 * i + 1 < nk) ? e1 : 0.0f;
-                sum += e0 + e1;
-                split2(e0, e1, ph[i], pl[i]);
-              }
-              const int o0 = ((2 * c) ^ (row & 7)) << 4, o1 = ((2 * c + 1) ^ (row & 7)) << 4;
-              *reinterpret_cast<uint4*>(prow + o0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-              *reinterpret_cast<uint4*>(prow + o1) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
-              *reinterpret_cast<uint4*>(prow + 16384 + o0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-              *reinterpret_cast<uint4*>(prow + 16384 + o1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
-            }
-            fence_proxy_async_smem();
-          }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&p_full[pb]));
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s_empty[g]));     // the score buffer may be overwritten
       }
-      // ---- O row / sum -> split16 -> global: all of the row's TMEM loads in flight, one wait
+      red_max[hf * 128 + row] = mx;
+      group_sync();
+      mx = fmaxf(mx, red_max[(hf ^ 1) * 128 + row]);
+      const float mc = (mx == -INFINITY) ? 0.0f : mx * sc;
+      // ---- pass 2: P = exp2(sc * s - sc * max) (unnormalised), fp32 partial row sum, P -> shared memory
+      float sum = 0.0f;
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int pseq = j * nkb + kb, pb = pseq & 1;
+        mbar_wait(smem_u32(&p_empty[pb]), (((uint32_t)pseq >> 1) & 1u) ^ 1u);    // PV(pseq - 2) has read the buffer
+        if (active) {
+          const int nch = (kb == nkb - 1 ? p.rem : KBLK) / 16;
+          // row `row` of the [128 x 64] K-major SWIZZLE_128B tile: 16-B chunk index XOR (row & 7)
+          uint8_t* const prow = sP + pb * P_BYTES + row * 128;
+#pragma unroll 1
+          for (int c = hf; c < nch; c += 2) {
+            uint32_t r[16];
+            tmem_ld16(s_addr + (uint32_t)(kb * KBLK + c * 16), r);
+            uint32_t ph[8], pl[8];
+            const int k0 = kb * KBLK + c * 16;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float e0, e1;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fmaf(__uint_as_float(r[2 * i]), sc, -mc)));
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fmaf(__uint_as_float(r[2 * i + 1]), sc, -mc)));
+              e0 = (k0 + 2 * i < nk) ? e0 : 0.0f;
+              e1 = (k0 + 2 * i + 1 < nk) ? e1 : 0.0f;
+              sum += e0 + e1;
+              split2(e0, e1, ph[i], pl[i]);
+            }
+            const int o0 = ((2 * c) ^ (row & 7)) << 4, o1 = ((2 * c + 1) ^ (row & 7)) << 4;
+            *reinterpret_cast<uint4*>(prow + o0) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+            *reinterpret_cast<uint4*>(prow + o1) = make_uint4(ph[4], ph[5], ph[6], ph[7]);
+            *reinterpret_cast<uint4*>(prow + 16384 + o0) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+            *reinterpret_cast<uint4*>(prow + 16384 + o1) = make_uint4(pl[4], pl[5], pl[6], pl[7]);
+          }
+          fence_proxy_async_smem();                      // generic-proxy writes -> tcgen05.mma reads
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&p_full[pb]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&s_empty[g]));     // the score buffer may be overwritten
+      red_sum[hf * 128 + row] = sum;
+      group_sync();
+      sum += red_sum[(hf ^ 1) * 128 + row];
+      // ---- this warp's half of the O row / sum -> split16 -> global
       mbar_wait(smem_u32(&o_full[ob]), ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
       if (active) {
         const float inv = 1.0f / sum;
-        const uint32_t o_addr = tmem_base + lane_addr + (uint32_t)(SB * scols + ob * HD);
-        const int64_t o = ((int64_t)it.s * p.Lq + it.qt * 128 + row) * p.ld_out + it.h * HD;
+        constexpr int OC = HD / 2;                           // O columns per warp
+        const uint32_t o_addr = tmem_base + lane_addr + (uint32_t)(SB * scols + ob * HD + hf * OC);
+        const int64_t o = ((int64_t)it.s * p.Lq + it.qt * 128 + row) * p.ld_out + it.h * HD + hf * OC;
+        uint4* const dh = reinterpret_cast<uint4*>(p.out_hi + o);
+        uint4* const dl = reinterpret_cast<uint4*>(p.out_lo + o);
 #pragma unroll
-        for (int hh = 0; hh < HD / 64; ++hh) {
-          uint32_t r0[32], r1[32];
-          tmem_ld32_nowait(o_addr + (uint32_t)(hh * 64), r0);
-          tmem_ld32_nowait(o_addr + (uint32_t)(hh * 64 + 32), r1);
-          tmem_ld_wait();
-          uint4* const dh = reinterpret_cast<uint4*>(p.out_hi + o + hh * 64);
-          uint4* const dl = reinterpret_cast<uint4*>(p.out_lo + o + hh * 64);
+        for (int c = 0; c < OC / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(o_addr + (uint32_t)(c * 16), r);
+          uint32_t oh[8], ol[8];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t (&r)[32] = c < 2 ? r0 : r1;
-            const int b0 = (c & 1) * 16;
-            uint32_t oh[8], ol[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              split2(__uint_as_float(r[b0 + 2 * i]) * inv, __uint_as_float(r[b0 + 2 * i + 1]) * inv, oh[i], ol[i]);
-            if (row < rows_valid) {
-              dh[2 * c] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-              dh[2 * c + 1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-              dl[2 * c] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-              dl[2 * c + 1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
-            }
+          for (int i = 0; i < 8; ++i)
+            split2(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv, oh[i], ol[i]);
+          if (row < rows_valid) {
+            dh[2 * c] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+            dh[2 * c + 1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+            dl[2 * c] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            dl[2 * c + 1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
           }
         }
       }
@@ -445,7 +387,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, 512);
   }
@@ -478,7 +420,7 @@ bool plan_shape(const AttnArgs& a, AtcParams* p) {
   if (scols + 2 * a.hd > 512) return false;
   p->SB = (2 * scols + 2 * a.hd <= 512) ? 2 : 1;
   const int q_bytes = 2 * ns * p->QR * 128, slot = 2 * ns * KBLK * 128;
-  const int fixed = 1024 + 2 * P_BYTES + 512;          // alignment slack + P ring + barriers
+  const int fixed = 1024 + 2 * P_BYTES + RED_BYTES + 512;   // alignment slack + P ring + exchange buffers + barriers
   for (int qb = 2; qb >= 1; --qb) {
     const int left = SMEM_LIMIT - fixed - qb * q_bytes;
     const int rs = left / slot;
@@ -488,7 +430,7 @@ bool plan_shape(const AttnArgs& a, AtcParams* p) {
 }
 int smem_bytes(const AttnArgs& a, const AtcParams& p) {
   const int ns = a.hd / 64;
-  return 1024 + p.QB * 2 * ns * p.QR * 128 + p.RS * 2 * ns * KBLK * 128 + 2 * P_BYTES + 512;
+  return 1024 + p.QB * 2 * ns * p.QR * 128 + p.RS * 2 * ns * KBLK * 128 + 2 * P_BYTES + RED_BYTES + 512;
 }
 
 }  // namespace

@@ -346,6 +346,9 @@ static StepCoef make_coef(const mldb_handle* h, int64_t t, int n_inference) {
 static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
 // ----------------------------------------------------------------------------- op dispatch
+static inline ActBuf rows_of(ActBuf b, int64_t row0, int rows) {
+  b.hi += row0 * b.cols; b.rows = rows; return b;
+}
 static inline void kcount(mldb_handle* h, int kind) { h->kstat[kind]++; count_launch(h); }
 static void op_gemm(mldb_handle* h, const GemmArgs& g, cudaStream_t st) {
   if (h->use_tc && tc_gemm_supported(h->tc, g)) {
@@ -386,8 +389,20 @@ static void op_attn(mldb_handle* h, const AttnArgs& a, cudaStream_t st) {
 static void op_ffn(mldb_handle* h, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, float* cf32, cudaStream_t st) {
   if (h->use_tc && tc_ffn_supported(h->tc, g1, g2, l2)) {
     // one launch: the hidden activations stay in shared memory / TMEM (gemm_tc.cu k_ffn_tc)
-    if (!tc_ffn(h->tc, g1, g2, l2, st)) h->op_failed = true;
+    // The m-tiles of the last, partial round (316 tiles on 74 CTA pairs = 2.13 rounds) are spread over the idle
+    // SMs by a hidden-dimension split (option ffn_tail); their residual + LayerNorm finish in a row kernel.
+    int tail_rows = 0, tail_split = 1;
+    if (!tc_ffn(h->tc, g1, g2, l2, h->ffn_tail ? cf32 : nullptr, st, &tail_rows, &tail_split)) h->op_failed = true;
     kcount(h, MLDB_KSTAT_FFN_TC);
+    if (tail_rows > 0) {
+      kcount(h, MLDB_KSTAT_FFN_TC);
+      const int64_t r0 = g1.M - tail_rows;
+      LnArgs lt = l2;
+      lt.c = cf32; lt.ldc = 256; lt.c_parts = tail_split; lt.c_part_stride = (int64_t)tail_rows * 256;
+      lt.res = rows_of(l2.res, r0, tail_rows); lt.out = rows_of(l2.out, r0, tail_rows); lt.M = tail_rows;
+      simt_ln(lt, st);
+      kcount(h, MLDB_KSTAT_LN_SIMT);
+    }
     return;
   }
   op_gemm(h, g1, st);
@@ -447,9 +462,6 @@ struct SeqInfo {
   int len_mod = 0;
 };
 
-static inline ActBuf rows_of(ActBuf b, int64_t row0, int rows) {
-  b.hi += row0 * b.cols; b.rows = rows; return b;
-}
 // the workspace rows of sequences [s0, s0 + n): a self-contained workspace for that sub-batch
 static StackWs ws_slice(const StackWs& ws, int s0, int n) {
   StackWs w = ws;
@@ -642,6 +654,8 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   if (env) h->attn_kind = !strcmp(env, "mma") ? 1 : (!strcmp(env, "simt") ? 2 : 0);
   env = getenv("MLDB_BRANCHES");
   if (env) h->branches = std::min(std::max(atoi(env), 1), (int)mldb_handle::MAX_BRANCHES);
+  env = getenv("MLDB_FFN_TAIL");
+  if (env) h->ffn_tail = atoi(env) != 0;
   e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   for (int i = 0; i < mldb_handle::MAX_BRANCHES - 1 && e == cudaSuccess; ++i) {
     e = cudaStreamCreateWithFlags(&h->br_stream[i], cudaStreamNonBlocking);
@@ -680,6 +694,8 @@ extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* val
     else FAIL(MLDB_ERR_INVALID, "gemm must be tc|simt");
   } else if (!strcmp(name, "ffn_fused")) {
     tc_set_ffn_fused(h->tc, atoi(value) != 0);
+  } else if (!strcmp(name, "ffn_tail")) {
+    h->ffn_tail = atoi(value) != 0;
   } else if (!strcmp(name, "attn")) {
     if (!strcmp(value, "tc")) h->attn_kind = 0;
     else if (!strcmp(value, "mma")) h->attn_kind = 1;

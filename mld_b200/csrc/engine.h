@@ -124,6 +124,7 @@ struct mldb_handle {
   // so one range's kernel tails (316 m-tiles on 148 SMs = 2.13 rounds) and kernel boundaries are
   // filled by the other range's kernels.  1 = off.
   int branches = 2;
+  bool ffn_tail = true;      // hidden-split of the fused FFN's last partial round of m-tiles (option ffn_tail)
   int attn_kind = 0;         // 0 = tcgen05 (attn_tc.cu), 1 = mma.sync (attn_mma.cu), 2 = CUDA-core; option `attn`
   // which kernel every operator of the path was ENQUEUED on (recorded launches, incl. graph capture);
   // read through mldb_kernel_stats so that tests can assert "nothing fell back to CUDA cores"

@@ -267,13 +267,19 @@ __device__ __forceinline__ void decode_item(int j, const TcParams& p, int bn, in
 // Persistent: CTA (pair) c walks items c, c + #CTAs (pairs), ...; item t -> (m = t / n_tiles, n = t % n_tiles).
 // The accumulator is double-buffered in TMEM (2 x BN columns) so the epilogue of tile i overlaps
 // the TMA/MMA main loop of tile i + 1.
-template <int BN, int CG, bool LN>
+// EPI selects the epilogue: EPI_FAST = plain, split16 output, identity row mapping, every 32-column chunk
+// inside N (the per-layer GEMMs); EPI_LN = residual + LayerNorm; EPI_GENERIC = plain with everything else
+// (positional table, row remapping, zeroed padding rows, fp32 output, ragged N: the per-batch embedding /
+// final-layer GEMMs) kept out of the hot kernels' instruction stream.
+enum { EPI_FAST = 0, EPI_LN = 1, EPI_GENERIC = 2 };
+template <int BN, int CG, int EPI, int ACT = ACT_NONE>      // ACT: the fast epilogue's activation (NONE | GELU)
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
           const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
           const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
           const TcParams p) {
+  constexpr bool LN = EPI == EPI_LN;
   static_assert(!LN || BN == 256, "the LayerNorm epilogue covers a full 256-wide row");
   using Cfg = TileCfg<BN, CG>;
   constexpr int STAGES = Cfg::STAGES;
@@ -422,12 +428,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       }
     }
   } else if constexpr (!LN) {
-    // ------------------------------------------------------------------ plain epilogue (warps 2..9)
+    // ------------------------------------------------------------------ plain epilogues (warps 2..9)
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     const int hf = (warp - 2) >> 2;                  // which half of the tile's columns
     const int row = q * 32 + lane;
     constexpr int CH = BN / 64;                      // 32-column chunks per warp
-    uint32_t r[32], r2[32];
+    uint32_t r[32];
     float v[32];
     int tbuf = 0;                                    // staging pair for the next TMA store
     uint8_t* const stg = s_stage + (warp - 2) * Cfg::STG_WARP;
@@ -447,9 +453,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       const int64_t orow = (int64_t)seq * p.out_group + p.out_off + pos;
       const bool zero = row_ok && p.zero_lengths != nullptr && pos >= p.zero_lengths[seq];
       const float* tab = p.addtab ? p.addtab + (int64_t)(p.out_off + pos) * p.N : nullptr;
-      // fast path: identity row mapping, split16 output, no table / masking (warp-uniform)
-      const bool fast = p.addtab == nullptr && p.zero_lengths == nullptr && p.out_hi != nullptr &&
-                        p.out_f32 == nullptr && p.in_group >= p.M && p.out_group == 0 && p.out_off == 0;
       const float inv_scale = p.inv_scale;
       const int act = p.act, N = p.N;
       __half* const ohi = p.out_hi;
@@ -458,13 +461,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       // one 32-column chunk: accumulator registers -> bias / activation -> split16 -> global
       auto chunk = [&](const uint32_t (&r)[32], int c) {
         const int nb = n0 + hf * (BN / 2) + c * 32;
-        if (fast && nb + 32 <= N) {               // warp-uniform branch: all lanes take part
-          switch (act) {                          // once per chunk
-            case ACT_NONE: epi_chunk_fast<ACT_NONE>(r, v, s_bias + nb, inv_scale); break;
-            case ACT_GELU: epi_chunk_fast<ACT_GELU>(r, v, s_bias + nb, inv_scale); break;
-            case ACT_RELU: epi_chunk_fast<ACT_RELU>(r, v, s_bias + nb, inv_scale); break;
-            default:       epi_chunk_fast<ACT_SILU>(r, v, s_bias + nb, inv_scale); break;
-          }
+        if constexpr (EPI == EPI_FAST) {
+          epi_chunk_fast<ACT>(r, v, s_bias + nb, inv_scale);
           uint32_t ph[16], pl[16];
           pack_split(v, ph, pl);
           if (CG == 2 && p.tma_out) {
@@ -508,19 +506,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         }
         __syncwarp();
       };
-      // The TMEM load of chunk c + 1 is in flight while chunk c is processed (a tcgen05.ld + wait round
-      // trip costs ~300 cycles; only two epilogue warps share an SM sub-partition to hide it).
-      tmem_ld32_nowait(trow, r);                   // warp-collective: no divergence around it
 #pragma unroll 1
-      for (int c = 0; c < CH; c += 2) {
-        tmem_ld_wait();
-        if (c + 1 < CH) tmem_ld32_nowait(trow + (c + 1) * 32, r2);
+      for (int c = 0; c < CH; ++c) {
+        tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
         chunk(r, c);
-        if (c + 1 < CH) {
-          tmem_ld_wait();
-          if (c + 2 < CH) tmem_ld32_nowait(trow + (c + 2) * 32, r);
-          chunk(r2, c + 1);
-        }
       }
       // this warp is done reading the accumulator stage: hand it back to the MMA warp
       tc_fence_before();
@@ -539,7 +528,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     const int row = q * 32 + lane;
     constexpr int NCH = 8;                           // 32-column chunks per row
     uint8_t* const stg = s_stage + (warp - 2) * Cfg::STG_WARP;
-    uint32_t r[32], r2[32];
+    uint32_t r[32];
     float v[32];
     int tbuf = 0;
     for (int it = g; it < nlocal; it += 2) {
@@ -565,13 +554,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       tc_fence_after();
       float s1 = 0.0f, s2 = 0.0f, shiftK = 0.0f;
       const float sc = p.inv_scale;
-      // TMEM loads are issued one chunk ahead of their use and the parking stores are not waited for one by
-      // one: a tcgen05.ld / st + wait round trip costs ~300 cycles and this group has only itself to hide it.
-      tmem_ld32_nowait(trow, r);
 #pragma unroll 1
       for (int c = 0; c < NCH; c += 2) {
         uint4 rh[4], rl[4];
-        // ---- chunk c (residual buffers A, accumulator registers r)
+        // ---- chunk c (buffers A)
         if (has_res) {
           if (CG == 2) planes_to_rows(stg, gAh, gAl, lane, rh, rl);
           else { plane_to_rows(stg, gAh, lane, rh); plane_to_rows(stg, gAl, lane, rl); }
@@ -583,12 +569,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
         }
-        tmem_ld_wait();
-        tmem_ld32_nowait(trow + (c + 1) * 32, r2);
+        tmem_ld32(trow + c * 32, r);
         if (c == 0) shiftK = ln_shift(r, rh, rl, s_bias, sc);
         ln_stats_chunk(r, rh, rl, s_bias + c * 32, sc, shiftK, s1, s2);
-        tmem_st32_nowait(trow + c * 32, r);
-        // ---- chunk c + 1 (residual buffers B, accumulator registers r2)
+        tmem_st32(trow + c * 32, r);
+        // ---- chunk c + 1 (buffers B)
         if (has_res) {
           if (CG == 2) planes_to_rows(stg, gBh, gBl, lane, rh, rl);
           else { plane_to_rows(stg, gBh, lane, rh); plane_to_rows(stg, gBl, lane, rl); }
@@ -597,17 +582,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
             load_plane_issue(rbl + (c + 3) * 32, p.ld_res, rows_valid, lane, gBl);
           }
         }
-        tmem_ld_wait();
-        if (c + 2 < NCH) tmem_ld32_nowait(trow + (c + 2) * 32, r);
-        ln_stats_chunk(r2, rh, rl, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
-        tmem_st32_nowait(trow + (c + 1) * 32, r2);
+        tmem_ld32(trow + (c + 1) * 32, r);
+        ln_stats_chunk(r, rh, rl, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
+        tmem_st32(trow + (c + 1) * 32, r);
       }
-      tmem_st_wait();                                // the parked row is complete before it is read back
       const float e1 = s1 * (1.0f / 256), e2 = s2 * (1.0f / 256);
       const float rstd = rsqrtf(fmaxf(e2 - e1 * e1, 0.0f) + 1e-5f);
       const float nb_ = -(shiftK + e1) * rstd;       // y = x * rstd + nb_
-      auto norm_store = [&](const uint32_t (&rr)[32], int c) {
-        ln_norm_chunk(rr, v, s_gamma + c * 32, s_beta + c * 32, rstd, nb_);
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        tmem_ld32(trow + c * 32, r);
+        ln_norm_chunk(r, v, s_gamma + c * 32, s_beta + c * 32, rstd, nb_);
         uint32_t ph[16], pl[16];
         pack_split(v, ph, pl);
         if (CG == 2 && p.tma_out) {
@@ -618,16 +603,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
           store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
         }
-      };
-      tmem_ld32_nowait(trow, r);
-#pragma unroll 1
-      for (int c = 0; c < NCH; c += 2) {
-        tmem_ld_wait();
-        tmem_ld32_nowait(trow + (c + 1) * 32, r2);
-        norm_store(r, c);
-        tmem_ld_wait();
-        if (c + 2 < NCH) tmem_ld32_nowait(trow + (c + 2) * 32, r);
-        norm_store(r2, c + 1);
       }
       tc_fence_before();
       __syncwarp();
@@ -657,6 +632,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
 // W2 k-blocks through one ring (2 x 64 KB; 3 x 48 KB per CTA of a pair) in exactly that order.
 struct FfnParams {
   int M, m_tiles, n_chunks;
+  // Hidden-dimension split of the LAST, partial round of m-tiles: `split` CTA groups share one m-tile
+  // (pair), each walks n_chunks / split hidden chunks and stores its partial W2 product into its own slice
+  // of `partial` (fp32 [split][M][256]; bias added by split 0; plain stores: deterministic); the residual +
+  // LayerNorm then run as a row kernel that sums the slices in order.  split == 1: the normal fused kernel.
+  int split;
+  float* partial;
   float inv_s1, inv_s2;
   const float* b1; const float* b2; const float* gamma; const float* beta;
   const __half* res_hi; const __half* res_lo; int ld_res;
@@ -714,11 +695,15 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
-  const int NC = p.n_chunks;
   const int rank = CG > 1 ? (int)cluster_ctarank() : 0;
   const int ncl = (int)gridDim.x / CG, cid = (int)blockIdx.x / CG;
   const int ngroups = (p.m_tiles + CG - 1) / CG;
-  const int nlocal = (ngroups - cid + ncl - 1) / ncl;
+  const bool split_mode = p.split > 1;
+  const int NC = p.n_chunks / p.split;                    // hidden chunks this CTA (group) walks per m-tile
+  const int chunk0 = split_mode ? (cid % p.split) * NC : 0;
+  const int nlocal = split_mode ? 1 : (ngroups - cid + ncl - 1) / ncl;
+  // m-tile group of the j-th local item
+  auto mgroup = [&](int j) { return split_mode ? cid / p.split : cid + j * ncl; };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -740,7 +725,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   if (CG > 1) { __syncthreads(); cluster_sync_all(); }
   if (warp == 1) tmem_alloc<CG>(smem_u32(tmem_slot), Cfg::TMEM_COLS);
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_b1[i] = (p.b1 && i < NC * Cfg::CHUNK) ? p.b1[i] : 0.0f;
+    for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_b1[i] = (p.b1 && i < p.n_chunks * Cfg::CHUNK) ? p.b1[i] : 0.0f;
     for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) {
       s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; s_b2[i] = p.b2 ? p.b2[i] : 0.0f;
     }
@@ -779,7 +764,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       else tma_load_2d_2sm(dst, map, full, c0, c1);
     };
     for (int j = 0; j < nlocal; ++j) {
-      const int m0 = ((cid + j * ncl) * CG + rank) * BM;
+      const int m0 = (mgroup(j) * CG + rank) * BM;
       for (int i = 0; i <= NC; ++i) {
         if (i < NC) {
           for (int kb = 0; kb < 4; ++kb, ++kbg) {
@@ -789,8 +774,8 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
               const uint32_t dst = stage_begin(Cfg::F1_BYTES, full);
               load(dst, &tmXh, full, kb * BK, m0);
               load(dst + 16384, &tmXl, full, kb * BK, m0);
-              load(dst + 32768, &tmW1h, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
-              load(dst + 32768 + Cfg::W1_BYTES, &tmW1l, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
+              load(dst + 32768, &tmW1h, full, kb * BK, (chunk0 + i) * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
+              load(dst + 32768 + Cfg::W1_BYTES, &tmW1l, full, kb * BK, (chunk0 + i) * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
             }
             __syncwarp();
           }
@@ -801,8 +786,8 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
             if (elect_one()) {
               uint32_t full;
               const uint32_t dst = stage_begin(Cfg::F2_BYTES, full);
-              load(dst, &tmW2h, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
-              load(dst + Cfg::W2_BYTES, &tmW2l, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
+              load(dst, &tmW2h, full, (chunk0 + i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
+              load(dst + Cfg::W2_BYTES, &tmW2l, full, (chunk0 + i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
             }
             __syncwarp();
           }
@@ -884,11 +869,11 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
     const int hf = (warp - 2) >> 2;                  // column half of a chunk / of the output row
     const int row = q * 32 + lane;
     uint8_t* const stg = hs + (warp - 2) * 8192;     // LayerNorm staging lives in the (then idle) Hs buffer
-    uint32_t r[32], r2[32];
+    uint32_t r[32];
     float v[32];
     int g = 0;                                       // hidden chunks handled so far
     for (int j = 0; j < nlocal; ++j) {
-      const int m0 = ((cid + j * ncl) * CG + rank) * BM;
+      const int m0 = (mgroup(j) * CG + rank) * BM;
       // ---- E1: hidden chunks -> Hs
       for (int c = 0; c < NC; ++c, ++g) {
         const int b = g & 1;
@@ -896,14 +881,12 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         tc_fence_after();
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * Cfg::CHUNK + hf * 64);
         uint32_t PH[2][16], PL[2][16];
-        tmem_ld32_nowait(tacc, r);                   // the second 32 columns load while the first get their GELU
-        tmem_ld_wait();
-        tmem_ld32_nowait(tacc + 32, r2);
-        epi_chunk_fast<ACT_GELU>(r, v, s_b1 + c * Cfg::CHUNK + hf * 64, p.inv_s1);
-        pack_split(v, PH[0], PL[0]);
-        tmem_ld_wait();
-        epi_chunk_fast<ACT_GELU>(r2, v, s_b1 + c * Cfg::CHUNK + hf * 64 + 32, p.inv_s1);
-        pack_split(v, PH[1], PL[1]);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          tmem_ld32(tacc + cc * 32, r);
+          epi_chunk_fast<ACT_GELU>(r, v, s_b1 + (chunk0 + c) * Cfg::CHUNK + hf * 64 + cc * 32, p.inv_s1);
+          pack_split(v, PH[cc], PL[cc]);
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(&bar_a1empty[b]);
@@ -921,6 +904,35 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         fence_proxy_async_smem();                    // generic-proxy writes -> tcgen05.mma reads
         __syncwarp();
         if (lane == 0) arrive_leader(bar_hfull);
+      }
+      if (split_mode) {
+        // ---- partial W2 product of this CTA's hidden chunks -> this split's fp32 slice (bias by split 0);
+        // the rows' residual + LayerNorm run afterwards as a row kernel over the summed slices
+        const int m = m0 + row;
+        const int cb = hf * 128;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * Cfg::CHUNK + cb);
+        mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);
+        tc_fence_after();
+        const bool add_bias = chunk0 == 0;
+        float* const drow = p.partial + ((int64_t)(cid % p.split) * p.M + m) * 256 + cb;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_ld32(trow + c * 32, r);
+          if (m < p.M) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 b = add_bias ? reinterpret_cast<const float4*>(s_b2 + cb + c * 32)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+              float4 x;
+              x.x = fmaf(__uint_as_float(r[4 * i + 0]), p.inv_s2, b.x); x.y = fmaf(__uint_as_float(r[4 * i + 1]), p.inv_s2, b.y);
+              x.z = fmaf(__uint_as_float(r[4 * i + 2]), p.inv_s2, b.z); x.w = fmaf(__uint_as_float(r[4 * i + 3]), p.inv_s2, b.w);
+              reinterpret_cast<float4*>(drow + c * 32)[i] = x;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(bar_a2empty);
+        continue;
       }
       // ---- residual + LayerNorm on acc2.  Two warps share a row (column halves of 128): each keeps
       // one-pass statistics shifted by ITS first value and the halves are merged with the pairwise
@@ -945,7 +957,6 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       tc_fence_after();
       float s1 = 0.0f, s2 = 0.0f, shiftK = 0.0f;
       const float sc = p.inv_s2;
-      tmem_ld32_nowait(trow, r);                     // TMEM loads run one chunk ahead, parking stores are not awaited one by one
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint4 rh[4], rl[4];
@@ -959,15 +970,11 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
 #pragma unroll
           for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
         }
-        uint32_t (&rc)[32] = (c & 1) ? r2 : r;
-        uint32_t (&rn)[32] = (c & 1) ? r : r2;
-        tmem_ld_wait();
-        if (c + 1 < 4) tmem_ld32_nowait(trow + (c + 1) * 32, rn);
-        if (c == 0) shiftK = ln_shift(rc, rh, rl, s_b2 + cb, sc);
-        ln_stats_chunk(rc, rh, rl, s_b2 + cb + c * 32, sc, shiftK, s1, s2);
-        tmem_st32_nowait(trow + c * 32, rc);
+        tmem_ld32(trow + c * 32, r);
+        if (c == 0) shiftK = ln_shift(r, rh, rl, s_b2 + cb, sc);
+        ln_stats_chunk(r, rh, rl, s_b2 + cb + c * 32, sc, shiftK, s1, s2);
+        tmem_st32(trow + c * 32, r);
       }
-      tmem_st_wait();
       // this half: mean_h = K + s1/128, M2_h = s2 - s1^2/128
       const float mean_h = shiftK + s1 * (1.0f / 128), m2_h = fmaxf(s2 - s1 * s1 * (1.0f / 128), 0.0f);
       s_part[hf * 256 + row] = mean_h;
@@ -980,8 +987,10 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       const float rstd = rsqrtf(var + 1e-5f);
       const float nb_ = -mean * rstd;
       int tbuf = 0;
-      auto norm_store = [&](const uint32_t (&rr)[32], int c) {
-        ln_norm_chunk(rr, v, s_gamma + cb + c * 32, s_beta + cb + c * 32, rstd, nb_);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld32(trow + c * 32, r);
+        ln_norm_chunk(r, v, s_gamma + cb + c * 32, s_beta + cb + c * 32, rstd, nb_);
         uint32_t ph[16], pl[16];
         pack_split(v, ph, pl);
         if (p.tma_out) {
@@ -992,16 +1001,6 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
           store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
           store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
         }
-      };
-      tmem_ld32_nowait(trow, r);
-#pragma unroll 1
-      for (int c = 0; c < 4; c += 2) {
-        tmem_ld_wait();
-        tmem_ld32_nowait(trow + (c + 1) * 32, r2);
-        norm_store(r, c);
-        tmem_ld_wait();
-        if (c + 2 < 4) tmem_ld32_nowait(trow + (c + 2) * 32, r);
-        norm_store(r2, c + 1);
       }
       // Hs (the staging) is rewritten by the next tile's E1 and s_part by its LayerNorm: the TMA engine
       // must have read the staging and everyone must have read the partial statistics
@@ -1048,9 +1047,13 @@ TcCtx* tc_create(int device) {
   auto opt_in = [&](auto kernel, int bytes) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   };
-  opt_in(k_gemm_tc<256, 1, false>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1, false>, TileCfg<128, 1>::SMEM_BYTES);
-  opt_in(k_gemm_tc<256, 2, false>, TileCfg<256, 2>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2, false>, TileCfg<128, 2>::SMEM_BYTES);
-  opt_in(k_gemm_tc<256, 1, true>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<256, 2, true>, TileCfg<256, 2>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 1, EPI_FAST>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1, EPI_FAST>, TileCfg<128, 1>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 2, EPI_FAST>, TileCfg<256, 2>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2, EPI_FAST>, TileCfg<128, 2>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 1, EPI_FAST, ACT_GELU>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1, EPI_FAST, ACT_GELU>, TileCfg<128, 1>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 2, EPI_FAST, ACT_GELU>, TileCfg<256, 2>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2, EPI_FAST, ACT_GELU>, TileCfg<128, 2>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 1, EPI_GENERIC>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1, EPI_GENERIC>, TileCfg<128, 1>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 2, EPI_GENERIC>, TileCfg<256, 2>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2, EPI_GENERIC>, TileCfg<128, 2>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 1, EPI_LN>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<256, 2, EPI_LN>, TileCfg<256, 2>::SMEM_BYTES);
   opt_in(k_ffn_tc<1>, FfnCfg<1>::SMEM_BYTES); opt_in(k_ffn_tc<2>, FfnCfg<2>::SMEM_BYTES);
   if (e != cudaSuccess) {
     mldb_set_err(std::string("cudaFuncSetAttribute(k_gemm_tc): ") + cudaGetErrorString(e));
@@ -1149,12 +1152,14 @@ bool tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   TcParams p;
   fill_params(g, ln, bn, &p);
   CUtensorMap mOh = mA1h, mOl = mA1l;
+  // the fast plain epilogue: split16 output, identity row mapping, N a whole number of tiles
+  const bool fast = !ln && g.out.hi && !g.out_f32 && !g.addtab && !g.zero_lengths && g.in_group >= g.M &&
+                    g.out_group == 0 && g.out_off == 0 && g.w.N % bn == 0 && (g.act == ACT_NONE || g.act == ACT_GELU);
   if (cl == 2 && ln) {
     if (!make_map_out(c, &mOh, ln->out.hi, g.M, 256, ln->out.cols) || !make_map_out(c, &mOl, ln->out.lo(), g.M, 256, ln->out.cols))
       return map_fail("gemm ln out", g.M, g.w.N, g.w.K);
     p.tma_out = 1;
-  } else if (cl == 2 && g.out.hi && !g.out_f32 && !g.addtab && !g.zero_lengths && g.in_group >= g.M &&
-             g.out_group == 0 && g.out_off == 0) {
+  } else if (cl == 2 && fast) {
     if (!make_map_out(c, &mOh, g.out.hi + g.out_col0, g.M, g.w.N, g.out.cols) ||
         !make_map_out(c, &mOl, g.out.lo() + g.out_col0, g.M, g.w.N, g.out.cols))
       return map_fail("gemm out", g.M, g.w.N, g.w.K);
@@ -1163,12 +1168,19 @@ bool tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   const int ngroups = ((p.m_tiles + cl - 1) / cl) * p.n_tiles;
   const int ncl = ngroups < c->sm_count / cl ? ngroups : c->sm_count / cl;
   dim3 grid(ncl * cl);
-#define MLDB_LAUNCH(BN_, CL_, LN_)                                                                                   \
-  launch_pdl_cluster(k_gemm_tc<BN_, CL_, LN_>, grid, dim3(NUM_THREADS), TileCfg<BN_, CL_>::SMEM_BYTES, st, CL_, mA1h, \
-                     mA1l, mA2h, mA2l, mWh, mWl, mOh, mOl, p)
-  if (ln)             { if (cl == 2) MLDB_LAUNCH(256, 2, true); else MLDB_LAUNCH(256, 1, true); }
-  else if (bn == 256) { if (cl == 2) MLDB_LAUNCH(256, 2, false); else MLDB_LAUNCH(256, 1, false); }
-  else                { if (cl == 2) MLDB_LAUNCH(128, 2, false); else MLDB_LAUNCH(128, 1, false); }
+#define MLDB_LAUNCH(BN_, CL_, ...)                                                                                       \
+  launch_pdl_cluster(k_gemm_tc<BN_, CL_, __VA_ARGS__>, grid, dim3(NUM_THREADS), TileCfg<BN_, CL_>::SMEM_BYTES, st, CL_, \
+                     mA1h, mA1l, mA2h, mA2l, mWh, mWl, mOh, mOl, p)
+#define MLDB_LAUNCH_SHAPE(...)                                                                        \
+  do {                                                                                                \
+    if (bn == 256) { if (cl == 2) MLDB_LAUNCH(256, 2, __VA_ARGS__); else MLDB_LAUNCH(256, 1, __VA_ARGS__); } \
+    else           { if (cl == 2) MLDB_LAUNCH(128, 2, __VA_ARGS__); else MLDB_LAUNCH(128, 1, __VA_ARGS__); } \
+  } while (0)
+  if (ln)                           { if (cl == 2) MLDB_LAUNCH(256, 2, EPI_LN); else MLDB_LAUNCH(256, 1, EPI_LN); }
+  else if (fast && g.act == ACT_GELU) MLDB_LAUNCH_SHAPE(EPI_FAST, ACT_GELU);
+  else if (fast)                      MLDB_LAUNCH_SHAPE(EPI_FAST);
+  else                                MLDB_LAUNCH_SHAPE(EPI_GENERIC);
+#undef MLDB_LAUNCH_SHAPE
 #undef MLDB_LAUNCH
   return true;
 }
@@ -1189,32 +1201,67 @@ bool tc_ffn_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, co
   if (g1.in_group < g1.M || g1.out_group != 0 || g1.out_off != 0) return false;
   return true;
 }
-bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, cudaStream_t st) {
+// One launch of the fused kernel over rows [row0, row0 + M) of the operands.  split > 1: hidden-split mode
+// (partial products into `partial`, see FfnParams).
+static bool ffn_launch(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, int64_t row0, int M, int split,
+                       float* partial, cudaStream_t st) {
   CUtensorMap mXh, mXl, mW1h, mW1l, mW2h, mW2l, mOh, mOl;
-  const int m_tiles = (g1.M + BM - 1) / BM;
+  const int m_tiles = (M + BM - 1) / BM;
   const int cg = (m_tiles >= 2 && c->sm_count % 2 == 0) ? 2 : 1;
-  const bool ok = make_map(c, &mXh, g1.a1.hi, g1.M, g1.K1, BM) && make_map(c, &mXl, g1.a1.lo(), g1.M, g1.K1, BM) &&
+  const __half* xh = g1.a1.hi + row0 * g1.a1.cols;
+  __half* oh = l2.out.hi + row0 * l2.out.cols;
+  const bool ok = make_map(c, &mXh, xh, M, g1.K1, BM) && make_map(c, &mXl, xh + g1.a1.plane_stride, M, g1.K1, BM) &&
                   make_map(c, &mW1h, g1.w.w, g1.w.N, g1.w.K, FfnCfg<1>::CHUNK / cg) &&
                   make_map(c, &mW1l, g1.w.w + g1.w.plane_stride, g1.w.N, g1.w.K, FfnCfg<1>::CHUNK / cg) &&
                   make_map(c, &mW2h, g2.w.w, g2.w.N, g2.w.K, 256 / cg) &&
                   make_map(c, &mW2l, g2.w.w + g2.w.plane_stride, g2.w.N, g2.w.K, 256 / cg) &&
-                  make_map_out(c, &mOh, l2.out.hi, g1.M, 256, l2.out.cols) &&
-                  make_map_out(c, &mOl, l2.out.lo(), g1.M, 256, l2.out.cols);
-  if (!ok) return map_fail("ffn", g1.M, g1.w.N, g1.w.K);
+                  make_map_out(c, &mOh, oh, M, 256, l2.out.cols) &&
+                  make_map_out(c, &mOl, oh + l2.out.plane_stride, M, 256, l2.out.cols);
+  if (!ok) return map_fail("ffn", M, g1.w.N, g1.w.K);
   FfnParams p{};
-  p.M = g1.M; p.m_tiles = m_tiles; p.n_chunks = g1.w.N / FfnCfg<1>::CHUNK;
+  p.M = M; p.m_tiles = m_tiles; p.n_chunks = g1.w.N / FfnCfg<1>::CHUNK;
+  p.split = split; p.partial = partial;
   p.inv_s1 = g1.w.inv_scale; p.inv_s2 = g2.w.inv_scale;
   p.b1 = g1.w.bias; p.b2 = g2.w.bias; p.gamma = l2.gamma; p.beta = l2.beta;
-  p.res_hi = l2.res.hi; p.res_lo = l2.res.hi ? l2.res.lo() : nullptr; p.ld_res = l2.res.cols;
-  p.out_hi = l2.out.hi; p.out_lo = l2.out.lo(); p.ld_out = l2.out.cols;
+  p.res_hi = l2.res.hi ? l2.res.hi + row0 * l2.res.cols : nullptr;
+  p.res_lo = l2.res.hi ? l2.res.hi + l2.res.plane_stride + row0 * l2.res.cols : nullptr; p.ld_res = l2.res.cols;
+  p.out_hi = oh; p.out_lo = oh + l2.out.plane_stride; p.ld_out = l2.out.cols;
   p.tma_out = 1;
   const int groups = (m_tiles + cg - 1) / cg;
-  const int ncl = groups < c->sm_count / cg ? groups : c->sm_count / cg;
+  const int ncl = split > 1 ? groups * split : (groups < c->sm_count / cg ? groups : c->sm_count / cg);
   if (cg == 2)
     launch_pdl_cluster(k_ffn_tc<2>, dim3(ncl * 2), dim3(NUM_THREADS), FfnCfg<2>::SMEM_BYTES, st, 2, mXh, mXl, mW1h, mW1l,
                        mW2h, mW2l, mOh, mOl, p);
   else
     launch_pdl(k_ffn_tc<1>, dim3(ncl), dim3(NUM_THREADS), FfnCfg<1>::SMEM_BYTES, st, mXh, mXl, mW1h, mW1l, mW2h, mW2l,
                mOh, mOl, p);
+  return true;
+}
+
+// Rows of the last, partial round of m-tile pairs and the hidden split that spreads them over the idle SMs
+// (0 rows: no tail handling - the tile count fills whole rounds, or the last round is more than half full).
+void tc_ffn_tail_plan(const TcCtx* c, int M, int n_chunks, int* tail_rows, int* split) {
+  *tail_rows = 0; *split = 1;
+  const int m_tiles = (M + BM - 1) / BM;
+  if (c->sm_count % 2 || m_tiles < c->sm_count) return;        // pairs only, at least one full round
+  const int slots = c->sm_count / 2, pairs = (m_tiles + 1) / 2, rem = pairs % slots;
+  if (rem == 0 || 2 * rem > slots) return;
+  int sp = 1;
+  while (sp * 2 * rem <= slots && n_chunks % (sp * 2) == 0) sp *= 2;
+  if (sp == 1) return;
+  *split = sp;
+  *tail_rows = M - (pairs - rem) * 2 * BM;
+}
+
+// l2.c == nullptr.  tail_partial: fp32 [split][tail_rows][256] scratch of the caller or nullptr.
+bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, float* tail_partial, cudaStream_t st,
+            int* tail_rows_out, int* tail_split_out) {
+  int tail_rows = 0, split = 1;
+  if (tail_partial) tc_ffn_tail_plan(c, g1.M, g1.w.N / FfnCfg<1>::CHUNK, &tail_rows, &split);
+  if (tail_rows_out) *tail_rows_out = tail_rows;
+  const int main_rows = g1.M - tail_rows;
+  if (!ffn_launch(c, g1, g2, l2, 0, main_rows, 1, nullptr, st)) return false;
+  if (tail_rows > 0 && !ffn_launch(c, g1, g2, l2, main_rows, tail_rows, split, tail_partial, st)) return false;
+  if (tail_split_out) *tail_split_out = split;
   return true;
 }

@@ -223,6 +223,12 @@ int mldb_profile_op(mldb_handle* h, const char* op, int32_t B, int32_t S_ctx, in
 int mldb_profile_steps(mldb_handle* h, const void* cond, const float* init_noise, int32_t B, int32_t S_ctx,
                        float* ms_out);
 
+/* Debug aid: in-kernel timeline of the tcgen05 kernels (GEMM / FFN / attention).  enable != 0 starts recording:
+ * every warp role of CTA 0 appends {tag | warp << 16 | aux << 24, SM clock} at its pipeline events (tags in the
+ * kernels' tl_event calls).  enable == 0 copies the events into out (HOST int64[2 * cap]), sets *count and stops.
+ * Process-wide; recording costs one atomic per event in CTA 0 only. */
+int mldb_debug_timeline(int32_t enable, int64_t* out, int32_t cap, int32_t* count);
+
 /* Debug aid for the kernel unit tests: y = act(A W^T + b), or LayerNorm(A W^T + b + R) when gamma is
  * given, through the engine's GEMM operators (use_tc: 1 = tcgen05 path, 0 = CUDA-core path).
  * A [M,K], R [M,N], out [M,N]: fp32 DEVICE; W [N,K], bias/gamma/beta [N]: fp32 HOST.  0 < K1 < K feeds

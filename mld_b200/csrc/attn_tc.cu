@@ -56,6 +56,7 @@ struct AtcParams {
   const int32_t* lengths; int kv_prefix, len_mod, seq0;
   __half* out_hi; __half* out_lo; int ld_out;
   float scale_log2e;       // log2(e) / sqrt(head_dim)
+  long long* tl;           // debug timeline (nullptr normally)
 };
 
 struct Item { int s, h, qt; };
@@ -99,6 +100,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 12);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  int tl_n = 0;                                       // debug-timeline event counter of this warp
   const int items = p.nseq * p.heads * p.n_qt;
   const int nlocal = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nkb = p.nkb, SB = p.SB, QB = p.QB, RS = p.RS;
@@ -130,6 +132,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       const Item it = decode_item((int)blockIdx.x + j * (int)gridDim.x, p);
       const int qb = j % QB;
       mbar_wait(smem_u32(&q_empty[qb]), (((uint32_t)(j / QB)) & 1u) ^ 1u);
+      tl_event(p.tl, tl_n, 20, j);                                     // producer: Q(j) buffer free, loads issued
       if (elect_one()) {
         const uint32_t full = smem_u32(&q_full[qb]);
         mbar_expect_tx(full, (uint32_t)q_bytes);
@@ -167,6 +170,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       for (int kb = 0; kb < nkb; ++kb, ++rc) {
         const int sl_i = rc % RS;
         mbar_wait(smem_u32(&r_empty[sl_i]), (((uint32_t)(rc / RS)) & 1u) ^ 1u);
+        tl_event(p.tl, tl_n, 21, j);                                   // producer: slot free for V(j, kb)
         if (elect_one()) {
           const bool last = kb == nkb - 1;
           const int rows = last ? p.rem : KBLK;
@@ -203,11 +207,13 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       // phases of its barrier one by one, whatever SB is (a parity wait must never lag two phases).
       if (j >= SB) mbar_wait(smem_u32(&s_empty[(j - SB) & 1]), ((uint32_t)(j - SB) >> 1) & 1u);
       tc_fence_after();
+      tl_event(p.tl, tl_n, 22, j);                                     // MMA: Q(j) landed, score buffer free
       const uint32_t qbase = smem_u32(sQ + qb * q_bytes);
       for (int kb = 0; kb < nkb; ++kb, ++rc) {
         const int sl_i = rc % RS;
         mbar_wait(smem_u32(&r_full[sl_i]), ((uint32_t)(rc / RS)) & 1u);
         tc_fence_after();
+        tl_event(p.tl, tl_n, 23, j);                                   // MMA: K(j, kb) landed, S MMAs issue
         if (elect_one()) {
           const int n = kb == nkb - 1 ? p.rem : KBLK;
           const uint32_t idesc_s = make_idesc(n, 128, false);
@@ -236,14 +242,17 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
     };
     auto issue_pv = [&](int j) {                      // O(j) = P V, block by block
       const int ob = j & 1;
+      tl_event(p.tl, tl_n, 24, j);                                     // MMA: S chains issued, turning to PV(j)
       mbar_wait(smem_u32(&o_empty[ob]), (((uint32_t)j >> 1) & 1u) ^ 1u);
       tc_fence_after();
       for (int kb = 0; kb < nkb; ++kb, ++rc) {
         const int pseq = j * nkb + kb, pb = pseq & 1;
         const int sl_i = rc % RS;
         mbar_wait(smem_u32(&p_full[pb]), ((uint32_t)pseq >> 1) & 1u);
+        tl_event(p.tl, tl_n, 25, j);                                   // MMA: P(j, kb) written
         mbar_wait(smem_u32(&r_full[sl_i]), ((uint32_t)(rc / RS)) & 1u);
         tc_fence_after();
+        tl_event(p.tl, tl_n, 26, j);                                   // MMA: V(j, kb) landed, PV MMAs issue
         if (elect_one()) {
           const int nks = (kb == nkb - 1 ? p.rem : KBLK) / 16;
           const uint32_t vbase = smem_u32(sR + sl_i * SLOT_BYTES);
@@ -294,8 +303,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       int nk = p.Lk;
       if (p.lengths) nk = min(p.Lk, p.kv_prefix + p.lengths[p.len_mod > 0 ? (p.seq0 + it.s) % p.len_mod : it.s]);
       const uint32_t s_addr = tmem_base + lane_addr + (uint32_t)(sb * scols);
+      tl_event(p.tl, tl_n, 30, j);                                     // softmax: waiting for S(j)
       mbar_wait(smem_u32(&s_full[g]), ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
+      tl_event(p.tl, tl_n, 31, j);                                     // softmax: S(j) ready
       // ---- pass 1: maximum over this warp's 16-key chunks (c = hf, hf + 2, ...), then over both halves
       float mx = -INFINITY;
       if (active) {
@@ -308,6 +319,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
         }
       }
       red_max[hf * 128 + row] = mx;
+      tl_event(p.tl, tl_n, 32, j);                                     // softmax: pass 1 done
       group_sync();
       mx = fmaxf(mx, red_max[(hf ^ 1) * 128 + row]);
       const float mc = (mx == -INFINITY) ? 0.0f : mx * sc;
@@ -352,11 +364,13 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&s_empty[g]));     // the score buffer may be overwritten
       red_sum[hf * 128 + row] = sum;
+      tl_event(p.tl, tl_n, 33, j);                                     // softmax: pass 2 done (P written)
       group_sync();
       sum += red_sum[(hf ^ 1) * 128 + row];
       // ---- this warp's half of the O row / sum -> split16 -> global
       mbar_wait(smem_u32(&o_full[ob]), ((uint32_t)j >> 1) & 1u);
       tc_fence_after();
+      tl_event(p.tl, tl_n, 34, j);                                     // softmax: O(j) ready
       if (active) {
         const float inv = 1.0f / sum;
         constexpr int OC = HD / 2;                           // O columns per warp
@@ -382,6 +396,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       }
       tc_fence_before();
       __syncwarp();
+      tl_event(p.tl, tl_n, 35, j);                                     // softmax: epilogue done
       if (lane == 0) mbar_arrive(smem_u32(&o_empty[ob]));
     }
   }
@@ -473,6 +488,7 @@ bool tc_attention(const AttnArgs& a, cudaStream_t st) {
   p.lengths = a.lengths; p.kv_prefix = a.kv_prefix; p.len_mod = a.len_mod; p.seq0 = a.seq0;
   p.out_hi = a.out.hi; p.out_lo = a.out.lo(); p.ld_out = a.out.cols;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)a.hd);
+  p.tl = tc::mldb_timeline_buffer();
   const int items = a.nseq * a.heads * p.n_qt;
   const int grid = items < g_sm_count ? items : g_sm_count;
   if (a.hd == 64)

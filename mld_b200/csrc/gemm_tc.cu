@@ -56,6 +56,7 @@ struct TcParams {
   const __half* res_hi; const __half* res_lo; int ld_res;
   const float* gamma; const float* beta;
   int tma_out;   // the epilogue drains through TMA stores (maps tmOh / tmOl cover out + out_col0)
+  long long* tl; // debug timeline (nullptr normally)
 };
 
 constexpr int EPI_WARPS = 8;
@@ -201,6 +202,28 @@ __device__ __forceinline__ void ln_stats_chunk(uint32_t (&r)[32], const uint4 (&
     }
   }
 }
+// the same without a residual operand (it arrived through the accumulator: [W | I] weights)
+__device__ __forceinline__ void ln_stats_chunk_nores(uint32_t (&r)[32], const float* bch, float sc, float shiftK,
+                                                     float& s1, float& s2) {
+  const float4* b4 = reinterpret_cast<const float4*>(bch);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float4 b = b4[i];
+    const float x0 = fmaf(__uint_as_float(r[4 * i + 0]), sc, b.x), x1 = fmaf(__uint_as_float(r[4 * i + 1]), sc, b.y);
+    const float x2 = fmaf(__uint_as_float(r[4 * i + 2]), sc, b.z), x3 = fmaf(__uint_as_float(r[4 * i + 3]), sc, b.w);
+    const float d0 = x0 - shiftK, d1 = x1 - shiftK, d2 = x2 - shiftK, d3 = x3 - shiftK;
+    s1 += (d0 + d1) + (d2 + d3);
+    s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
+    r[4 * i + 0] = __float_as_uint(x0); r[4 * i + 1] = __float_as_uint(x1);
+    r[4 * i + 2] = __float_as_uint(x2); r[4 * i + 3] = __float_as_uint(x3);
+  }
+}
+__device__ __forceinline__ float ln_shift_nores(const uint32_t (&r)[32], const float* bch, float sc) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc += fmaf(__uint_as_float(r[i]), sc, bch[i]);
+  return acc * (1.0f / 32);
+}
 // Shift of the one-pass variance: the mean of the row's first 32 pre-norm values.  (A single value - the
 // first element - can sit 3 sigma off the mean and E[(x-K)^2] - E[x-K]^2 then cancels ~3 bits.)
 __device__ __forceinline__ float ln_shift(const uint32_t (&r)[32], const uint4 (&rh)[4], const uint4 (&rl)[4],
@@ -301,6 +324,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
+  int tl_n = 0;                                     // debug-timeline event counter of this warp
   const int rank = CG > 1 ? (int)cluster_ctarank() : 0;
   const int ncl = (int)gridDim.x / CG, cid = (int)blockIdx.x / CG;          // clusters, this CTA's cluster
   const int ngroups = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;               // (m-group, n) items
@@ -341,6 +365,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     for (int j = 0; j < nlocal; ++j) {
       int m0, n0;
       decode_item(j, p, BN, CG, rank, m0, n0);
+      tl_event(p.tl, tl_n, 1, j);                                    // producer: tile j begins
       for (int kb = 0; kb < p.kblocks; ++kb, ++kbg) {
         const int s = kbg % STAGES;
         const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
@@ -391,6 +416,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         if (CG == 1) mbar_wait(smem_u32(&bar_tempty[as]), (((uint32_t)it >> 1) & 1u) ^ 1u);   // epilogue drained it
         else mbar_wait_cluster(smem_u32(&bar_tempty[as]), (((uint32_t)it >> 1) & 1u) ^ 1u);
         tc_fence_after();
+        tl_event(p.tl, tl_n, 2, it);                                   // MMA: accumulator stage free, tile `it` begins
         const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
         const int nkb = p.kblocks;
         for (int kb = 0; kb < nkb; ++kb, ++kbg) {
@@ -425,6 +451,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           }
           __syncwarp();
         }
+        tl_event(p.tl, tl_n, 3, it);                                   // MMA: tile `it` issued
       }
     }
   } else if constexpr (!LN) {
@@ -448,6 +475,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       const int rows_valid = min(32, p.M - wrow0);   // <= 0: nothing to write
       mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
+      tl_event(p.tl, tl_n, 4, it);                                     // epilogue: accumulator of tile `it` ready
       int seq = 0, pos = m;
       if (row_ok && p.in_group < p.M) { seq = m / p.in_group; pos = m - seq * p.in_group; }
       const int64_t orow = (int64_t)seq * p.out_group + p.out_off + pos;
@@ -514,6 +542,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       // this warp is done reading the accumulator stage: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
+      tl_event(p.tl, tl_n, 5, it);                                     // epilogue: tile `it` drained
       if (lane == 0) { if (CG == 1) mbar_arrive(smem_u32(&bar_tempty[as])); else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[as]), 0)); }
     }
     if (CG == 2 && lane == 0) tma_store_wait_read<0>();   // staging fully read by the TMA engine
@@ -550,8 +579,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         load_plane_issue(rbh + 32, p.ld_res, rows_valid, lane, gBh);
         load_plane_issue(rbl + 32, p.ld_res, rows_valid, lane, gBl);
       }
+      tl_event(p.tl, tl_n, 6, it);                                     // LN epilogue: residual loads issued, waiting for tile `it`
       mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
+      tl_event(p.tl, tl_n, 4, it);
       float s1 = 0.0f, s2 = 0.0f, shiftK = 0.0f;
       const float sc = p.inv_scale;
 #pragma unroll 1
@@ -565,13 +596,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
             load_plane_issue(rbh + (c + 2) * 32, p.ld_res, rows_valid, lane, gAh);
             load_plane_issue(rbl + (c + 2) * 32, p.ld_res, rows_valid, lane, gAl);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
         }
         tmem_ld32(trow + c * 32, r);
-        if (c == 0) shiftK = ln_shift(r, rh, rl, s_bias, sc);
-        ln_stats_chunk(r, rh, rl, s_bias + c * 32, sc, shiftK, s1, s2);
+        if (has_res) {
+          if (c == 0) shiftK = ln_shift(r, rh, rl, s_bias, sc);
+          ln_stats_chunk(r, rh, rl, s_bias + c * 32, sc, shiftK, s1, s2);
+        } else {
+          if (c == 0) shiftK = ln_shift_nores(r, s_bias, sc);
+          ln_stats_chunk_nores(r, s_bias + c * 32, sc, shiftK, s1, s2);
+        }
         tmem_st32(trow + c * 32, r);
         // ---- chunk c + 1 (buffers B)
         if (has_res) {
@@ -583,12 +616,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           }
         }
         tmem_ld32(trow + (c + 1) * 32, r);
-        ln_stats_chunk(r, rh, rl, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
+        if (has_res) ln_stats_chunk(r, rh, rl, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
+        else ln_stats_chunk_nores(r, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
         tmem_st32(trow + (c + 1) * 32, r);
       }
       const float e1 = s1 * (1.0f / 256), e2 = s2 * (1.0f / 256);
       const float rstd = rsqrtf(fmaxf(e2 - e1 * e1, 0.0f) + 1e-5f);
       const float nb_ = -(shiftK + e1) * rstd;       // y = x * rstd + nb_
+      tl_event(p.tl, tl_n, 7, it);                                     // LN epilogue: statistics pass done
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         tmem_ld32(trow + c * 32, r);
@@ -606,6 +641,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
+      tl_event(p.tl, tl_n, 5, it);
       if (lane == 0) { if (CG == 1) mbar_arrive(smem_u32(&bar_tempty[as])); else mbar_arrive_cluster(mapa_u32(smem_u32(&bar_tempty[as]), 0)); }
     }
     if (CG == 2 && lane == 0) tma_store_wait_read<0>();
@@ -638,6 +674,7 @@ struct FfnParams {
   // LayerNorm then run as a row kernel that sums the slices in order.  split == 1: the normal fused kernel.
   int split;
   float* partial;
+  long long* tl;
   float inv_s1, inv_s2;
   const float* b1; const float* b2; const float* gamma; const float* beta;
   const __half* res_hi; const __half* res_lo; int ld_res;
@@ -695,6 +732,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
+  int tl_n = 0;                                     // debug-timeline event counter of this warp
   const int rank = CG > 1 ? (int)cluster_ctarank() : 0;
   const int ncl = (int)gridDim.x / CG, cid = (int)blockIdx.x / CG;
   const int ngroups = (p.m_tiles + CG - 1) / CG;
@@ -830,6 +868,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
             const int b = g1 & 1;
             wait_epi(&bar_a1empty[b], (((uint32_t)g1 >> 1) & 1u) ^ 1u);
             tc_fence_after();
+            tl_event(p.tl, tl_n, 10, i);                             // MMA: F1(i) may start (acc1 buffer free)
             const uint32_t tacc = tmem_base + (uint32_t)(b * Cfg::CHUNK);
             for (int kb = 0; kb < 4; ++kb, ++kbg) {
               const int s = kbg % STAGES;
@@ -846,8 +885,10 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
               wait_epi(bar_a2empty, ((uint32_t)j & 1u) ^ 1u);
               tc_fence_after();
             }
+            tl_event(p.tl, tl_n, 11, i - 1);                         // MMA: F1 chain issued, waiting for Hs(i - 1)
             wait_epi(bar_hfull, (uint32_t)g2 & 1u);
             tc_fence_after();
+            tl_event(p.tl, tl_n, 12, i - 1);                         // MMA: F2(i - 1) starts
             const uint32_t tacc = tmem_base + 2u * Cfg::CHUNK;
             for (int kb = 0; kb < 2; ++kb, ++kbg) {
               const int s = kbg % STAGES;
@@ -879,6 +920,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         const int b = g & 1;
         mbar_wait(smem_u32(&bar_a1full[b]), ((uint32_t)g >> 1) & 1u);
         tc_fence_after();
+        tl_event(p.tl, tl_n, 13, c);                                 // E1(c): acc1 ready
         const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * Cfg::CHUNK + hf * 64);
         uint32_t PH[2][16], PL[2][16];
 #pragma unroll
@@ -903,6 +945,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
           }
         fence_proxy_async_smem();                    // generic-proxy writes -> tcgen05.mma reads
         __syncwarp();
+        tl_event(p.tl, tl_n, 14, c);                                 // E1(c): Hs written
         if (lane == 0) arrive_leader(bar_hfull);
       }
       if (split_mode) {
@@ -955,6 +998,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       }
       mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);      // all F2 MMAs retired: acc2 complete, Hs idle
       tc_fence_after();
+      tl_event(p.tl, tl_n, 15, j);                                   // LN tail: acc2 ready
       float s1 = 0.0f, s2 = 0.0f, shiftK = 0.0f;
       const float sc = p.inv_s2;
 #pragma unroll
@@ -1008,6 +1052,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       epi_bar_sync();
       tc_fence_before();
       __syncwarp();
+      tl_event(p.tl, tl_n, 16, j);                                   // LN tail done
       if (lane == 0) arrive_leader(bar_a2empty);
     }
   }
@@ -1128,6 +1173,7 @@ static void fill_params(const GemmArgs& g, const LnArgs* ln, int bn, TcParams* o
   }
   p.m_tiles = (g.M + BM - 1) / BM;
   p.n_tiles = (g.w.N + bn - 1) / bn;
+  p.tl = tc::mldb_timeline_buffer();
   *out = p;
 }
 
@@ -1220,7 +1266,7 @@ static bool ffn_launch(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const L
   if (!ok) return map_fail("ffn", M, g1.w.N, g1.w.K);
   FfnParams p{};
   p.M = M; p.m_tiles = m_tiles; p.n_chunks = g1.w.N / FfnCfg<1>::CHUNK;
-  p.split = split; p.partial = partial;
+  p.split = split; p.partial = partial; p.tl = tc::mldb_timeline_buffer();
   p.inv_s1 = g1.w.inv_scale; p.inv_s2 = g2.w.inv_scale;
   p.b1 = g1.w.bias; p.b2 = g2.w.bias; p.gamma = l2.gamma; p.beta = l2.beta;
   p.res_hi = l2.res.hi ? l2.res.hi + row0 * l2.res.cols : nullptr;

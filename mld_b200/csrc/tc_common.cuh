@@ -251,6 +251,20 @@ __device__ __forceinline__ void split2(float x0, float x1, uint32_t& hi, uint32_
   lo = *reinterpret_cast<const uint32_t*>(&l2);
 }
 
+// Debug timeline (mldb_debug_timeline): when `tl` is non-null, lane 0 of the calling warp of CTA 0 stores
+// (tag | aux << 24, SM clock) into its warp's private slot array (plain stores, no atomics: ~10 cycles per
+// event).  Layout: [32 warps][TL_CAPW events][2]; `n` is the warp's own event counter (a register).
+constexpr int TL_CAPW = 512;
+__device__ __forceinline__ void tl_event(long long* tl, int& n, int tag, int aux = 0) {
+  if (tl != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && n < TL_CAPW) {
+    long long* e = tl + ((size_t)(threadIdx.x >> 5) * TL_CAPW + n) * 2;
+    e[0] = (long long)tag | ((long long)aux << 24);
+    e[1] = clock64();
+    ++n;
+  }
+}
+long long* mldb_timeline_buffer();   // engine.cu: the device buffer while a timeline is being recorded, else nullptr
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                         const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,

@@ -182,7 +182,7 @@ def test_full_size_batch_invariance_and_oracle_subset(engines):
     big = eng.sample(ctx, noise, lengths, want=("latents", "feats", "joints"))
     assert torch.equal(big["latents"][:, idx[:3]], small["latents"][:, :3])
     assert _rel(big["latents"][:, idx], small["latents"]) < 5e-6
-    assert _joint_err(big["joints"][idx], [small["joints"][i, :n] for i, n in enumerate(sub_len)], sub_len) < 1e-4
+    assert _joint_err(big["joints"][idx], [small["joints"][i, :n].cpu() for i, n in enumerate(sub_len)], sub_len) < 1e-4
     assert float(big["feats"][1, 120:].abs().max()) == 0.0
     jo, _, _ = O.mld_forward(engines["dsd"], O.DenoiserCfg(), engines["vsd"], O.VaeCfg(), O.DDIMScheduler(), 50,
                              sub_ctx, noise[idx], sub_len, engines["mean"], engines["std"])

@@ -284,9 +284,6 @@ int mldb_reset_kernel_stats(mldb_handle* h);
  *   "gemm"       "tc" | "simt"          tcgen05 kernels (default) or the CUDA-core reference kernels  MLDB_GEMM
  *   "attn"       "tc" | "mma" | "simt"  attention core: tcgen05 (default), mma.sync, CUDA cores       MLDB_ATTN
  *   "ffn_fused"  0 | 1                  fused FFN kernel k_ffn_tc (default 1)
- *   "ffn_tail"   0 | 1                  spread the fused FFN's last partial round of m-tiles over the idle SMs by
- *                                       a hidden-dimension split (default 1; re-associates the hidden sum of those
- *                                       rows: results agree to fp32 rounding, not bit for bit)         MLDB_FFN_TAIL
  *   "branches"   1..4                   concurrent sub-batch branches inside a denoiser step (2)      MLDB_BRANCHES
  *   "graph"      0 | 1                  CUDA-graph replay of the step loop (1)                        MLDB_GRAPH
  * Environment only: MLDB_PDL (programmatic dependent launch, 1). */

@@ -25,9 +25,12 @@
 //                    instruction - not by TMEM or MUFU throughput; twice the warps halve an item's latency.)
 //   warp 16          TMA producer: Q tile (own double buffer), then K blocks and V blocks through
 //                    one ring of 64-key slots, in exactly the order the MMA warp consumes them
-//   warp 17          TMEM allocator + MMA issuer: S(j+1) is issued before PV(j) when two score
-//                    buffers fit in TMEM, so the tensor pipe works on the next item while a softmax
-//                    group is busy with this one
+//   warp 17 / 18     the two MMA issuers: warp 17 (also the TMEM allocator) issues the S = Q K^T chains, warp 18
+//                    the O = P V chains.  They work on different accumulators, so nothing orders them but
+//                    the data (with two score buffers S(j+1) runs while a softmax group is busy with item
+//                    j).  One issuer for both was the kernel's pacer: the in-kernel timeline showed ~6.7k
+//                    cycles per item on that warp alone (39 MMAs x ~50 cycles of issue + ~9 barrier waits x
+//                    ~450 cycles), with the softmax warps idle 75 % of the time.
 // TMEM: S buffers (nkb*64 columns each) then two O buffers (head_dim columns each), <= 512 columns.
 #include <stdio.h>
 #include <stdlib.h>
@@ -38,8 +41,8 @@
 namespace {
 using namespace tc;
 
-constexpr int ATC_THREADS = 576;
-constexpr int WARP_TMA = 16, WARP_MMA = 17;
+constexpr int ATC_THREADS = 608;
+constexpr int WARP_TMA = 16, WARP_MMA = 17, WARP_MMA2 = 18;   // S issuer (+ TMEM allocator), PV issuer
 constexpr int RED_BYTES = 2 * 2 * 2 * 128 * 4;   // [group][max | sum][column half][row] exchange buffers
 constexpr int KBLK = 64;                  // keys per block
 constexpr int P_BYTES = 2 * 16384;        // one P block: [128 rows x 64 keys] hi plane + lo plane
@@ -195,25 +198,25 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       load_v(j);
     }
   } else if (warp == WARP_MMA) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc_o = make_idesc(64, 128, true);
-    const uint32_t sP_u = smem_u32(sP);
-    int rc = 0;
-    auto issue_s = [&](int j) {                       // S(j) = Q K^T, block by block
+    // ------------------------------------------------------------------ MMA issuer 1: S(j) = Q K^T, block by block
+    // ring position of K(j, 0): the producer's order is K(0) | K(1) V(0) | K(2) V(1) | ... with two score
+    // buffers, K(0) V(0) | K(1) V(1) | ... with one
+    for (int j = 0; j < nlocal; ++j) {
       const int qb = j % QB, sb = j % SB, g = j & 1;
+      const int rc0 = SB == 2 ? (j == 0 ? 0 : (2 * j - 1) * nkb) : 2 * j * nkb;
       mbar_wait(smem_u32(&q_full[qb]), ((uint32_t)(j / QB)) & 1u);
       // score buffer sb was last read by item j - SB, i.e. by softmax group (j - SB) & 1 as ITS item number
       // (j - SB) >> 1.  The full / empty barriers are per GROUP (not per buffer): every waiter then sees the
       // phases of its barrier one by one, whatever SB is (a parity wait must never lag two phases).
       if (j >= SB) mbar_wait(smem_u32(&s_empty[(j - SB) & 1]), ((uint32_t)(j - SB) >> 1) & 1u);
       tc_fence_after();
-      tl_event(p.tl, tl_n, 22, j);                                     // MMA: Q(j) landed, score buffer free
+      tl_event(p.tl, tl_n, 22, j);                               // MMA: Q(j) landed, score buffer free
       const uint32_t qbase = smem_u32(sQ + qb * q_bytes);
-      for (int kb = 0; kb < nkb; ++kb, ++rc) {
-        const int sl_i = rc % RS;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int rc = rc0 + kb, sl_i = rc % RS;
         mbar_wait(smem_u32(&r_full[sl_i]), ((uint32_t)(rc / RS)) & 1u);
         tc_fence_after();
-        tl_event(p.tl, tl_n, 23, j);                                   // MMA: K(j, kb) landed, S MMAs issue
+        tl_event(p.tl, tl_n, 23, j);                             // MMA: K(j, kb) landed, S MMAs issue
         if (elect_one()) {
           const int n = kb == nkb - 1 ? p.rem : KBLK;
           const uint32_t idesc_s = make_idesc(n, 128, false);
@@ -239,20 +242,26 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
         }
         __syncwarp();
       }
-    };
-    auto issue_pv = [&](int j) {                      // O(j) = P V, block by block
+      tl_event(p.tl, tl_n, 24, j);                               // MMA: S(j) issued
+    }
+  } else if (warp == WARP_MMA2) {
+    // ------------------------------------------------------------------ MMA issuer 2: O(j) = P V, block by block
+    const uint32_t idesc_o = make_idesc(64, 128, true);
+    const uint32_t sP_u = smem_u32(sP);
+    for (int j = 0; j < nlocal; ++j) {
       const int ob = j & 1;
-      tl_event(p.tl, tl_n, 24, j);                                     // MMA: S chains issued, turning to PV(j)
+      // ring position of V(j, 0): after K(j + 1) with two score buffers - except for the last item, which has none
+      const int rc0 = (SB == 2 && j + 1 < nlocal) ? (2 * j + 2) * nkb : (2 * j + 1) * nkb;
       mbar_wait(smem_u32(&o_empty[ob]), (((uint32_t)j >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      for (int kb = 0; kb < nkb; ++kb, ++rc) {
+      for (int kb = 0; kb < nkb; ++kb) {
         const int pseq = j * nkb + kb, pb = pseq & 1;
-        const int sl_i = rc % RS;
+        const int rc = rc0 + kb, sl_i = rc % RS;
         mbar_wait(smem_u32(&p_full[pb]), ((uint32_t)pseq >> 1) & 1u);
-        tl_event(p.tl, tl_n, 25, j);                                   // MMA: P(j, kb) written
+        tl_event(p.tl, tl_n, 25, j);                             // MMA: P(j, kb) written
         mbar_wait(smem_u32(&r_full[sl_i]), ((uint32_t)(rc / RS)) & 1u);
         tc_fence_after();
-        tl_event(p.tl, tl_n, 26, j);                                   // MMA: V(j, kb) landed, PV MMAs issue
+        tl_event(p.tl, tl_n, 26, j);                             // MMA: V(j, kb) landed, PV MMAs issue
         if (elect_one()) {
           const int nks = (kb == nkb - 1 ? p.rem : KBLK) / 16;
           const uint32_t vbase = smem_u32(sR + sl_i * SLOT_BYTES);
@@ -276,12 +285,6 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
         }
         __syncwarp();
       }
-    };
-    if (SB == 2 && nlocal > 0) issue_s(0);
-    for (int j = 0; j < nlocal; ++j) {
-      if (SB == 2) { if (j + 1 < nlocal) issue_s(j + 1); }   // S(j+1) overlaps softmax(j)
-      else issue_s(j);
-      issue_pv(j);
     }
   } else {
     // ------------------------------------------------------------------ softmax + epilogue groups

@@ -220,20 +220,6 @@ static int pack_named(mldb_handle* h, const std::string& wkey, const std::string
   const float* b = bkey.empty() ? nullptr : rt(h, bkey).host.data() + row0;
   return pack_linear(h, w.host.data() + (size_t)row0 * K, nrows, K, b, out, pad_k ? (K + 63) / 64 * 64 : 0);
 }
-// out-projection with the residual folded into the GEMM: W' = [W | I] along K (nn.Linear [N, K] -> [N, K + N]),
-// so that [att | x] . W'^T = att . W^T + x: the residual add of `x + attn(x)` (cross_attention.py:262-263)
-// runs on the tensor pipe (x_hi . I and x_lo . I are exact in fp32) and the LayerNorm epilogue no longer
-// fetches and transposes the residual tile.  The power-of-two weight scale covers the identity too.
-static int pack_named_plus_identity(mldb_handle* h, const std::string& wkey, const std::string& bkey, LinW* out) {
-  const RawTensor& w = rt(h, wkey);
-  const int N = (int)w.shape[0], K = (int)w.shape.back();
-  std::vector<float> cat((size_t)N * (K + N), 0.0f);
-  for (int n = 0; n < N; ++n) {
-    memcpy(&cat[(size_t)n * (K + N)], &w.host[(size_t)n * K], K * sizeof(float));
-    cat[(size_t)n * (K + N) + K + n] = 1.0f;
-  }
-  return pack_linear(h, cat.data(), N, K + N, rt(h, bkey).host.data(), out);
-}
 static int pack_ln(mldb_handle* h, const std::string& p, int d, LnW* out) {
   TRY(upload_f32(h, rt(h, p + "weight").host.data(), d, &out->g));
   TRY(upload_f32(h, rt(h, p + "bias").host.data(), d, &out->b));
@@ -242,7 +228,6 @@ static int pack_ln(mldb_handle* h, const std::string& p, int d, LnW* out) {
 static int pack_enc_layer(mldb_handle* h, const std::string& p, int d, EncW* w) {
   TRY(pack_named(h, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", &w->in_proj));
   TRY(pack_named(h, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", &w->out_proj));
-  if (d == 256) TRY(pack_named_plus_identity(h, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", &w->out_proj_r));
   TRY(pack_named(h, p + "linear1.weight", p + "linear1.bias", &w->l1));
   TRY(pack_named(h, p + "linear2.weight", p + "linear2.bias", &w->l2));
   TRY(pack_ln(h, p + "norm1.", d, &w->n1));
@@ -252,10 +237,6 @@ static int pack_enc_layer(mldb_handle* h, const std::string& p, int d, EncW* w) 
 static int pack_dec_layer(mldb_handle* h, const std::string& p, int d, DecW* w) {
   TRY(pack_named(h, p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", &w->sa_in));
   TRY(pack_named(h, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", &w->sa_out));
-  if (d == 256) {
-    TRY(pack_named_plus_identity(h, p + "self_attn.out_proj.weight", p + "self_attn.out_proj.bias", &w->sa_out_r));
-    TRY(pack_named_plus_identity(h, p + "multihead_attn.out_proj.weight", p + "multihead_attn.out_proj.bias", &w->ca_out_r));
-  }
   // packed in_proj rows are [Wq; Wk; Wv] (nn.MultiheadAttention): q part and kv part
   TRY(pack_named(h, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", &w->ca_q, 0, d));
   TRY(pack_named(h, p + "multihead_attn.in_proj_weight", p + "multihead_attn.in_proj_bias", &w->ca_kv, d, 2 * d));
@@ -408,20 +389,8 @@ static void op_attn(mldb_handle* h, const AttnArgs& a, cudaStream_t st) {
 static void op_ffn(mldb_handle* h, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, float* cf32, cudaStream_t st) {
   if (h->use_tc && tc_ffn_supported(h->tc, g1, g2, l2)) {
     // one launch: the hidden activations stay in shared memory / TMEM (gemm_tc.cu k_ffn_tc)
-    // The m-tiles of the last, partial round (316 tiles on 74 CTA pairs = 2.13 rounds) are spread over the idle
-    // SMs by a hidden-dimension split (option ffn_tail); their residual + LayerNorm finish in a row kernel.
-    int tail_rows = 0, tail_split = 1;
-    if (!tc_ffn(h->tc, g1, g2, l2, h->ffn_tail ? cf32 : nullptr, st, &tail_rows, &tail_split)) h->op_failed = true;
+    if (!tc_ffn(h->tc, g1, g2, l2, st)) h->op_failed = true;
     kcount(h, MLDB_KSTAT_FFN_TC);
-    if (tail_rows > 0) {
-      kcount(h, MLDB_KSTAT_FFN_TC);
-      const int64_t r0 = g1.M - tail_rows;
-      LnArgs lt = l2;
-      lt.c = cf32; lt.ldc = 256; lt.c_parts = tail_split; lt.c_part_stride = (int64_t)tail_rows * 256;
-      lt.res = rows_of(l2.res, r0, tail_rows); lt.out = rows_of(l2.out, r0, tail_rows); lt.M = tail_rows;
-      simt_ln(lt, st);
-      kcount(h, MLDB_KSTAT_LN_SIMT);
-    }
     return;
   }
   op_gemm(h, g1, st);
@@ -497,17 +466,14 @@ static StackWs ws_slice(const StackWs& ws, int s0, int n) {
   w.sx = sel(ws.sx); w.sq = sel(ws.sq); w.satt = sel(ws.satt); w.sx1 = sel(ws.sx1); w.sh = sel(ws.sh); w.sout = sel(ws.sout);
   return w;
 }
-// out-projection + residual + LayerNorm: with `w_r` ([W | I], see pack_named_plus_identity) the residual is a
-// second A source of the GEMM, else it is added in the epilogue
-static void out_proj_ln(mldb_handle* h, const LinW& w, const LinW& w_r, const LnW& n, ActBuf att, ActBuf res, ActBuf xout,
-                        int M, int d, float* cf32, cudaStream_t st) {
-  GemmArgs g; g.a1 = att; g.K1 = d; g.M = M;
-  LnArgs l; l.gamma = n.g; l.beta = n.b; l.M = M; l.d = d; l.out = xout;
-  if (h->res_mma && w_r.w) { g.a2 = res; g.K2 = d; g.w = w_r; }
-  else { g.w = w; l.res = res; }
+// out-projection + residual + LayerNorm (cross_attention.py:262-263)
+static void out_proj_ln(mldb_handle* h, const LinW& w, const LnW& n, ActBuf att, ActBuf res, ActBuf xout, int M, int d,
+                        float* cf32, cudaStream_t st) {
+  GemmArgs g; g.a1 = att; g.K1 = d; g.M = M; g.w = w;
+  LnArgs l; l.res = res; l.gamma = n.g; l.beta = n.b; l.M = M; l.d = d; l.out = xout;
   op_gemm_ln(h, g, l, cf32, st);
 }
-static void self_attn_block(mldb_handle* h, const LinW& in_proj, const LinW& out_proj, const LinW& out_proj_r, const LnW& n,
+static void self_attn_block(mldb_handle* h, const LinW& in_proj, const LinW& out_proj, const LnW& n,
                             ActBuf xin, ActBuf xout, StackWs& ws, const SeqInfo& si, int heads,
                             cudaStream_t st) {
   const int d = ws.d;
@@ -517,7 +483,7 @@ static void self_attn_block(mldb_handle* h, const LinW& in_proj, const LinW& out
   a.Lk = ws.L; a.nseq = ws.nseq; a.heads = heads; a.hd = d / heads;
   a.lengths = si.lengths; a.kv_prefix = si.kv_prefix; a.len_mod = si.len_mod; a.seq0 = 0; a.out = ws.att;
   op_attn(h, a, st);
-  out_proj_ln(h, out_proj, out_proj_r, n, ws.att, xin, xout, ws.M, d, ws.cf32, st);
+  out_proj_ln(h, out_proj, n, ws.att, xin, xout, ws.M, d, ws.cf32, st);
 }
 static void ffn_block(mldb_handle* h, const LinW& l1, const LinW& l2, const LnW& n, ActBuf xin,
                       ActBuf xout, StackWs& ws, int act, cudaStream_t st) {
@@ -529,14 +495,14 @@ static void ffn_block(mldb_handle* h, const LinW& l1, const LinW& l2, const LnW&
 // TransformerEncoderLayer.forward_post (cross_attention.py:259-272)
 static void enc_layer(mldb_handle* h, const StackW& sw, const EncW& w, ActBuf xin, ActBuf xout,
                       StackWs& ws, const SeqInfo& si, cudaStream_t st) {
-  self_attn_block(h, w.in_proj, w.out_proj, w.out_proj_r, w.n1, xin, ws.x1, ws, si, sw.heads, st);
+  self_attn_block(h, w.in_proj, w.out_proj, w.n1, xin, ws.x1, ws, si, sw.heads, st);
   ffn_block(h, w.l1, w.l2, w.n2, ws.x1, xout, ws, ACT_GELU, st);
 }
 // TransformerDecoderLayer.forward_post (cross_attention.py:323-345)
 static void dec_layer(mldb_handle* h, const StackW& sw, const DecW& w, ActBuf xin, ActBuf xout,
                       ActBuf mem, StackWs& ws, const SeqInfo& si, cudaStream_t st) {
   const int d = ws.d;
-  self_attn_block(h, w.sa_in, w.sa_out, w.sa_out_r, w.n1, xin, ws.x1, ws, si, sw.heads, st);
+  self_attn_block(h, w.sa_in, w.sa_out, w.n1, xin, ws.x1, ws, si, sw.heads, st);
   if (ws.Lmem == 1) {
     // One memory token: softmax over a single key is exactly 1, so the cross-attention output of
     // every query row of sequence b is out_proj(W_v z_b + b_v) + b_o - a per-sequence vector added
@@ -559,7 +525,7 @@ static void dec_layer(mldb_handle* h, const StackW& sw, const DecW& w, ActBuf xi
   AttnArgs a; a.q = ws.qc; a.q_col0 = 0; a.Lq = ws.L; a.kv = ws.kvm; a.k_col0 = 0; a.v_col0 = d;
   a.Lk = ws.Lmem; a.nseq = ws.nseq; a.heads = sw.heads; a.hd = d / sw.heads; a.out = ws.att;
   op_attn(h, a, st);
-  out_proj_ln(h, w.ca_out, w.ca_out_r, w.n2, ws.att, ws.x1, ws.x2, ws.M, d, ws.cf32, st);
+  out_proj_ln(h, w.ca_out, w.n2, ws.att, ws.x1, ws.x2, ws.M, d, ws.cf32, st);
   ffn_block(h, w.l1, w.l2, w.n3, ws.x2, xout, ws, ACT_GELU, st);
 }
 static void any_layer(mldb_handle* h, const StackW& sw, int li, ActBuf xin, ActBuf xout, ActBuf mem,
@@ -600,7 +566,7 @@ static ActBuf enc_layer_selected(mldb_handle* h, const StackW& sw, const EncW& w
   a.Lk = ws.L; a.nseq = ws.nseq; a.heads = sw.heads; a.hd = d / sw.heads; a.lengths = si.lengths;
   a.kv_prefix = si.kv_prefix; a.len_mod = si.len_mod; a.out = ws.satt;
   op_attn(h, a, st);
-  out_proj_ln(h, w.out_proj, w.out_proj_r, w.n1, ws.satt, ws.sx, ws.sx1, R, d, ws.cf32, st);
+  out_proj_ln(h, w.out_proj, w.n1, ws.satt, ws.sx, ws.sx1, R, d, ws.cf32, st);
   GemmArgs g1; g1.a1 = ws.sx1; g1.K1 = d; g1.M = R; g1.w = w.l1; g1.act = ACT_GELU; g1.out = ws.sh;
   GemmArgs g2; g2.a1 = ws.sh; g2.K1 = ws.ff; g2.M = R; g2.w = w.l2;
   LnArgs l2; l2.res = ws.sx1; l2.gamma = w.n2.g; l2.beta = w.n2.b; l2.M = R; l2.d = d; l2.out = ws.sout;
@@ -677,10 +643,6 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   if (env) h->attn_kind = !strcmp(env, "mma") ? 1 : (!strcmp(env, "simt") ? 2 : 0);
   env = getenv("MLDB_BRANCHES");
   if (env) h->branches = std::min(std::max(atoi(env), 1), (int)mldb_handle::MAX_BRANCHES);
-  env = getenv("MLDB_RES_MMA");
-  if (env) h->res_mma = atoi(env) != 0;
-  env = getenv("MLDB_FFN_TAIL");
-  if (env) h->ffn_tail = atoi(env) != 0;
   e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
   for (int i = 0; i < mldb_handle::MAX_BRANCHES - 1 && e == cudaSuccess; ++i) {
     e = cudaStreamCreateWithFlags(&h->br_stream[i], cudaStreamNonBlocking);
@@ -719,10 +681,6 @@ extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* val
     else FAIL(MLDB_ERR_INVALID, "gemm must be tc|simt");
   } else if (!strcmp(name, "ffn_fused")) {
     tc_set_ffn_fused(h->tc, atoi(value) != 0);
-  } else if (!strcmp(name, "res_mma")) {
-    h->res_mma = atoi(value) != 0;
-  } else if (!strcmp(name, "ffn_tail")) {
-    h->ffn_tail = atoi(value) != 0;
   } else if (!strcmp(name, "attn")) {
     if (!strcmp(value, "tc")) h->attn_kind = 0;
     else if (!strcmp(value, "mma")) h->attn_kind = 1;
@@ -1616,7 +1574,7 @@ extern "C" int mldb_profile_op(mldb_handle* h, const char* op, int32_t B, int32_
       AttnArgs a; a.q = ws.qkv; a.Lq = ws.L; a.kv = ws.qkv; a.k_col0 = d; a.v_col0 = 2 * d; a.Lk = ws.L;
       a.nseq = ws.nseq; a.heads = c.num_heads; a.hd = d / c.num_heads; a.out = ws.att; op_attn(h, a, st);
     } else if (!strcmp(op, "outproj_ln")) {
-      out_proj_ln(h, w.out_proj, w.out_proj_r, w.n1, ws.att, ws.x0, ws.x1, ws.M, d, ws.cf32, st);
+      out_proj_ln(h, w.out_proj, w.n1, ws.att, ws.x0, ws.x1, ws.M, d, ws.cf32, st);
     } else if (!strcmp(op, "ffn1")) {
       GemmArgs g; g.a1 = ws.x1; g.K1 = d; g.M = ws.M; g.w = w.l1; g.act = ACT_GELU; g.out = ws.h; op_gemm(h, g, st);
     } else if (!strcmp(op, "ffn2_ln")) {

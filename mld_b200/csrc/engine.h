@@ -15,13 +15,11 @@ struct LnW { float* g = nullptr; float* b = nullptr; };
 
 struct EncW {  // TransformerEncoderLayer (cross_attention.py:236-257)
   LinW in_proj, out_proj, l1, l2;
-  LinW out_proj_r;        // [W_o | I]: out-projection with the residual as a second A source (d == 256)
   LnW n1, n2;
   LinW q_only, kv_only;   // row slices [0:d) / [d:3d) of in_proj, packed for the stack's last layer
 };
 struct DecW {  // TransformerDecoderLayer (cross_attention.py:297-321)
   LinW sa_in, sa_out, ca_q, ca_kv, ca_v, ca_out, l1, l2;   // ca_v: rows [2d,3d) for the 1-memory-token collapse
-  LinW sa_out_r, ca_out_r;                                 // [W_o | I] variants (see EncW::out_proj_r)
   LnW n1, n2, n3;
 };
 enum StackKind { STACK_SKIP_ENC = 0, STACK_SKIP_DEC = 1, STACK_PLAIN_DEC = 2 };
@@ -126,8 +124,6 @@ struct mldb_handle {
   // so one range's kernel tails (316 m-tiles on 148 SMs = 2.13 rounds) and kernel boundaries are
   // filled by the other range's kernels.  1 = off.
   int branches = 2;
-  bool res_mma = true;       // out-projection residual through the tensor pipe ([W | I] weights; option res_mma)
-  bool ffn_tail = true;      // hidden-split of the fused FFN's last partial round of m-tiles (option ffn_tail)
   int attn_kind = 0;         // 0 = tcgen05 (attn_tc.cu), 1 = mma.sync (attn_mma.cu), 2 = CUDA-core; option `attn`
   // which kernel every operator of the path was ENQUEUED on (recorded launches, incl. graph capture);
   // read through mldb_kernel_stats so that tests can assert "nothing fell back to CUDA cores"

@@ -202,28 +202,6 @@ __device__ __forceinline__ void ln_stats_chunk(uint32_t (&r)[32], const uint4 (&
     }
   }
 }
-// the same without a residual operand (it arrived through the accumulator: [W | I] weights)
-__device__ __forceinline__ void ln_stats_chunk_nores(uint32_t (&r)[32], const float* bch, float sc, float shiftK,
-                                                     float& s1, float& s2) {
-  const float4* b4 = reinterpret_cast<const float4*>(bch);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const float4 b = b4[i];
-    const float x0 = fmaf(__uint_as_float(r[4 * i + 0]), sc, b.x), x1 = fmaf(__uint_as_float(r[4 * i + 1]), sc, b.y);
-    const float x2 = fmaf(__uint_as_float(r[4 * i + 2]), sc, b.z), x3 = fmaf(__uint_as_float(r[4 * i + 3]), sc, b.w);
-    const float d0 = x0 - shiftK, d1 = x1 - shiftK, d2 = x2 - shiftK, d3 = x3 - shiftK;
-    s1 += (d0 + d1) + (d2 + d3);
-    s2 = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, s2))));
-    r[4 * i + 0] = __float_as_uint(x0); r[4 * i + 1] = __float_as_uint(x1);
-    r[4 * i + 2] = __float_as_uint(x2); r[4 * i + 3] = __float_as_uint(x3);
-  }
-}
-__device__ __forceinline__ float ln_shift_nores(const uint32_t (&r)[32], const float* bch, float sc) {
-  float acc = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 32; ++i) acc += fmaf(__uint_as_float(r[i]), sc, bch[i]);
-  return acc * (1.0f / 32);
-}
 // Shift of the one-pass variance: the mean of the row's first 32 pre-norm values.  (A single value - the
 // first element - can sit 3 sigma off the mean and E[(x-K)^2] - E[x-K]^2 then cancels ~3 bits.)
 __device__ __forceinline__ float ln_shift(const uint32_t (&r)[32], const uint4 (&rh)[4], const uint4 (&rl)[4],
@@ -371,6 +349,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
         const uint32_t ph = (uint32_t)(kbg / STAGES) & 1u;
         mbar_wait(smem_u32(&bar_empty[s]), ph ^ 1u);
         if (elect_one()) {
+          if (kb == 0 && j + 1 < nlocal) {
+            // The ring is only two or three k-blocks deep (64 KB stages): measured with the in-kernel timeline,
+            // a k-block took 2.1-2.6k cycles to arrive against 1.57k cycles of MMA work, i.e. the main loop ran
+            // at the HBM latency.  The NEXT item's activation rows are therefore pulled into L2 one whole item
+            // ahead (weights are L2-resident anyway).
+            int m1, n1;
+            decode_item(j + 1, p, BN, CG, rank, m1, n1);
+            if (m1 != m0) {
+              for (int k2 = 0; k2 < p.kblocks; ++k2) {
+                if (k2 < p.kb1) { tma_prefetch_2d(&tmA1h, k2 * BK, m1); tma_prefetch_2d(&tmA1l, k2 * BK, m1); }
+                else { tma_prefetch_2d(&tmA2h, (k2 - p.kb1) * BK, m1); tma_prefetch_2d(&tmA2l, (k2 - p.kb1) * BK, m1); }
+              }
+            }
+          }
           uint32_t full = smem_u32(&bar_full[s]);
           if (CG == 1) {
             mbar_expect_tx(full, Cfg::STAGE_BYTES);
@@ -596,15 +588,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
             load_plane_issue(rbh + (c + 2) * 32, p.ld_res, rows_valid, lane, gAh);
             load_plane_issue(rbl + (c + 2) * 32, p.ld_res, rows_valid, lane, gAl);
           }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
         }
         tmem_ld32(trow + c * 32, r);
-        if (has_res) {
-          if (c == 0) shiftK = ln_shift(r, rh, rl, s_bias, sc);
-          ln_stats_chunk(r, rh, rl, s_bias + c * 32, sc, shiftK, s1, s2);
-        } else {
-          if (c == 0) shiftK = ln_shift_nores(r, s_bias, sc);
-          ln_stats_chunk_nores(r, s_bias + c * 32, sc, shiftK, s1, s2);
-        }
+        if (c == 0) shiftK = ln_shift(r, rh, rl, s_bias, sc);
+        ln_stats_chunk(r, rh, rl, s_bias + c * 32, sc, shiftK, s1, s2);
         tmem_st32(trow + c * 32, r);
         // ---- chunk c + 1 (buffers B)
         if (has_res) {
@@ -616,8 +606,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           }
         }
         tmem_ld32(trow + (c + 1) * 32, r);
-        if (has_res) ln_stats_chunk(r, rh, rl, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
-        else ln_stats_chunk_nores(r, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
+        ln_stats_chunk(r, rh, rl, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
         tmem_st32(trow + (c + 1) * 32, r);
       }
       const float e1 = s1 * (1.0f / 256), e2 = s2 * (1.0f / 256);
@@ -668,12 +657,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
 // W2 k-blocks through one ring (2 x 64 KB; 3 x 48 KB per CTA of a pair) in exactly that order.
 struct FfnParams {
   int M, m_tiles, n_chunks;
-  // Hidden-dimension split of the LAST, partial round of m-tiles: `split` CTA groups share one m-tile
-  // (pair), each walks n_chunks / split hidden chunks and stores its partial W2 product into its own slice
-  // of `partial` (fp32 [split][M][256]; bias added by split 0; plain stores: deterministic); the residual +
-  // LayerNorm then run as a row kernel that sums the slices in order.  split == 1: the normal fused kernel.
-  int split;
-  float* partial;
   long long* tl;
   float inv_s1, inv_s2;
   const float* b1; const float* b2; const float* gamma; const float* beta;
@@ -736,12 +719,9 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   const int rank = CG > 1 ? (int)cluster_ctarank() : 0;
   const int ncl = (int)gridDim.x / CG, cid = (int)blockIdx.x / CG;
   const int ngroups = (p.m_tiles + CG - 1) / CG;
-  const bool split_mode = p.split > 1;
-  const int NC = p.n_chunks / p.split;                    // hidden chunks this CTA (group) walks per m-tile
-  const int chunk0 = split_mode ? (cid % p.split) * NC : 0;
-  const int nlocal = split_mode ? 1 : (ngroups - cid + ncl - 1) / ncl;
-  // m-tile group of the j-th local item
-  auto mgroup = [&](int j) { return split_mode ? cid / p.split : cid + j * ncl; };
+  const int NC = p.n_chunks;
+  const int nlocal = (ngroups - cid + ncl - 1) / ncl;
+  auto mgroup = [&](int j) { return cid + j * ncl; };        // m-tile group of the j-th local item
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -808,12 +788,16 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
           for (int kb = 0; kb < 4; ++kb, ++kbg) {
             mbar_wait(smem_u32(&bar_empty[kbg % STAGES]), (((uint32_t)(kbg / STAGES)) & 1u) ^ 1u);
             if (elect_one()) {
+              if (i == 0 && kb == 0 && j + 1 < nlocal) {      // next tile's x rows -> L2, a whole tile ahead
+                const int m1 = (mgroup(j + 1) * CG + rank) * BM;
+                for (int k2 = 0; k2 < 4; ++k2) { tma_prefetch_2d(&tmXh, k2 * BK, m1); tma_prefetch_2d(&tmXl, k2 * BK, m1); }
+              }
               uint32_t full;
               const uint32_t dst = stage_begin(Cfg::F1_BYTES, full);
               load(dst, &tmXh, full, kb * BK, m0);
               load(dst + 16384, &tmXl, full, kb * BK, m0);
-              load(dst + 32768, &tmW1h, full, kb * BK, (chunk0 + i) * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
-              load(dst + 32768 + Cfg::W1_BYTES, &tmW1l, full, kb * BK, (chunk0 + i) * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
+              load(dst + 32768, &tmW1h, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
+              load(dst + 32768 + Cfg::W1_BYTES, &tmW1l, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
             }
             __syncwarp();
           }
@@ -824,8 +808,8 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
             if (elect_one()) {
               uint32_t full;
               const uint32_t dst = stage_begin(Cfg::F2_BYTES, full);
-              load(dst, &tmW2h, full, (chunk0 + i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
-              load(dst + Cfg::W2_BYTES, &tmW2l, full, (chunk0 + i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
+              load(dst, &tmW2h, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
+              load(dst + Cfg::W2_BYTES, &tmW2l, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
             }
             __syncwarp();
           }
@@ -926,7 +910,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           tmem_ld32(tacc + cc * 32, r);
-          epi_chunk_fast<ACT_GELU>(r, v, s_b1 + (chunk0 + c) * Cfg::CHUNK + hf * 64 + cc * 32, p.inv_s1);
+          epi_chunk_fast<ACT_GELU>(r, v, s_b1 + c * Cfg::CHUNK + hf * 64 + cc * 32, p.inv_s1);
           pack_split(v, PH[cc], PL[cc]);
         }
         tc_fence_before();
@@ -947,35 +931,6 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         __syncwarp();
         tl_event(p.tl, tl_n, 14, c);                                 // E1(c): Hs written
         if (lane == 0) arrive_leader(bar_hfull);
-      }
-      if (split_mode) {
-        // ---- partial W2 product of this CTA's hidden chunks -> this split's fp32 slice (bias by split 0);
-        // the rows' residual + LayerNorm run afterwards as a row kernel over the summed slices
-        const int m = m0 + row;
-        const int cb = hf * 128;
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * Cfg::CHUNK + cb);
-        mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);
-        tc_fence_after();
-        const bool add_bias = chunk0 == 0;
-        float* const drow = p.partial + ((int64_t)(cid % p.split) * p.M + m) * 256 + cb;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          tmem_ld32(trow + c * 32, r);
-          if (m < p.M) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 b = add_bias ? reinterpret_cast<const float4*>(s_b2 + cb + c * 32)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-              float4 x;
-              x.x = fmaf(__uint_as_float(r[4 * i + 0]), p.inv_s2, b.x); x.y = fmaf(__uint_as_float(r[4 * i + 1]), p.inv_s2, b.y);
-              x.z = fmaf(__uint_as_float(r[4 * i + 2]), p.inv_s2, b.z); x.w = fmaf(__uint_as_float(r[4 * i + 3]), p.inv_s2, b.w);
-              reinterpret_cast<float4*>(drow + c * 32)[i] = x;
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) arrive_leader(bar_a2empty);
-        continue;
       }
       // ---- residual + LayerNorm on acc2.  Two warps share a row (column halves of 128): each keeps
       // one-pass statistics shifted by ITS first value and the halves are merged with the pairwise
@@ -1247,67 +1202,33 @@ bool tc_ffn_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, co
   if (g1.in_group < g1.M || g1.out_group != 0 || g1.out_off != 0) return false;
   return true;
 }
-// One launch of the fused kernel over rows [row0, row0 + M) of the operands.  split > 1: hidden-split mode
-// (partial products into `partial`, see FfnParams).
-static bool ffn_launch(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, int64_t row0, int M, int split,
-                       float* partial, cudaStream_t st) {
+bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, cudaStream_t st) {
   CUtensorMap mXh, mXl, mW1h, mW1l, mW2h, mW2l, mOh, mOl;
-  const int m_tiles = (M + BM - 1) / BM;
+  const int m_tiles = (g1.M + BM - 1) / BM;
   const int cg = (m_tiles >= 2 && c->sm_count % 2 == 0) ? 2 : 1;
-  const __half* xh = g1.a1.hi + row0 * g1.a1.cols;
-  __half* oh = l2.out.hi + row0 * l2.out.cols;
-  const bool ok = make_map(c, &mXh, xh, M, g1.K1, BM) && make_map(c, &mXl, xh + g1.a1.plane_stride, M, g1.K1, BM) &&
+  const bool ok = make_map(c, &mXh, g1.a1.hi, g1.M, g1.K1, BM) && make_map(c, &mXl, g1.a1.lo(), g1.M, g1.K1, BM) &&
                   make_map(c, &mW1h, g1.w.w, g1.w.N, g1.w.K, FfnCfg<1>::CHUNK / cg) &&
                   make_map(c, &mW1l, g1.w.w + g1.w.plane_stride, g1.w.N, g1.w.K, FfnCfg<1>::CHUNK / cg) &&
                   make_map(c, &mW2h, g2.w.w, g2.w.N, g2.w.K, 256 / cg) &&
                   make_map(c, &mW2l, g2.w.w + g2.w.plane_stride, g2.w.N, g2.w.K, 256 / cg) &&
-                  make_map_out(c, &mOh, oh, M, 256, l2.out.cols) &&
-                  make_map_out(c, &mOl, oh + l2.out.plane_stride, M, 256, l2.out.cols);
-  if (!ok) return map_fail("ffn", M, g1.w.N, g1.w.K);
+                  make_map_out(c, &mOh, l2.out.hi, g1.M, 256, l2.out.cols) &&
+                  make_map_out(c, &mOl, l2.out.lo(), g1.M, 256, l2.out.cols);
+  if (!ok) return map_fail("ffn", g1.M, g1.w.N, g1.w.K);
   FfnParams p{};
-  p.M = M; p.m_tiles = m_tiles; p.n_chunks = g1.w.N / FfnCfg<1>::CHUNK;
-  p.split = split; p.partial = partial; p.tl = tc::mldb_timeline_buffer();
+  p.M = g1.M; p.m_tiles = m_tiles; p.n_chunks = g1.w.N / FfnCfg<1>::CHUNK;
+  p.tl = tc::mldb_timeline_buffer();
   p.inv_s1 = g1.w.inv_scale; p.inv_s2 = g2.w.inv_scale;
   p.b1 = g1.w.bias; p.b2 = g2.w.bias; p.gamma = l2.gamma; p.beta = l2.beta;
-  p.res_hi = l2.res.hi ? l2.res.hi + row0 * l2.res.cols : nullptr;
-  p.res_lo = l2.res.hi ? l2.res.hi + l2.res.plane_stride + row0 * l2.res.cols : nullptr; p.ld_res = l2.res.cols;
-  p.out_hi = oh; p.out_lo = oh + l2.out.plane_stride; p.ld_out = l2.out.cols;
+  p.res_hi = l2.res.hi; p.res_lo = l2.res.hi ? l2.res.lo() : nullptr; p.ld_res = l2.res.cols;
+  p.out_hi = l2.out.hi; p.out_lo = l2.out.lo(); p.ld_out = l2.out.cols;
   p.tma_out = 1;
   const int groups = (m_tiles + cg - 1) / cg;
-  const int ncl = split > 1 ? groups * split : (groups < c->sm_count / cg ? groups : c->sm_count / cg);
+  const int ncl = groups < c->sm_count / cg ? groups : c->sm_count / cg;
   if (cg == 2)
     launch_pdl_cluster(k_ffn_tc<2>, dim3(ncl * 2), dim3(NUM_THREADS), FfnCfg<2>::SMEM_BYTES, st, 2, mXh, mXl, mW1h, mW1l,
                        mW2h, mW2l, mOh, mOl, p);
   else
     launch_pdl(k_ffn_tc<1>, dim3(ncl), dim3(NUM_THREADS), FfnCfg<1>::SMEM_BYTES, st, mXh, mXl, mW1h, mW1l, mW2h, mW2l,
                mOh, mOl, p);
-  return true;
-}
-
-// Rows of the last, partial round of m-tile pairs and the hidden split that spreads them over the idle SMs
-// (0 rows: no tail handling - the tile count fills whole rounds, or the last round is more than half full).
-void tc_ffn_tail_plan(const TcCtx* c, int M, int n_chunks, int* tail_rows, int* split) {
-  *tail_rows = 0; *split = 1;
-  const int m_tiles = (M + BM - 1) / BM;
-  if (c->sm_count % 2 || m_tiles < c->sm_count) return;        // pairs only, at least one full round
-  const int slots = c->sm_count / 2, pairs = (m_tiles + 1) / 2, rem = pairs % slots;
-  if (rem == 0 || 2 * rem > slots) return;
-  int sp = 1;
-  while (sp * 2 * rem <= slots && n_chunks % (sp * 2) == 0) sp *= 2;
-  if (sp == 1) return;
-  *split = sp;
-  *tail_rows = M - (pairs - rem) * 2 * BM;
-}
-
-// l2.c == nullptr.  tail_partial: fp32 [split][tail_rows][256] scratch of the caller or nullptr.
-bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, float* tail_partial, cudaStream_t st,
-            int* tail_rows_out, int* tail_split_out) {
-  int tail_rows = 0, split = 1;
-  if (tail_partial) tc_ffn_tail_plan(c, g1.M, g1.w.N / FfnCfg<1>::CHUNK, &tail_rows, &split);
-  if (tail_rows_out) *tail_rows_out = tail_rows;
-  const int main_rows = g1.M - tail_rows;
-  if (!ffn_launch(c, g1, g2, l2, 0, main_rows, 1, nullptr, st)) return false;
-  if (tail_rows > 0 && !ffn_launch(c, g1, g2, l2, main_rows, tail_rows, split, tail_partial, st)) return false;
-  if (tail_split_out) *tail_split_out = split;
   return true;
 }

@@ -14,12 +14,5 @@ bool tc_gemm_ln_supported(const TcCtx* c, const GemmArgs& g, const LnArgs& l);
 bool tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st);
 // FFN block linear1 + GELU + linear2 + residual + LayerNorm as one launch (hidden stays on the SM)
 bool tc_ffn_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2);
-// tail_partial != nullptr (fp32 scratch, split x tail_rows x 256 of tc_ffn_tail_plan): the m-tiles of the last,
-// partial round are spread over the idle SMs by splitting the hidden dimension; each split stores its partial
-// product into its slice and *tail_rows_out (> 0) / *tail_split_out tell the caller to finish those rows with
-// a residual + LayerNorm row kernel that sums the slices (LnArgs::c_parts).  Rows [0, M - tail_rows) are
-// complete after the call.
-bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, float* tail_partial, cudaStream_t st,
-            int* tail_rows_out, int* tail_split_out);
-void tc_ffn_tail_plan(const TcCtx* c, int M, int n_chunks, int* tail_rows, int* split);
+bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, cudaStream_t st);
 int tc_set_ffn_fused(TcCtx* c, int on);   // returns the previous setting

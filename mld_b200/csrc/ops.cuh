@@ -40,7 +40,6 @@ struct GemmArgs {
 // (gamma2/beta2) applied on top (last block's norm2 followed by the stack's final norm).
 struct LnArgs {
   const float* c = nullptr; int ldc = 0;   // fp32 GEMM result incl. bias (nullable)
-  int c_parts = 1; int64_t c_part_stride = 0;   // c is the in-order sum of c_parts slices, c_part_stride floats apart
   ActBuf res{};                              // residual (nullable: res.hi == nullptr)
   const float* rowvec = nullptr; int rv_group = 1;
   const float* gamma = nullptr; const float* beta = nullptr;

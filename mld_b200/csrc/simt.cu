@@ -115,10 +115,7 @@ __global__ void __launch_bounds__(256) k_ln(const LnArgs a) {
     const int n = i * 32 + lane;
     float x = 0.0f;
     if (n < a.d) {
-      if (a.c) {
-        x = a.c[irow * a.ldc + n];
-        for (int pt = 1; pt < a.c_parts; ++pt) x += a.c[pt * a.c_part_stride + irow * a.ldc + n];
-      }
+      if (a.c) x += a.c[irow * a.ldc + n];
       if (a.res.hi) {
         int64_t o = irow * a.res.cols + n;
         x += join_f32(a.res.hi[o], a.res.lo()[o]);

@@ -425,7 +425,7 @@ def diffusion_reverse(dsd: SD, dcfg: DenoiserCfg, scheduler, num_inference_steps
     latents = init_noise * scheduler.init_noise_sigma                 # :310
     scheduler.set_timesteps(num_inference_steps)                      # :312
     is_ddim = isinstance(scheduler, DDIMScheduler)
-    for i, t in enumerate(scheduler.timesteps):                       # :323
+    for i, t in enumerate(scheduler.timesteps.to(latents.device)):    # :323 (from_numpy ignores a device context)
         model_in = torch.cat([latents] * 2) if cfg_on else latents    # :325-327
         lengths_rev = (list(lengths) * 2 if cfg_on else lengths) if lengths is not None else None
         noise_pred = denoiser_forward(dsd, dcfg, model_in, t, encoder_hidden_states, lengths_rev)

@@ -104,6 +104,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   int tl_n = 0;                                       // debug-timeline event counter of this warp
+  tl_event(p.tl, tl_n, 40);                       // kernel entry
   const int items = p.nseq * p.heads * p.n_qt;
   const int nlocal = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nkb = p.nkb, SB = p.SB, QB = p.QB, RS = p.RS;
@@ -127,6 +128,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                                         // q|k|v come from the previous kernel
+  tl_event(p.tl, tl_n, 41);                       // the previous kernel has completed
 
   if (warp == WARP_TMA) {
     // ------------------------------------------------------------------ TMA producer
@@ -405,6 +407,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
   }
   tc_fence_before();
   __syncthreads();
+  tl_event(p.tl, tl_n, 42);                       // kernel exit
   if (warp == WARP_MMA) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, 512);

@@ -61,22 +61,39 @@ struct TcParams {
 
 constexpr int EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;     // producer warp + MMA warp + epilogue warps
+// The kernels with a LayerNorm epilogue (k_gemm_tc<EPI_LN>, k_ffn_tc) run SIXTEEN epilogue warps: the LayerNorm
+// of a 128 x 256 tile is a chain of TMEM loads, shared-memory transposes and conversions that is latency-bound
+// per warp (the in-kernel timeline showed ~12k cycles per tile on 8 warps, IPC < 0.4 per scheduler), so it gets
+// four warps per scheduler instead of two.  576 threads -> 112 registers per thread.
+constexpr int LN_WARPS = 16;
+constexpr int LN_THREADS = 64 + LN_WARPS * 32;
 constexpr int MAX_N = 1024;                          // bias staging capacity
 
-template <int BN, int CG = 1>
+enum { EPI_FAST = 0, EPI_LN = 1, EPI_GENERIC = 2 };     // epilogue variants of k_gemm_tc (see the kernel)
+
+template <int BN, int CG = 1, int EPI = EPI_GENERIC>
 struct TileCfg {
-  static constexpr int STAGES = BN == 256 ? 2 : 3;
+  // The per-layer plain GEMMs (256-wide tiles on CTA pairs, fast epilogue) get a THREE-deep ring: with two
+  // 64 KB stages a stage's round trip (TMA issue -> L2 -> MMA -> commit -> producer wake-up) did not fit under
+  // one k-block of MMA work and the main loop ran at 2.1-2.6k cycles per k-block instead of 1.57k (in-kernel
+  // timeline).  The third stage is paid for by single-buffering the TMA-store staging and reading the bias
+  // straight from global memory (L1-resident broadcast loads) instead of staging it.
+  static constexpr bool DEEP = EPI == EPI_FAST && BN == 256 && CG == 2;
+  static constexpr int STAGES = (BN == 256 && !DEEP) ? 2 : 3;
   static constexpr int A_BYTES = BM * BK * 2;          // one plane of the A tile (16 KB)
   static constexpr int W_BYTES = BN / CG * BK * 2;     // one plane of this CTA's part of the W tile
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;             // double-buffered accumulator
-  // per-warp staging: one 32 rows x 64 B transpose buffer (CG = 1: st.global epilogue) or two
-  // {hi, lo} pairs of them (CG = 2: the epilogue drains through TMA bulk stores)
-  static constexpr int STG_WARP = CG == 2 ? 8192 : 2048;
-  static constexpr int STG_BYTES = EPI_WARPS * STG_WARP;
-  // bias[MAX_N] + gamma[256] + beta[256] + staging + barriers
-  static constexpr int AUX_BYTES = MAX_N * 4 + 2 * 256 * 4 + 256 + STG_BYTES;
+  // per-warp staging: one 32 rows x 64 B transpose buffer (CG = 1: st.global epilogue) or {hi, lo} pairs of
+  // them (CG = 2: the epilogue drains through TMA bulk stores; two pairs alternate unless DEEP)
+  static constexpr int NEPI = EPI == EPI_LN ? LN_WARPS : EPI_WARPS;       // epilogue warps
+  static constexpr int STG_WARP = CG == 2 ? ((DEEP || EPI == EPI_LN) ? 4096 : 8192) : 2048;
+  static constexpr int STG_BYTES = NEPI * STG_WARP;
+  static constexpr int VEC_BYTES = DEEP ? 0 : MAX_N * 4 + 2 * 256 * 4;     // bias[MAX_N] + gamma[256] + beta[256]
+  static constexpr int PART_BYTES = EPI == EPI_LN ? 4 * 2 * 128 * 4 : 0;   // LayerNorm partial statistics
+  static constexpr int AUX_BYTES = VEC_BYTES + PART_BYTES + 256 + STG_BYTES;   // + barriers
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + AUX_BYTES + 1024;   // + alignment slack
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 // fp32 x32 -> split16 hi/lo planes (64 B each) with packed conversions
@@ -136,30 +153,13 @@ __device__ __forceinline__ void plane_to_rows(uint8_t* stg, const uint4 (&g)[4],
   for (int j = 0; j < 4; ++j) rowv[j] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
   __syncwarp();
 }
-// both planes at once (two staging tiles, half the warp barriers)
-__device__ __forceinline__ void planes_to_rows(uint8_t* stg, const uint4 (&gh)[4], const uint4 (&gl)[4], int lane,
-                                               uint4 (&rh)[4], uint4 (&rl)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = i * 8 + (lane >> 2), qq = lane & 3;
-    *reinterpret_cast<uint4*>(stg + stg_off(rr, qq)) = gh[i];
-    *reinterpret_cast<uint4*>(stg + 2048 + stg_off(rr, qq)) = gl[i];
-  }
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    rh[j] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
-    rl[j] = *reinterpret_cast<const uint4*>(stg + 2048 + stg_off(lane, j));
-  }
-  __syncwarp();
-}
 // fp32 x32 -> packed split16 words (hi and lo planes)
 __device__ __forceinline__ void pack_split(const float (&v)[32], uint32_t (&ph)[16], uint32_t (&pl)[16]) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) split2(v[2 * i], v[2 * i + 1], ph[i], pl[i]);
 }
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory"); }
+__device__ __forceinline__ void ln_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(LN_WARPS * 32) : "memory"); }
 
 // x[i] = act(acc[i] * s + bias[i]) for one 32-column chunk; bias read as float4 broadcasts.
 template <int ACT>
@@ -177,51 +177,6 @@ __device__ __forceinline__ void epi_chunk_fast(const uint32_t (&r)[32], float (&
   }
 }
 
-// one 32-column chunk of the LayerNorm statistics pass: x = acc * sc + bias + (res_hi + res_lo);
-// accumulates sum(x - K), sum((x - K)^2) and leaves x in r[] (to be parked in TMEM)
-__device__ __forceinline__ void ln_stats_chunk(uint32_t (&r)[32], const uint4 (&rh)[4], const uint4 (&rl)[4],
-                                               const float* bch, float sc, float shiftK, float& s1, float& s2) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t ah[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
-    const uint32_t al[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
-    const float4 b0 = reinterpret_cast<const float4*>(bch)[2 * i], b1 = reinterpret_cast<const float4*>(bch)[2 * i + 1];
-    const float bia[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&ah[j]));
-      const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&al[j]));
-      const int e = i * 8 + j * 2;
-      const float x0 = fmaf(__uint_as_float(r[e]), sc, bia[2 * j]) + (hf2.x + lf2.x);
-      const float x1 = fmaf(__uint_as_float(r[e + 1]), sc, bia[2 * j + 1]) + (hf2.y + lf2.y);
-      const float d0 = x0 - shiftK, d1 = x1 - shiftK;
-      s1 += d0 + d1;
-      s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
-      r[e] = __float_as_uint(x0);
-      r[e + 1] = __float_as_uint(x1);
-    }
-  }
-}
-// Shift of the one-pass variance: the mean of the row's first 32 pre-norm values.  (A single value - the
-// first element - can sit 3 sigma off the mean and E[(x-K)^2] - E[x-K]^2 then cancels ~3 bits.)
-__device__ __forceinline__ float ln_shift(const uint32_t (&r)[32], const uint4 (&rh)[4], const uint4 (&rl)[4],
-                                          const float* bch, float sc) {
-  float acc = 0.0f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t ah[4] = {rh[i].x, rh[i].y, rh[i].z, rh[i].w};
-    const uint32_t al[4] = {rl[i].x, rl[i].y, rl[i].z, rl[i].w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 hf2 = __half22float2(*reinterpret_cast<const __half2*>(&ah[j]));
-      const float2 lf2 = __half22float2(*reinterpret_cast<const __half2*>(&al[j]));
-      const int e = i * 8 + j * 2;
-      acc += fmaf(__uint_as_float(r[e]), sc, bch[e]) + (hf2.x + lf2.x);
-      acc += fmaf(__uint_as_float(r[e + 1]), sc, bch[e + 1]) + (hf2.y + lf2.y);
-    }
-  }
-  return acc * (1.0f / 32);
-}
 // y = (x * a + b) * gamma + beta for one parked 32-column chunk
 __device__ __forceinline__ void ln_norm_chunk(const uint32_t (&r)[32], float (&v)[32], const float* g, const float* be,
                                               float a, float b) {
@@ -237,10 +192,12 @@ __device__ __forceinline__ void ln_norm_chunk(const uint32_t (&r)[32], float (&v
   }
 }
 // row-owner packed chunk -> SWIZZLE_64B staging pair -> two TMA bulk stores (lane 0 owns the warp's
-// bulk groups; at most one older pair in flight per warp: the caller alternates `buf`)
+// bulk groups; at most PENDING older pairs still being read by the TMA engine: 1 = the caller alternates two
+// staging pairs, 0 = one pair)
+template <int PENDING = 1>
 __device__ __forceinline__ void stage_and_store(uint8_t* sb2, const uint32_t (&ph)[16], const uint32_t (&pl)[16], int lane,
                                                 const CUtensorMap* mh, const CUtensorMap* ml, int col, int row0) {
-  if (lane == 0) tma_store_wait_read<1>();
+  if (lane == 0) tma_store_wait_read<PENDING>();
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -254,6 +211,118 @@ __device__ __forceinline__ void stage_and_store(uint8_t* sb2, const uint32_t (&p
     tma_store_2d(ml, smem_u32(sb2 + 2048), col, row0);
     tma_store_commit();
   }
+}
+
+// ---- residual + LayerNorm of one 128 x 256 accumulator tile by SIXTEEN warps.  Warp -> TMEM lane quarter q
+// (32 rows, a thread owns one row) x column quarter cq (64 columns = two 32-column chunks).  Every thread
+// keeps one-pass statistics of its 64 values shifted by the mean of its first chunk (var = E[(x-K)^2] -
+// E[x-K]^2 does not cancel); the four quarters of a row are merged with the pairwise (Chan) update through
+// shared memory in a FIXED order, so every warp derives the same mean / rstd; the pre-norm values are parked
+// in TMEM between the passes.  The residual is loaded (coalesced pattern) before the accumulator is awaited.
+struct LnResidual { uint4 gh[4], gl[4]; };           // one 32-column chunk of both planes in flight (32 registers)
+// r[32] (fp32 bits) += one fp16 plane of the same 32 columns (row-owner layout: 4 x 16 B)
+__device__ __forceinline__ void add_plane(uint32_t (&r)[32], const uint4 (&pv)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t w[4] = {pv[i].x, pv[i].y, pv[i].z, pv[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      const int e = i * 8 + j * 2;
+      r[e] = __float_as_uint(__uint_as_float(r[e]) + f.x);
+      r[e + 1] = __float_as_uint(__uint_as_float(r[e + 1]) + f.y);
+    }
+  }
+}
+__device__ __forceinline__ void ln16_issue_residual(LnResidual& t, const __half* res_hi, const __half* res_lo, int ld_res,
+                                                    int wrow0, int col, int rows_valid, int lane) {
+  if (res_hi == nullptr) return;
+  load_plane_issue(res_hi + (int64_t)wrow0 * ld_res + col, ld_res, rows_valid, lane, t.gh);
+  load_plane_issue(res_lo + (int64_t)wrow0 * ld_res + col, ld_res, rows_valid, lane, t.gl);
+}
+// trow: TMEM address of this thread's row at the tile's column cb = cq * 64.  stg: this warp's staging
+// (4 KB with WIDE_STG: both planes transposed at once and the TMA-store pair; else 2 KB).  s_vec*: bias / gamma /
+// beta of the 256 columns.  s_part: [4 quarters][mean | M2][128 rows].
+template <bool WIDE_STG>
+__device__ __forceinline__ void ln16_finish(LnResidual& t, const __half* res_hi, const __half* res_lo, int ld_res, uint32_t trow, int cq, int row, int lane, uint8_t* stg,
+                                            const float* s_bias, const float* s_gamma, const float* s_beta, float* s_part,
+                                            float sc, int wrow0, int rows_valid, bool tma_out, const CUtensorMap* mOh,
+                                            const CUtensorMap* mOl, __half* out_hi, __half* out_lo, int ld_out,
+                                            long long* tl, int& tl_n) {
+  const int cb = cq * 64;
+  uint32_t r[32];
+  float v[32];
+  float s1 = 0.0f, s2 = 0.0f, shiftK = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    tmem_ld32(trow + c * 32, r);
+    // x = acc * sc + bias, then + residual hi plane, then + lo plane (one plane at a time: the row-owner copy
+    // of a plane is 16 registers, and 112 per thread is all there is with 576 threads)
+    const float4* b4 = reinterpret_cast<const float4*>(s_bias + cb + c * 32);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 b = b4[i];
+      r[4 * i + 0] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 0]), sc, b.x));
+      r[4 * i + 1] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 1]), sc, b.y));
+      r[4 * i + 2] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 2]), sc, b.z));
+      r[4 * i + 3] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 3]), sc, b.w));
+    }
+    if (res_hi != nullptr) {
+      // the first chunk's planes were requested before the accumulator was awaited; the second chunk's are
+      // requested as soon as the first one's registers are free and arrive under the first chunk's statistics
+      uint4 rv[4];
+      plane_to_rows(stg, t.gh, lane, rv);
+      add_plane(r, rv);
+      plane_to_rows(stg + (WIDE_STG ? 2048 : 0), t.gl, lane, rv);
+      add_plane(r, rv);
+      if (c == 0) ln16_issue_residual(t, res_hi, res_lo, ld_res, wrow0, cb + 32, rows_valid, lane);
+    }
+    if (c == 0) {                                  // shift: the mean of the first chunk
+      float acc = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc += __uint_as_float(r[i]);
+      shiftK = acc * (1.0f / 32);
+    }
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+      const float d0 = __uint_as_float(r[i]) - shiftK, d1 = __uint_as_float(r[i + 1]) - shiftK;
+      s1 += d0 + d1;
+      s2 = fmaf(d0, d0, fmaf(d1, d1, s2));
+    }
+    tmem_st32(trow + c * 32, r);
+  }
+  tl_event(tl, tl_n, 7);                            // LayerNorm: statistics pass done
+  // this quarter: mean_q = K + s1/64, M2_q = s2 - s1^2/64
+  s_part[cq * 256 + row] = shiftK + s1 * (1.0f / 64);
+  s_part[cq * 256 + 128 + row] = fmaxf(s2 - s1 * s1 * (1.0f / 64), 0.0f);
+  ln_bar_sync();
+  tl_event(tl, tl_n, 17);                           // LayerNorm: quarters merged
+  const float m0 = s_part[row], m1 = s_part[256 + row], m2 = s_part[512 + row], m3 = s_part[768 + row];
+  const float mean = 0.25f * ((m0 + m1) + (m2 + m3));
+  const float d0 = m0 - mean, d1 = m1 - mean, d2 = m2 - mean, d3 = m3 - mean;
+  const float M2 = ((s_part[128 + row] + s_part[384 + row]) + (s_part[640 + row] + s_part[896 + row])) +
+                   64.0f * ((d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3));
+  const float rstd = rsqrtf(M2 * (1.0f / 256) + 1e-5f);
+  const float nb_ = -mean * rstd;                    // y = x * rstd + nb_
+#pragma unroll 1
+  for (int c = 0; c < 2; ++c) {
+    tmem_ld32(trow + c * 32, r);
+    ln_norm_chunk(r, v, s_gamma + cb + c * 32, s_beta + cb + c * 32, rstd, nb_);
+    uint32_t ph[16], pl[16];
+    pack_split(v, ph, pl);
+    if (WIDE_STG && tma_out) {
+      stage_and_store<0>(stg, ph, pl, lane, mOh, mOl, cb + c * 32, wrow0);
+    } else {
+      const int64_t o = (int64_t)wrow0 * ld_out + cb + c * 32;
+      store_plane_coalesced(stg, ph, out_hi + o, ld_out, rows_valid, lane);
+      store_plane_coalesced(stg, pl, out_lo + o, ld_out, rows_valid, lane);
+    }
+  }
+  // the staging is the next tile's transpose buffer and s_part its statistics: the TMA engine must have read
+  // the former, every warp the latter
+  tl_event(tl, tl_n, 18);                           // LayerNorm: normalised, stores issued
+  if (WIDE_STG && tma_out && lane == 0) tma_store_wait_read<0>();
+  ln_bar_sync();
 }
 
 // j-th work item of this CTA: CTA pairs (CG = 2) walk (m-pair, n) items in lockstep - CTA rank r of
@@ -272,9 +341,8 @@ __device__ __forceinline__ void decode_item(int j, const TcParams& p, int bn, in
 // inside N (the per-layer GEMMs); EPI_LN = residual + LayerNorm; EPI_GENERIC = plain with everything else
 // (positional table, row remapping, zeroed padding rows, fp32 output, ragged N: the per-batch embedding /
 // final-layer GEMMs) kept out of the hot kernels' instruction stream.
-enum { EPI_FAST = 0, EPI_LN = 1, EPI_GENERIC = 2 };
 template <int BN, int CG, int EPI, int ACT = ACT_NONE>      // ACT: the fast epilogue's activation (NONE | GELU)
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(EPI == EPI_LN ? LN_THREADS : NUM_THREADS, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUtensorMap tmA1l,
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
           const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
@@ -282,18 +350,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           const TcParams p) {
   constexpr bool LN = EPI == EPI_LN;
   static_assert(!LN || BN == 256, "the LayerNorm epilogue covers a full 256-wide row");
-  using Cfg = TileCfg<BN, CG>;
+  using Cfg = TileCfg<BN, CG, EPI>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int EMPTY_ARRIVALS = (LN ? 4 : EPI_WARPS) * CG;   // LN: one group of four warps per accumulator stage
+  constexpr bool DEEP = Cfg::DEEP;
+  constexpr int NEPI = Cfg::NEPI;                             // epilogue warps (16 with LayerNorm)
+  constexpr int EMPTY_ARRIVALS = NEPI * CG;
   extern __shared__ uint8_t smem_raw[];
   // 1024-B alignment by pointer arithmetic (an integer round trip would lose the shared address space
   // and turn every staging access into a generic LD/ST)
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* aux = smem + STAGES * Cfg::STAGE_BYTES;
-  float* s_bias = reinterpret_cast<float*>(aux);              // [MAX_N]
-  float* s_gamma = s_bias + MAX_N;                            // [256]
-  float* s_beta = s_gamma + 256;                              // [256]
-  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_beta + 256);   // [EPI_WARPS][STG_WARP], 16B aligned
+  float* s_bias = reinterpret_cast<float*>(aux);              // [MAX_N]   (none of the three when DEEP)
+  float* s_gamma = s_bias + (DEEP ? 0 : MAX_N);               // [256]
+  float* s_beta = s_gamma + (DEEP ? 0 : 256);                 // [256]
+  float* s_part = s_beta + (DEEP ? 0 : 256);                  // LayerNorm partial statistics (EPI_LN only)
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_part) + Cfg::PART_BYTES;   // [NEPI][STG_WARP], 16B aligned
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + Cfg::STG_BYTES);
   uint64_t* bar_full = bars;                    // [STAGES]
   uint64_t* bar_empty = bars + STAGES;          // [STAGES]
@@ -303,6 +374,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   int tl_n = 0;                                     // debug-timeline event counter of this warp
+  tl_event(p.tl, tl_n, 40);                       // kernel entry
   const int rank = CG > 1 ? (int)cluster_ctarank() : 0;
   const int ncl = (int)gridDim.x / CG, cid = (int)blockIdx.x / CG;          // clusters, this CTA's cluster
   const int ngroups = ((p.m_tiles + CG - 1) / CG) * p.n_tiles;               // (m-group, n) items
@@ -322,10 +394,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   }
   if (CG > 1) { __syncthreads(); cluster_sync_all(); }   // 2-SM TMEM allocation needs both CTAs of the pair resident
   if (warp == 1) tmem_alloc<CG>(smem_u32(tmem_slot), Cfg::TMEM_COLS);
-  if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.0f;
+  if (warp >= 2 && !DEEP) {
+    for (int i = threadIdx.x - 64; i < MAX_N; i += NEPI * 32) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.0f;
     if (LN)
-      for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) { s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
+      for (int i = threadIdx.x - 64; i < 256; i += NEPI * 32) { s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; }
   }
   pdl_trigger();               // let the next kernel's prologue overlap our tail
   tc_fence_before();
@@ -334,6 +406,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();                  // everything below touches activations of the previous kernel
+  tl_event(p.tl, tl_n, 41);                       // the previous kernel has completed
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
@@ -482,12 +555,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       auto chunk = [&](const uint32_t (&r)[32], int c) {
         const int nb = n0 + hf * (BN / 2) + c * 32;
         if constexpr (EPI == EPI_FAST) {
-          epi_chunk_fast<ACT>(r, v, s_bias + nb, inv_scale);
+          epi_chunk_fast<ACT>(r, v, DEEP ? p.bias + nb : s_bias + nb, inv_scale);
           uint32_t ph[16], pl[16];
           pack_split(v, ph, pl);
           if (CG == 2 && p.tma_out) {
-            stage_and_store(stg + tbuf * 4096, ph, pl, lane, &tmOh, &tmOl, nb, wrow0);   // the map clips rows >= M
-            tbuf ^= 1;
+            stage_and_store<DEEP ? 0 : 1>(stg + tbuf * 4096, ph, pl, lane, &tmOh, &tmOl, nb, wrow0);   // the map clips rows >= M
+            if (!DEEP) tbuf ^= 1;
           } else {
             const int64_t o = (int64_t)wrow0 * p.ld_out + p.out_col0 + nb;
             store_plane_coalesced(stg, ph, ohi + o, p.ld_out, rows_valid, lane);
@@ -540,94 +613,27 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     if (CG == 2 && lane == 0) tma_store_wait_read<0>();   // staging fully read by the TMA engine
   } else {
     // ------------------------------------------------------------------ LayerNorm epilogue (warps 2..9)
-    // y = LayerNorm(acc * s + bias + residual) over the 256-wide row, eps 1e-5.  Group g = (warp - 2) / 4
-    // drains the accumulator stages of tiles it = g, g + 2, ...; a thread owns the whole row: statistics
-    // in one pass with the row's first value as the shift (var = E[(x-K)^2] - E[x-K]^2 does not cancel),
-    // the pre-norm row parked in TMEM between the two passes.
-    const int q = warp & 3;
-    const int g = (warp - 2) >> 2;
+    // y = LayerNorm(acc * s + bias + residual) over the 256-wide row, eps 1e-5: all sixteen warps drain one
+    // accumulator stage together (ln16_finish), the MMA warp fills the other one meanwhile.
+    const int q = warp & 3;                          // TMEM lane quarter
+    const int cq = (warp - 2) >> 2;                  // column quarter of the row
     const int row = q * 32 + lane;
-    constexpr int NCH = 8;                           // 32-column chunks per row
     uint8_t* const stg = s_stage + (warp - 2) * Cfg::STG_WARP;
-    uint32_t r[32];
-    float v[32];
-    int tbuf = 0;
-    for (int it = g; it < nlocal; it += 2) {
-      const int as = it & 1;                         // == g
+    for (int it = 0; it < nlocal; ++it) {
+      const int as = it & 1;
       int m0, n0;
       decode_item(it, p, BN, CG, rank, m0, n0);
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cq * 64);
       const int wrow0 = m0 + q * 32;
       const int rows_valid = min(32, p.M - wrow0);
-      const bool has_res = p.res_hi != nullptr;      // warp-uniform
-      const __half* rbh = p.res_hi + (int64_t)wrow0 * p.ld_res;
-      const __half* rbl = p.res_lo + (int64_t)wrow0 * p.ld_res;
-      uint4 gAh[4], gAl[4], gBh[4], gBl[4];          // two residual chunks in flight (coalesced pattern)
-      if (CG == 2 && lane == 0) tma_store_wait_read<0>();   // the staging tiles double as transpose buffers
-      __syncwarp();
-      if (has_res) {
-        load_plane_issue(rbh, p.ld_res, rows_valid, lane, gAh);
-        load_plane_issue(rbl, p.ld_res, rows_valid, lane, gAl);
-        load_plane_issue(rbh + 32, p.ld_res, rows_valid, lane, gBh);
-        load_plane_issue(rbl + 32, p.ld_res, rows_valid, lane, gBl);
-      }
+      LnResidual t;
+      ln16_issue_residual(t, p.res_hi, p.res_lo, p.ld_res, wrow0, cq * 64, rows_valid, lane);
       tl_event(p.tl, tl_n, 6, it);                                     // LN epilogue: residual loads issued, waiting for tile `it`
       mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       tl_event(p.tl, tl_n, 4, it);
-      float s1 = 0.0f, s2 = 0.0f, shiftK = 0.0f;
-      const float sc = p.inv_scale;
-#pragma unroll 1
-      for (int c = 0; c < NCH; c += 2) {
-        uint4 rh[4], rl[4];
-        // ---- chunk c (buffers A)
-        if (has_res) {
-          if (CG == 2) planes_to_rows(stg, gAh, gAl, lane, rh, rl);
-          else { plane_to_rows(stg, gAh, lane, rh); plane_to_rows(stg, gAl, lane, rl); }
-          if (c + 2 < NCH) {
-            load_plane_issue(rbh + (c + 2) * 32, p.ld_res, rows_valid, lane, gAh);
-            load_plane_issue(rbl + (c + 2) * 32, p.ld_res, rows_valid, lane, gAl);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
-        }
-        tmem_ld32(trow + c * 32, r);
-        if (c == 0) shiftK = ln_shift(r, rh, rl, s_bias, sc);
-        ln_stats_chunk(r, rh, rl, s_bias + c * 32, sc, shiftK, s1, s2);
-        tmem_st32(trow + c * 32, r);
-        // ---- chunk c + 1 (buffers B)
-        if (has_res) {
-          if (CG == 2) planes_to_rows(stg, gBh, gBl, lane, rh, rl);
-          else { plane_to_rows(stg, gBh, lane, rh); plane_to_rows(stg, gBl, lane, rl); }
-          if (c + 3 < NCH) {
-            load_plane_issue(rbh + (c + 3) * 32, p.ld_res, rows_valid, lane, gBh);
-            load_plane_issue(rbl + (c + 3) * 32, p.ld_res, rows_valid, lane, gBl);
-          }
-        }
-        tmem_ld32(trow + (c + 1) * 32, r);
-        ln_stats_chunk(r, rh, rl, s_bias + (c + 1) * 32, sc, shiftK, s1, s2);
-        tmem_st32(trow + (c + 1) * 32, r);
-      }
-      const float e1 = s1 * (1.0f / 256), e2 = s2 * (1.0f / 256);
-      const float rstd = rsqrtf(fmaxf(e2 - e1 * e1, 0.0f) + 1e-5f);
-      const float nb_ = -(shiftK + e1) * rstd;       // y = x * rstd + nb_
-      tl_event(p.tl, tl_n, 7, it);                                     // LN epilogue: statistics pass done
-#pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        tmem_ld32(trow + c * 32, r);
-        ln_norm_chunk(r, v, s_gamma + c * 32, s_beta + c * 32, rstd, nb_);
-        uint32_t ph[16], pl[16];
-        pack_split(v, ph, pl);
-        if (CG == 2 && p.tma_out) {
-          stage_and_store(stg + tbuf * 4096, ph, pl, lane, &tmOh, &tmOl, c * 32, wrow0);
-          tbuf ^= 1;
-        } else {
-          const int64_t o = (int64_t)wrow0 * p.ld_out + c * 32;
-          store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
-          store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
-        }
-      }
+      ln16_finish<CG == 2>(t, p.res_hi, p.res_lo, p.ld_res, trow, cq, row, lane, stg, s_bias, s_gamma, s_beta, s_part, p.inv_scale, wrow0,
+                           rows_valid, CG == 2 && p.tma_out, &tmOh, &tmOl, p.out_hi, p.out_lo, p.ld_out, p.tl, tl_n);
       tc_fence_before();
       __syncwarp();
       tl_event(p.tl, tl_n, 5, it);
@@ -638,6 +644,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   tc_fence_before();
   __syncthreads();
   if (CG > 1) cluster_sync_all();   // nobody exits while the peer may still signal its barriers / read its smem
+  tl_event(p.tl, tl_n, 42);                       // kernel exit
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
@@ -657,6 +664,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
 // W2 k-blocks through one ring (2 x 64 KB; 3 x 48 KB per CTA of a pair) in exactly that order.
 struct FfnParams {
   int M, m_tiles, n_chunks;
+  int stagger;                 // experiment: start-up delay of cluster c = (c & 3) * stagger cycles
   long long* tl;
   float inv_s1, inv_s2;
   const float* b1; const float* b2; const float* gamma; const float* beta;
@@ -676,7 +684,7 @@ struct FfnCfg {
   static constexpr int HS_BYTES = 65536;                 // [plane][k-block][128 rows x 128 B]; also the
                                                          // LayerNorm epilogue's staging (Hs is idle then)
   static constexpr int TMEM_COLS = 512;                  // acc1 x 2 (128 cols each) + acc2 (256 cols)
-  static constexpr int AUX_BYTES = MAX_N * 4 + 3 * 256 * 4 + 4 * 128 * 4 + 256;
+  static constexpr int AUX_BYTES = MAX_N * 4 + 3 * 256 * 4 + 8 * 128 * 4 + 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + HS_BYTES + AUX_BYTES + 1024;
 };
 
@@ -687,7 +695,7 @@ struct FfnCfg {
 // (the 3-product split scheme reads every operand byte twice; at N = 128 a 1-SM MMA needs the full
 // 128 B/clk of shared-memory bandwidth for its operands alone).
 template <int CG>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(LN_THREADS, 1)
 k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
          const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW1l,
          const __grid_constant__ CUtensorMap tmW2h, const __grid_constant__ CUtensorMap tmW2l,
@@ -702,8 +710,8 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   float* s_b2 = s_b1 + MAX_N;                                 // [256]
   float* s_gamma = s_b2 + 256;
   float* s_beta = s_gamma + 256;
-  float* s_part = s_beta + 256;                               // [2 halves][2 values][128 rows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 4 * 128);
+  float* s_part = s_beta + 256;                               // [4 quarters][mean | M2][128 rows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_part + 8 * 128);
   uint64_t* bar_full = bars;                  // [STAGES] ring stage filled (TMA tx; 2-SM: the leader's)
   uint64_t* bar_empty = bars + 4;             // [STAGES] ring stage consumed (MMA commit, both CTAs)
   uint64_t* bar_a1full = bars + 8;            // [2] F1 chunk accumulated (MMA commit, both CTAs)
@@ -716,6 +724,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   int tl_n = 0;                                     // debug-timeline event counter of this warp
+  tl_event(p.tl, tl_n, 40);                       // kernel entry
   const int rank = CG > 1 ? (int)cluster_ctarank() : 0;
   const int ncl = (int)gridDim.x / CG, cid = (int)blockIdx.x / CG;
   const int ngroups = (p.m_tiles + CG - 1) / CG;
@@ -730,12 +739,12 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&bar_a1full[s]), 1);
-      mbar_init(smem_u32(&bar_a1empty[s]), EPI_WARPS * CG);
+      mbar_init(smem_u32(&bar_a1empty[s]), LN_WARPS * CG);
     }
-    mbar_init(smem_u32(bar_hfull), EPI_WARPS * CG);
+    mbar_init(smem_u32(bar_hfull), LN_WARPS * CG);
     mbar_init(smem_u32(bar_hempty), 1);
     mbar_init(smem_u32(bar_a2full), 1);
-    mbar_init(smem_u32(bar_a2empty), EPI_WARPS * CG);
+    mbar_init(smem_u32(bar_a2empty), LN_WARPS * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmXh); tma_prefetch_desc(&tmXl); tma_prefetch_desc(&tmW1h);
     tma_prefetch_desc(&tmW1l); tma_prefetch_desc(&tmW2h); tma_prefetch_desc(&tmW2l);
@@ -743,8 +752,8 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   if (CG > 1) { __syncthreads(); cluster_sync_all(); }
   if (warp == 1) tmem_alloc<CG>(smem_u32(tmem_slot), Cfg::TMEM_COLS);
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < MAX_N; i += EPI_WARPS * 32) s_b1[i] = (p.b1 && i < p.n_chunks * Cfg::CHUNK) ? p.b1[i] : 0.0f;
-    for (int i = threadIdx.x - 64; i < 256; i += EPI_WARPS * 32) {
+    for (int i = threadIdx.x - 64; i < MAX_N; i += LN_WARPS * 32) s_b1[i] = (p.b1 && i < p.n_chunks * Cfg::CHUNK) ? p.b1[i] : 0.0f;
+    for (int i = threadIdx.x - 64; i < 256; i += LN_WARPS * 32) {
       s_gamma[i] = p.gamma[i]; s_beta[i] = p.beta[i]; s_b2[i] = p.b2 ? p.b2[i] : 0.0f;
     }
   }
@@ -755,6 +764,11 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
+  tl_event(p.tl, tl_n, 41);                       // the previous kernel has completed
+  if (p.stagger > 0 && warp == 0) {               // only the producer is held back: everything else follows it
+    const long long t_end = clock64() + (long long)(cid & 3) * p.stagger;
+    while (clock64() < t_end) __nanosleep(200);
+  }
 
   // arrive on a barrier that lives in the leader CTA (2-SM) or in this CTA (1-SM)
   auto arrive_leader = [&](uint64_t* bar) {
@@ -889,11 +903,12 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue warps 2..9
+    // ------------------------------------------------------------------ epilogue warps 2..17
     const int q = warp & 3;                          // TMEM lane quarter
-    const int hf = (warp - 2) >> 2;                  // column half of a chunk / of the output row
+    const int cq = (warp - 2) >> 2;                  // column quarter: 32 of a chunk's 128 hidden columns (E1),
+                                                     // 64 of the 256 output columns (LayerNorm)
     const int row = q * 32 + lane;
-    uint8_t* const stg = hs + (warp - 2) * 8192;     // LayerNorm staging lives in the (then idle) Hs buffer
+    uint8_t* const stg = hs + (warp - 2) * 4096;     // LayerNorm staging lives in the (then idle) Hs buffer
     uint32_t r[32];
     float v[32];
     int g = 0;                                       // hidden chunks handled so far
@@ -905,106 +920,42 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         mbar_wait(smem_u32(&bar_a1full[b]), ((uint32_t)g >> 1) & 1u);
         tc_fence_after();
         tl_event(p.tl, tl_n, 13, c);                                 // E1(c): acc1 ready
-        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * Cfg::CHUNK + hf * 64);
-        uint32_t PH[2][16], PL[2][16];
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-          tmem_ld32(tacc + cc * 32, r);
-          epi_chunk_fast<ACT_GELU>(r, v, s_b1 + c * Cfg::CHUNK + hf * 64 + cc * 32, p.inv_s1);
-          pack_split(v, PH[cc], PL[cc]);
-        }
+        uint32_t PH[16], PL[16];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * Cfg::CHUNK + cq * 32), r);
+        epi_chunk_fast<ACT_GELU>(r, v, s_b1 + c * Cfg::CHUNK + cq * 32, p.inv_s1);
+        pack_split(v, PH, PL);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) arrive_leader(&bar_a1empty[b]);
         mbar_wait(smem_u32(bar_hempty), ((uint32_t)g & 1u) ^ 1u);     // F2(g - 1) has read Hs
-        // this thread's row, k-block hf: 128 B per plane = 8 x 16 B, 16-B index XOR (row & 7) (SWIZZLE_128B)
-        uint8_t* const hrow = hs + hf * 16384 + row * 128;
+        // this thread's row of k-block cq / 2, 64-byte half cq % 2: 4 x 16 B per plane, 16-B index XOR (row & 7)
+        // (SWIZZLE_128B)
+        uint8_t* const hrow = hs + (cq >> 1) * 16384 + row * 128;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-          for (int jj = 0; jj < 4; ++jj) {
-            const int sl = ((cc * 4 + jj) ^ (row & 7)) << 4;
-            *reinterpret_cast<uint4*>(hrow + sl) = make_uint4(PH[cc][4 * jj], PH[cc][4 * jj + 1], PH[cc][4 * jj + 2], PH[cc][4 * jj + 3]);
-            *reinterpret_cast<uint4*>(hrow + 32768 + sl) = make_uint4(PL[cc][4 * jj], PL[cc][4 * jj + 1], PL[cc][4 * jj + 2], PL[cc][4 * jj + 3]);
-          }
+        for (int jj = 0; jj < 4; ++jj) {
+          const int sl = (((cq & 1) * 4 + jj) ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(hrow + sl) = make_uint4(PH[4 * jj], PH[4 * jj + 1], PH[4 * jj + 2], PH[4 * jj + 3]);
+          *reinterpret_cast<uint4*>(hrow + 32768 + sl) = make_uint4(PL[4 * jj], PL[4 * jj + 1], PL[4 * jj + 2], PL[4 * jj + 3]);
+        }
         fence_proxy_async_smem();                    // generic-proxy writes -> tcgen05.mma reads
         __syncwarp();
         tl_event(p.tl, tl_n, 14, c);                                 // E1(c): Hs written
         if (lane == 0) arrive_leader(bar_hfull);
       }
-      // ---- residual + LayerNorm on acc2.  Two warps share a row (column halves of 128): each keeps
-      // one-pass statistics shifted by ITS first value and the halves are merged with the pairwise
-      // (Chan) update through shared memory; the pre-norm row is parked in TMEM between the passes.
-      // The residual is prefetched two 32-column chunks ahead (the first two before the accumulator is awaited).
+      // ---- residual + LayerNorm on acc2 (ln16_finish: sixteen warps, a row's four column quarters merged
+      // through shared memory); the first residual chunk is requested before the accumulator is awaited
       const int wrow0 = m0 + q * 32;
       const int rows_valid = min(32, p.M - wrow0);
-      const int cb = hf * 128;
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * Cfg::CHUNK + cb);
-      const bool has_res = p.res_hi != nullptr;
-      const __half* rbh = p.res_hi + (int64_t)wrow0 * p.ld_res + cb;
-      const __half* rbl = p.res_lo + (int64_t)wrow0 * p.ld_res + cb;
-      uint4 gh[2][4], gl[2][4];                      // two residual chunks in flight
-      if (has_res) {
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          load_plane_issue(rbh + c * 32, p.ld_res, rows_valid, lane, gh[c]);
-          load_plane_issue(rbl + c * 32, p.ld_res, rows_valid, lane, gl[c]);
-        }
-      }
+      LnResidual t;
+      ln16_issue_residual(t, p.res_hi, p.res_lo, p.ld_res, wrow0, cq * 64, rows_valid, lane);
       mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);      // all F2 MMAs retired: acc2 complete, Hs idle
       tc_fence_after();
       tl_event(p.tl, tl_n, 15, j);                                   // LN tail: acc2 ready
-      float s1 = 0.0f, s2 = 0.0f, shiftK = 0.0f;
-      const float sc = p.inv_s2;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint4 rh[4], rl[4];
-        if (has_res) {
-          planes_to_rows(stg, gh[c & 1], gl[c & 1], lane, rh, rl);
-          if (c + 2 < 4) {
-            load_plane_issue(rbh + (c + 2) * 32, p.ld_res, rows_valid, lane, gh[c & 1]);
-            load_plane_issue(rbl + (c + 2) * 32, p.ld_res, rows_valid, lane, gl[c & 1]);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) { rh[i] = make_uint4(0, 0, 0, 0); rl[i] = make_uint4(0, 0, 0, 0); }
-        }
-        tmem_ld32(trow + c * 32, r);
-        if (c == 0) shiftK = ln_shift(r, rh, rl, s_b2 + cb, sc);
-        ln_stats_chunk(r, rh, rl, s_b2 + cb + c * 32, sc, shiftK, s1, s2);
-        tmem_st32(trow + c * 32, r);
-      }
-      // this half: mean_h = K + s1/128, M2_h = s2 - s1^2/128
-      const float mean_h = shiftK + s1 * (1.0f / 128), m2_h = fmaxf(s2 - s1 * s1 * (1.0f / 128), 0.0f);
-      s_part[hf * 256 + row] = mean_h;
-      s_part[hf * 256 + 128 + row] = m2_h;
-      epi_bar_sync();
-      const float mean_o = s_part[(hf ^ 1) * 256 + row], m2_o = s_part[(hf ^ 1) * 256 + 128 + row];
-      const float dm = mean_h - mean_o;
-      const float mean = 0.5f * (mean_h + mean_o);
-      const float var = (m2_h + m2_o + dm * dm * 64.0f) * (1.0f / 256);
-      const float rstd = rsqrtf(var + 1e-5f);
-      const float nb_ = -mean * rstd;
-      int tbuf = 0;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        tmem_ld32(trow + c * 32, r);
-        ln_norm_chunk(r, v, s_gamma + cb + c * 32, s_beta + cb + c * 32, rstd, nb_);
-        uint32_t ph[16], pl[16];
-        pack_split(v, ph, pl);
-        if (p.tma_out) {
-          stage_and_store(stg + tbuf * 4096, ph, pl, lane, &tmOh, &tmOl, cb + c * 32, wrow0);
-          tbuf ^= 1;
-        } else {
-          const int64_t o = (int64_t)wrow0 * p.ld_out + cb + c * 32;
-          store_plane_coalesced(stg, ph, p.out_hi + o, p.ld_out, rows_valid, lane);
-          store_plane_coalesced(stg, pl, p.out_lo + o, p.ld_out, rows_valid, lane);
-        }
-      }
-      // Hs (the staging) is rewritten by the next tile's E1 and s_part by its LayerNorm: the TMA engine
-      // must have read the staging and everyone must have read the partial statistics
-      if (p.tma_out && lane == 0) tma_store_wait_read<0>();
-      epi_bar_sync();
+      ln16_finish<true>(t, p.res_hi, p.res_lo, p.ld_res,
+                        tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * Cfg::CHUNK + cq * 64), cq, row, lane, stg,
+                        s_b2, s_gamma, s_beta, s_part, p.inv_s2, wrow0, rows_valid, p.tma_out != 0, &tmOh, &tmOl,
+                        p.out_hi, p.out_lo, p.ld_out, p.tl, tl_n);
+      // (ln16_finish ends with a barrier over the sixteen warps: Hs - the staging - is free for the next E1)
       tc_fence_before();
       __syncwarp();
       tl_event(p.tl, tl_n, 16, j);                                   // LN tail done
@@ -1014,6 +965,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   tc_fence_before();
   __syncthreads();
   if (CG > 1) cluster_sync_all();
+  tl_event(p.tl, tl_n, 42);                       // kernel exit
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
@@ -1047,13 +999,13 @@ TcCtx* tc_create(int device) {
   auto opt_in = [&](auto kernel, int bytes) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   };
-  opt_in(k_gemm_tc<256, 1, EPI_FAST>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1, EPI_FAST>, TileCfg<128, 1>::SMEM_BYTES);
-  opt_in(k_gemm_tc<256, 2, EPI_FAST>, TileCfg<256, 2>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2, EPI_FAST>, TileCfg<128, 2>::SMEM_BYTES);
-  opt_in(k_gemm_tc<256, 1, EPI_FAST, ACT_GELU>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1, EPI_FAST, ACT_GELU>, TileCfg<128, 1>::SMEM_BYTES);
-  opt_in(k_gemm_tc<256, 2, EPI_FAST, ACT_GELU>, TileCfg<256, 2>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2, EPI_FAST, ACT_GELU>, TileCfg<128, 2>::SMEM_BYTES);
-  opt_in(k_gemm_tc<256, 1, EPI_GENERIC>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1, EPI_GENERIC>, TileCfg<128, 1>::SMEM_BYTES);
-  opt_in(k_gemm_tc<256, 2, EPI_GENERIC>, TileCfg<256, 2>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2, EPI_GENERIC>, TileCfg<128, 2>::SMEM_BYTES);
-  opt_in(k_gemm_tc<256, 1, EPI_LN>, TileCfg<256, 1>::SMEM_BYTES); opt_in(k_gemm_tc<256, 2, EPI_LN>, TileCfg<256, 2>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 1, EPI_FAST>, TileCfg<256, 1, EPI_FAST>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1, EPI_FAST>, TileCfg<128, 1, EPI_FAST>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 2, EPI_FAST>, TileCfg<256, 2, EPI_FAST>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2, EPI_FAST>, TileCfg<128, 2, EPI_FAST>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 1, EPI_FAST, ACT_GELU>, TileCfg<256, 1, EPI_FAST>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1, EPI_FAST, ACT_GELU>, TileCfg<128, 1, EPI_FAST>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 2, EPI_FAST, ACT_GELU>, TileCfg<256, 2, EPI_FAST>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2, EPI_FAST, ACT_GELU>, TileCfg<128, 2, EPI_FAST>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 1, EPI_GENERIC>, TileCfg<256, 1, EPI_GENERIC>::SMEM_BYTES); opt_in(k_gemm_tc<128, 1, EPI_GENERIC>, TileCfg<128, 1, EPI_GENERIC>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 2, EPI_GENERIC>, TileCfg<256, 2, EPI_GENERIC>::SMEM_BYTES); opt_in(k_gemm_tc<128, 2, EPI_GENERIC>, TileCfg<128, 2, EPI_GENERIC>::SMEM_BYTES);
+  opt_in(k_gemm_tc<256, 2, EPI_LN>, TileCfg<256, 2, EPI_LN>::SMEM_BYTES);
   opt_in(k_ffn_tc<1>, FfnCfg<1>::SMEM_BYTES); opt_in(k_ffn_tc<2>, FfnCfg<2>::SMEM_BYTES);
   if (e != cudaSuccess) {
     mldb_set_err(std::string("cudaFuncSetAttribute(k_gemm_tc): ") + cudaGetErrorString(e));
@@ -1090,6 +1042,11 @@ static bool make_map_out(const TcCtx* c, CUtensorMap* m, const __half* base, int
   return r == CUDA_SUCCESS;
 }
 
+template <int EPI, int ACT = ACT_NONE>
+static constexpr int threads_of() { return EPI == EPI_LN ? LN_THREADS : NUM_THREADS; }
+template <int BN, int CG, int EPI, int ACT = ACT_NONE>
+static constexpr int smem_of() { return TileCfg<BN, CG, EPI>::SMEM_BYTES; }
+
 static int pick_bn(const GemmArgs& g) { return (g.w.N % 256 == 0) ? 256 : 128; }
 
 bool tc_gemm_supported(const TcCtx* c, const GemmArgs& g) {
@@ -1104,7 +1061,7 @@ bool tc_gemm_supported(const TcCtx* c, const GemmArgs& g) {
 }
 
 bool tc_gemm_ln_supported(const TcCtx* c, const GemmArgs& g, const LnArgs& l) {
-  if (!tc_gemm_supported(c, g)) return false;
+  if (!tc_gemm_supported(c, g) || c->sm_count % 2) return false;
   if (g.w.N != 256 || l.d != 256 || g.act != ACT_NONE) return false;
   if (l.in_group != 0 || l.c != nullptr || l.out_f32 != nullptr || !l.out.hi) return false;
   if (l.out.cols != 256 || (l.res.hi && l.res.cols != 256)) return false;
@@ -1146,7 +1103,9 @@ bool tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   if (g.K2 > 0) ok = ok && make_map(c, &mA2h, g.a2.hi, g.M, g.K2, BM) && make_map(c, &mA2l, g.a2.lo(), g.M, g.K2, BM);
   else { mA2h = mA1h; mA2l = mA1l; }
   const int m_tiles_ = (g.M + BM - 1) / BM;
-  const int cl = (m_tiles_ >= 4 && c->sm_count % 2 == 0) ? 2 : 1;   // small problems: no pairs
+  // small problems: no pairs.  The LayerNorm epilogue exists for pairs only (its 16-warp staging does not fit
+  // next to a full-width W stage) - tc_gemm_ln_supported() has checked that the SM count is even.
+  const int cl = ((m_tiles_ >= 4 || ln) && c->sm_count % 2 == 0) ? 2 : 1;
   ok = ok && make_map(c, &mWh, g.w.w, g.w.N, g.w.K, bn / cl) &&
        make_map(c, &mWl, g.w.w + g.w.plane_stride, g.w.N, g.w.K, bn / cl);
   if (!ok) return map_fail("gemm", g.M, g.w.N, g.w.K);
@@ -1155,7 +1114,8 @@ bool tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   CUtensorMap mOh = mA1h, mOl = mA1l;
   // the fast plain epilogue: split16 output, identity row mapping, N a whole number of tiles
   const bool fast = !ln && g.out.hi && !g.out_f32 && !g.addtab && !g.zero_lengths && g.in_group >= g.M &&
-                    g.out_group == 0 && g.out_off == 0 && g.w.N % bn == 0 && (g.act == ACT_NONE || g.act == ACT_GELU);
+                    g.out_group == 0 && g.out_off == 0 && g.w.N % bn == 0 && g.w.bias != nullptr &&
+                    (g.act == ACT_NONE || g.act == ACT_GELU);
   if (cl == 2 && ln) {
     if (!make_map_out(c, &mOh, ln->out.hi, g.M, 256, ln->out.cols) || !make_map_out(c, &mOl, ln->out.lo(), g.M, 256, ln->out.cols))
       return map_fail("gemm ln out", g.M, g.w.N, g.w.K);
@@ -1170,14 +1130,14 @@ bool tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   const int ncl = ngroups < c->sm_count / cl ? ngroups : c->sm_count / cl;
   dim3 grid(ncl * cl);
 #define MLDB_LAUNCH(BN_, CL_, ...)                                                                                       \
-  launch_pdl_cluster(k_gemm_tc<BN_, CL_, __VA_ARGS__>, grid, dim3(NUM_THREADS), TileCfg<BN_, CL_>::SMEM_BYTES, st, CL_, \
+  launch_pdl_cluster(k_gemm_tc<BN_, CL_, __VA_ARGS__>, grid, dim3(threads_of<__VA_ARGS__>()), smem_of<BN_, CL_, __VA_ARGS__>(), st, CL_, \
                      mA1h, mA1l, mA2h, mA2l, mWh, mWl, mOh, mOl, p)
 #define MLDB_LAUNCH_SHAPE(...)                                                                        \
   do {                                                                                                \
     if (bn == 256) { if (cl == 2) MLDB_LAUNCH(256, 2, __VA_ARGS__); else MLDB_LAUNCH(256, 1, __VA_ARGS__); } \
     else           { if (cl == 2) MLDB_LAUNCH(128, 2, __VA_ARGS__); else MLDB_LAUNCH(128, 1, __VA_ARGS__); } \
   } while (0)
-  if (ln)                           { if (cl == 2) MLDB_LAUNCH(256, 2, EPI_LN); else MLDB_LAUNCH(256, 1, EPI_LN); }
+  if (ln)                           { if (cl != 2) return map_fail("gemm ln needs CTA pairs", g.M, g.w.N, g.w.K); MLDB_LAUNCH(256, 2, EPI_LN); }
   else if (fast && g.act == ACT_GELU) MLDB_LAUNCH_SHAPE(EPI_FAST, ACT_GELU);
   else if (fast)                      MLDB_LAUNCH_SHAPE(EPI_FAST);
   else                                MLDB_LAUNCH_SHAPE(EPI_GENERIC);
@@ -1222,13 +1182,14 @@ bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, 
   p.res_hi = l2.res.hi; p.res_lo = l2.res.hi ? l2.res.lo() : nullptr; p.ld_res = l2.res.cols;
   p.out_hi = l2.out.hi; p.out_lo = l2.out.lo(); p.ld_out = l2.out.cols;
   p.tma_out = 1;
+  { const char* e = getenv("MLDB_FFN_STAGGER"); p.stagger = e ? atoi(e) : 0; }
   const int groups = (m_tiles + cg - 1) / cg;
   const int ncl = groups < c->sm_count / cg ? groups : c->sm_count / cg;
   if (cg == 2)
-    launch_pdl_cluster(k_ffn_tc<2>, dim3(ncl * 2), dim3(NUM_THREADS), FfnCfg<2>::SMEM_BYTES, st, 2, mXh, mXl, mW1h, mW1l,
+    launch_pdl_cluster(k_ffn_tc<2>, dim3(ncl * 2), dim3(LN_THREADS), FfnCfg<2>::SMEM_BYTES, st, 2, mXh, mXl, mW1h, mW1l,
                        mW2h, mW2l, mOh, mOl, p);
   else
-    launch_pdl(k_ffn_tc<1>, dim3(ncl), dim3(NUM_THREADS), FfnCfg<1>::SMEM_BYTES, st, mXh, mXl, mW1h, mW1l, mW2h, mW2l,
+    launch_pdl(k_ffn_tc<1>, dim3(ncl), dim3(LN_THREADS), FfnCfg<1>::SMEM_BYTES, st, mXh, mXl, mW1h, mW1l, mW2h, mW2l,
                mOh, mOl, p);
   return true;
 }

@@ -6,9 +6,10 @@ import torch
 from mld_b200 import synth, _lib
 from mld_b200.engine import Engine, make_config
 
-TAGS = {1: "prod:tile", 2: "mma:tile_begin", 3: "mma:tile_issued", 4: "epi:acc_ready", 5: "epi:drained", 6: "ln:res_issued", 7: "ln:stats_done",
+TAGS = {1: "prod:tile", 2: "mma:tile_begin", 3: "mma:tile_issued", 4: "epi:acc_ready", 5: "epi:drained", 6: "ln:res_issued", 7: "ln:stats_done", 17: "ln:merged", 18: "ln:stores_issued",
         10: "mma:F1_start", 11: "mma:F1_issued", 12: "mma:F2_start", 13: "e1:acc1_ready", 14: "e1:hs_written", 15: "ln:acc2_ready", 16: "ln:done",
         20: "prod:Q", 21: "prod:Vslot", 22: "mma:S_go", 23: "mma:K_landed", 24: "mma:S_issued", 25: "mma:P_written", 26: "mma:V_landed",
+        40: "entry", 41: "pdl_waited", 42: "exit",
         30: "sm:wait_S", 31: "sm:S_ready", 32: "sm:pass1", 33: "sm:pass2", 34: "sm:O_ready", 35: "sm:epi_done"}
 op = sys.argv[1] if len(sys.argv) > 1 else "attn"
 maxe = int(sys.argv[2]) if len(sys.argv) > 2 else 400

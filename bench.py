@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_power_cap,power.limit")
         try:
             self._p = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
                                         "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -99,8 +99,18 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        def col(i):
+            out = []
+            for r in self.rows:
+                try:
+                    out.append(float(r[i]))
+                except (IndexError, ValueError):
+                    pass
+            return out
+        pw, pl = col(2), col(7)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w": statistics.median(pw) if pw else None,
+                "power_limit_w": max(pl) if pl else None}
 
 
 # ------------------------------------------------------------------------------------ model setups

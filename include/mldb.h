@@ -284,6 +284,10 @@ int mldb_reset_kernel_stats(mldb_handle* h);
  *   "gemm"       "tc" | "simt"          tcgen05 kernels (default) or the CUDA-core reference kernels  MLDB_GEMM
  *   "attn"       "tc" | "mma" | "simt"  attention core: tcgen05 (default), mma.sync, CUDA cores       MLDB_ATTN
  *   "ffn_fused"  0 | 1                  fused FFN kernel k_ffn_tc (default 1)
+ *   "ffn_split"  0 | 1                  fused FFN: cut the tile groups that do not fill a whole round of the
+ *                                        persistent grid along the hidden dimension (default 1; env MLDB_FFN_SPLIT).
+ *                                        Results stay bit-identical run to run, but the rows of a split tile are
+ *                                        summed in a different order, so they depend on the batch size in the last bits
  *   "branches"   1..4                   concurrent sub-batch branches inside a denoiser step (2)      MLDB_BRANCHES
  *   "graph"      0 | 1                  CUDA-graph replay of the step loop (1)                        MLDB_GRAPH
  * Environment only: MLDB_PDL (programmatic dependent launch, 1). */

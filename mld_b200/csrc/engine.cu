@@ -389,7 +389,9 @@ static void op_attn(mldb_handle* h, const AttnArgs& a, cudaStream_t st) {
 static void op_ffn(mldb_handle* h, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, float* cf32, cudaStream_t st) {
   if (h->use_tc && tc_ffn_supported(h->tc, g1, g2, l2)) {
     // one launch: the hidden activations stay in shared memory / TMEM (gemm_tc.cu k_ffn_tc)
-    if (!tc_ffn(h->tc, g1, g2, l2, st)) h->op_failed = true;
+    int k = 0;                                     // which stream: its own scratch (branches run concurrently)
+    for (int i = 0; i < mldb_handle::MAX_BRANCHES - 1; ++i) if (st == h->br_stream[i]) k = i + 1;
+    if (!tc_ffn(h->tc, g1, g2, l2, h->ffn_scratch[k], h->ffn_flags[k], st)) h->op_failed = true;
     kcount(h, MLDB_KSTAT_FFN_TC);
     return;
   }
@@ -649,6 +651,14 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming);
   }
   if (e != cudaSuccess) { mldb_destroy(h); FAIL(MLDB_ERR_CUDA, "branch streams: %s", cudaGetErrorString(e)); }
+  for (int i = 0; i < mldb_handle::MAX_BRANCHES && e == cudaSuccess; ++i) {
+    e = cudaMalloc((void**)&h->ffn_scratch[i], TC_FFN_SCRATCH_BYTES);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&h->ffn_flags[i], TC_FFN_FLAG_BYTES);
+    if (e == cudaSuccess) e = cudaMemset(h->ffn_flags[i], 0, TC_FFN_FLAG_BYTES);
+  }
+  if (e != cudaSuccess) { mldb_destroy(h); FAIL(MLDB_ERR_CUDA, "ffn scratch: %s", cudaGetErrorString(e)); }
+  env = getenv("MLDB_FFN_SPLIT");
+  if (env) tc_set_ffn_split(h->tc, atoi(env) != 0);
   *out = h;
   return MLDB_OK;
 }
@@ -668,6 +678,7 @@ extern "C" void mldb_destroy(mldb_handle* h) {
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  for (int i = 0; i < mldb_handle::MAX_BRANCHES; ++i) { cudaFree(h->ffn_scratch[i]); cudaFree(h->ffn_flags[i]); }
   mldb_comm_release(h);
   tc_destroy(h->tc);
   delete h;
@@ -681,6 +692,8 @@ extern "C" int mldb_set_option(mldb_handle* h, const char* name, const char* val
     else FAIL(MLDB_ERR_INVALID, "gemm must be tc|simt");
   } else if (!strcmp(name, "ffn_fused")) {
     tc_set_ffn_fused(h->tc, atoi(value) != 0);
+  } else if (!strcmp(name, "ffn_split")) {
+    tc_set_ffn_split(h->tc, atoi(value) != 0);
   } else if (!strcmp(name, "attn")) {
     if (!strcmp(value, "tc")) h->attn_kind = 0;
     else if (!strcmp(value, "mma")) h->attn_kind = 1;

@@ -131,6 +131,10 @@ struct mldb_handle {
   bool op_failed = false;    // an operator could not be enqueued (tensor-map encoding): sticky until reported
   static constexpr int MAX_BRANCHES = 4;
   cudaStream_t br_stream[MAX_BRANCHES - 1] = {};
+  // partial-accumulator scratch + flags of the fused FFN's hidden-dimension split (gemm_tc.h), one per stream a
+  // stack can run on: [0] the caller's stream, [k] br_stream[k - 1]
+  float* ffn_scratch[MAX_BRANCHES] = {};
+  int* ffn_flags[MAX_BRANCHES] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[MAX_BRANCHES - 1] = {};
   TcCtx* tc = nullptr;
   // the path's one collective (comm.cu): NCCL communicator bound at run time, gathers on a side stream

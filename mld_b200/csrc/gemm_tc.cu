@@ -248,7 +248,8 @@ __device__ __forceinline__ void ln16_finish(LnResidual& t, const __half* res_hi,
                                             const float* s_bias, const float* s_gamma, const float* s_beta, float* s_part,
                                             float sc, int wrow0, int rows_valid, bool tma_out, const CUtensorMap* mOh,
                                             const CUtensorMap* mOl, __half* out_hi, __half* out_lo, int ld_out,
-                                            long long* tl, int& tl_n) {
+                                            long long* tl, int& tl_n, const float* part0 = nullptr, int nparts = 0,
+                                            size_t part_stride = 0) {
   const int cb = cq * 64;
   uint32_t r[32];
   float v[32];
@@ -256,6 +257,25 @@ __device__ __forceinline__ void ln16_finish(LnResidual& t, const __half* res_hi,
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     tmem_ld32(trow + c * 32, r);
+    // partial accumulators of the same tile computed by other clusters (k_ffn_tc's hidden-dimension split),
+    // added in a fixed order
+    for (int pp = 0; pp < nparts; ++pp) {
+      const float4* src = reinterpret_cast<const float4*>(part0 + (size_t)pp * part_stride) + ((cq * 16 + c * 8) * 128 + row);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float4 a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = __ldcg(src + (hh * 4 + i) * 128);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = (hh * 4 + i) * 4;
+          r[e + 0] = __float_as_uint(__uint_as_float(r[e + 0]) + a[i].x);
+          r[e + 1] = __float_as_uint(__uint_as_float(r[e + 1]) + a[i].y);
+          r[e + 2] = __float_as_uint(__uint_as_float(r[e + 2]) + a[i].z);
+          r[e + 3] = __float_as_uint(__uint_as_float(r[e + 3]) + a[i].w);
+        }
+      }
+    }
     // x = acc * sc + bias, then + residual hi plane, then + lo plane (one plane at a time: the row-owner copy
     // of a plane is 16 registers, and 112 per thread is all there is with 576 threads)
     const float4* b4 = reinterpret_cast<const float4*>(s_bias + cb + c * 32);
@@ -664,6 +684,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
 // W2 k-blocks through one ring (2 x 64 KB; 3 x 48 KB per CTA of a pair) in exactly that order.
 struct FfnParams {
   int M, m_tiles, n_chunks;
+  // Work decomposition (see k_ffn_tc): every cluster runs `full` whole m-tile groups; the `left` groups that do
+  // not fill another round are cut along the hidden dimension into `parts` pieces, one per cluster.
+  int full, left, parts;
+  float* scratch;              // [slot][64 column groups][128 rows][4] fp32 partial accumulators of the pieces
+  int* flags;                  // [slot] 1 = partial written (reset by the reader)
   int stagger;                 // experiment: start-up delay of cluster c = (c & 3) * stagger cycles
   long long* tl;
   float inv_s1, inv_s2;
@@ -727,10 +752,21 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   tl_event(p.tl, tl_n, 40);                       // kernel entry
   const int rank = CG > 1 ? (int)cluster_ctarank() : 0;
   const int ncl = (int)gridDim.x / CG, cid = (int)blockIdx.x / CG;
-  const int ngroups = (p.m_tiles + CG - 1) / CG;
   const int NC = p.n_chunks;
-  const int nlocal = (ngroups - cid + ncl - 1) / ncl;
-  auto mgroup = [&](int j) { return cid + j * ncl; };        // m-tile group of the j-th local item
+  // Items of this cluster: `full` whole tile groups (cid, cid + ncl, ...), then - for the first left * parts
+  // clusters - one PIECE of a leftover group: hidden chunks [c0, c1) of group full * ncl + cid / parts.  Pieces
+  // 0 .. parts-2 are contributors (their raw fp32 accumulator goes to `scratch`), the last piece is the finisher
+  // (adds the contributors' accumulators in piece order, then bias + residual + LayerNorm as for a whole tile).
+  // Contributors have lower cluster ids than their finisher, so they are scheduled no later than it.
+  struct Item { int mg, c0, c1, mode, piece0; };             // mode: 0 whole tile, 1 contributor, 2 finisher
+  const int nlocal = p.full + (cid < p.left * p.parts ? 1 : 0);
+  auto item = [&](int j) -> Item {
+    if (j < p.full) return Item{cid + j * ncl, 0, NC, 0, 0};
+    const int t = cid / p.parts, part = cid - t * p.parts;
+    const int c0 = (part * NC + p.parts - 1) / p.parts, c1 = ((part + 1) * NC + p.parts - 1) / p.parts;
+    const int slot0 = (t * (p.parts - 1)) * CG + rank;       // slot of piece k of this CTA's rows: slot0 + k * CG
+    return Item{p.full * ncl + t, c0, c1, p.parts == 1 ? 0 : (part == p.parts - 1 ? 2 : 1), p.parts == 1 ? 0 : slot0 + (part == p.parts - 1 ? 0 : part * CG)};
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -796,22 +832,23 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       else tma_load_2d_2sm(dst, map, full, c0, c1);
     };
     for (int j = 0; j < nlocal; ++j) {
-      const int m0 = (mgroup(j) * CG + rank) * BM;
-      for (int i = 0; i <= NC; ++i) {
-        if (i < NC) {
+      const Item it = item(j);
+      const int m0 = (it.mg * CG + rank) * BM, nch = it.c1 - it.c0;
+      for (int i = 0; i <= nch; ++i) {
+        if (i < nch) {
           for (int kb = 0; kb < 4; ++kb, ++kbg) {
             mbar_wait(smem_u32(&bar_empty[kbg % STAGES]), (((uint32_t)(kbg / STAGES)) & 1u) ^ 1u);
             if (elect_one()) {
               if (i == 0 && kb == 0 && j + 1 < nlocal) {      // next tile's x rows -> L2, a whole tile ahead
-                const int m1 = (mgroup(j + 1) * CG + rank) * BM;
+                const int m1 = (item(j + 1).mg * CG + rank) * BM;
                 for (int k2 = 0; k2 < 4; ++k2) { tma_prefetch_2d(&tmXh, k2 * BK, m1); tma_prefetch_2d(&tmXl, k2 * BK, m1); }
               }
               uint32_t full;
               const uint32_t dst = stage_begin(Cfg::F1_BYTES, full);
               load(dst, &tmXh, full, kb * BK, m0);
               load(dst + 16384, &tmXl, full, kb * BK, m0);
-              load(dst + 32768, &tmW1h, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
-              load(dst + 32768 + Cfg::W1_BYTES, &tmW1l, full, kb * BK, i * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
+              load(dst + 32768, &tmW1h, full, kb * BK, (it.c0 + i) * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
+              load(dst + 32768 + Cfg::W1_BYTES, &tmW1l, full, kb * BK, (it.c0 + i) * Cfg::CHUNK + rank * (Cfg::CHUNK / CG));
             }
             __syncwarp();
           }
@@ -822,8 +859,8 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
             if (elect_one()) {
               uint32_t full;
               const uint32_t dst = stage_begin(Cfg::F2_BYTES, full);
-              load(dst, &tmW2h, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
-              load(dst + Cfg::W2_BYTES, &tmW2l, full, (i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
+              load(dst, &tmW2h, full, (it.c0 + i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
+              load(dst + Cfg::W2_BYTES, &tmW2l, full, (it.c0 + i - 1) * Cfg::CHUNK + kb * BK, rank * (256 / CG));
             }
             __syncwarp();
           }
@@ -861,8 +898,10 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       };
       int kbg = 0, g1 = 0, g2 = 0;                 // ring position, F1 chunks issued, F2 chunks issued
       for (int j = 0; j < nlocal; ++j) {
-        for (int i = 0; i <= NC; ++i) {
-          if (i < NC) {                            // F1(i)
+        const Item it = item(j);
+        const int nch = it.c1 - it.c0;             // hidden chunks of this item
+        for (int i = 0; i <= nch; ++i) {
+          if (i < nch) {                           // F1(i)
             const int b = g1 & 1;
             wait_epi(&bar_a1empty[b], (((uint32_t)g1 >> 1) & 1u) ^ 1u);
             tc_fence_after();
@@ -895,7 +934,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
               const uint32_t sWh = smem_u32(smem + s * Cfg::STAGE_BYTES);
               kblock(tacc, hs_u + kb * 16384, hs_u + 32768 + kb * 16384, sWh, sWh + Cfg::W2_BYTES, idesc2,
                      i == 1 && kb == 0, &bar_empty[s], kb == 1 ? bar_hempty : nullptr,
-                     (kb == 1 && i == NC) ? bar_a2full : nullptr);
+                     (kb == 1 && i == nch) ? bar_a2full : nullptr);
             }
             ++g2;
           }
@@ -913,9 +952,10 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
     float v[32];
     int g = 0;                                       // hidden chunks handled so far
     for (int j = 0; j < nlocal; ++j) {
-      const int m0 = (mgroup(j) * CG + rank) * BM;
+      const Item it = item(j);
+      const int m0 = (it.mg * CG + rank) * BM;
       // ---- E1: hidden chunks -> Hs
-      for (int c = 0; c < NC; ++c, ++g) {
+      for (int c = it.c0; c < it.c1; ++c, ++g) {
         const int b = g & 1;
         mbar_wait(smem_u32(&bar_a1full[b]), ((uint32_t)g >> 1) & 1u);
         tc_fence_after();
@@ -942,6 +982,31 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         tl_event(p.tl, tl_n, 14, c);                                 // E1(c): Hs written
         if (lane == 0) arrive_leader(bar_hfull);
       }
+      const uint32_t trow2 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * Cfg::CHUNK + cq * 64);
+      if (it.mode == 1) {
+        // ---- contributor piece: the raw fp32 accumulator -> scratch ([column group of 4][row][4]: a warp's
+        // 32 rows are 512 contiguous bytes per store), then the flag
+        mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);
+        tc_fence_after();
+        tl_event(p.tl, tl_n, 15, j);
+        float4* const dst = reinterpret_cast<float4*>(p.scratch + (size_t)it.piece0 * (BM * 256));
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tmem_ld32(trow2 + c * 32, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            dst[(cq * 16 + c * 8 + i) * 128 + row] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                                                  __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+        }
+        __threadfence();
+        ln_bar_sync();
+        if (threadIdx.x == 64) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.flags + it.piece0), "r"(1) : "memory");
+        tc_fence_before();
+        __syncwarp();
+        tl_event(p.tl, tl_n, 16, j);
+        if (lane == 0) arrive_leader(bar_a2empty);
+        continue;
+      }
       // ---- residual + LayerNorm on acc2 (ln16_finish: sixteen warps, a row's four column quarters merged
       // through shared memory); the first residual chunk is requested before the accumulator is awaited
       const int wrow0 = m0 + q * 32;
@@ -951,10 +1016,27 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);      // all F2 MMAs retired: acc2 complete, Hs idle
       tc_fence_after();
       tl_event(p.tl, tl_n, 15, j);                                   // LN tail: acc2 ready
-      ln16_finish<true>(t, p.res_hi, p.res_lo, p.ld_res,
-                        tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(2 * Cfg::CHUNK + cq * 64), cq, row, lane, stg,
+      const int nparts = it.mode == 2 ? p.parts - 1 : 0;
+      if (nparts > 0) {                                      // finisher: the contributors' partials must have landed
+        if (lane == 0) {
+          for (int pp = 0; pp < nparts; ++pp) {
+            const int* f = p.flags + it.piece0 + pp * CG;
+            uint32_t v = 0;
+            long long t_end = clock64() + 4000000000ll;      // ~2 s: a lost contributor is a bug, trap instead of hanging
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+              if (v == 0 && clock64() > t_end) __trap();
+            } while (v == 0);
+          }
+        }
+        __syncwarp();
+      }
+      ln16_finish<true>(t, p.res_hi, p.res_lo, p.ld_res, trow2, cq, row, lane, stg,
                         s_b2, s_gamma, s_beta, s_part, p.inv_s2, wrow0, rows_valid, p.tma_out != 0, &tmOh, &tmOl,
-                        p.out_hi, p.out_lo, p.ld_out, p.tl, tl_n);
+                        p.out_hi, p.out_lo, p.ld_out, p.tl, tl_n,
+                        nparts > 0 ? p.scratch + (size_t)it.piece0 * (BM * 256) : nullptr, nparts, (size_t)CG * (BM * 256));
+      if (nparts > 0 && threadIdx.x == 64)                   // everyone is past its partial loads: re-arm the flags
+        for (int pp = 0; pp < nparts; ++pp) p.flags[it.piece0 + pp * CG] = 0;
       // (ln16_finish ends with a barrier over the sixteen warps: Hs - the staging - is free for the next E1)
       tc_fence_before();
       __syncwarp();
@@ -979,6 +1061,7 @@ struct TcCtx {
   int device = 0;
   int sm_count = 148;
   int ffn_fused = 1;          // FFN1 + GELU + FFN2 + residual + LayerNorm as one launch (option ffn_fused)
+  int ffn_split = 1;          // cut the leftover tile groups of the fused FFN along the hidden dimension (option ffn_split)
   tc::PFN_tmapEncodeTiled encode = nullptr;
 };
 
@@ -1147,6 +1230,12 @@ bool tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
 }
 
 // FFN block (linear1 + GELU + linear2 + residual + LayerNorm) as one launch, d = 256.
+int tc_set_ffn_split(TcCtx* c, int on) {
+  if (!c) return 0;
+  const int old = c->ffn_split;
+  c->ffn_split = on;
+  return old;
+}
 int tc_set_ffn_fused(TcCtx* c, int on) {
   if (!c) return 0;
   const int old = c->ffn_fused;
@@ -1162,7 +1251,7 @@ bool tc_ffn_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, co
   if (g1.in_group < g1.M || g1.out_group != 0 || g1.out_off != 0) return false;
   return true;
 }
-bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, cudaStream_t st) {
+bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, float* scratch, int* flags, cudaStream_t st) {
   CUtensorMap mXh, mXl, mW1h, mW1l, mW2h, mW2l, mOh, mOl;
   const int m_tiles = (g1.M + BM - 1) / BM;
   const int cg = (m_tiles >= 2 && c->sm_count % 2 == 0) ? 2 : 1;
@@ -1184,7 +1273,17 @@ bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, 
   p.tma_out = 1;
   { const char* e = getenv("MLDB_FFN_STAGGER"); p.stagger = e ? atoi(e) : 0; }
   const int groups = (m_tiles + cg - 1) / cg;
-  const int ncl = groups < c->sm_count / cg ? groups : c->sm_count / cg;
+  const int ncl_max = c->sm_count / cg;
+  // whole rounds of tile groups, then the leftover groups cut along the hidden dimension so that the last
+  // round uses (nearly) every cluster instead of `left` of them (FfnParams).  scratch == nullptr, a knob
+  // (MLDB_FFN_SPLIT=0) or left * 2 > clusters: the leftover groups run as whole tiles.
+  p.full = groups / ncl_max; p.left = groups % ncl_max; p.parts = 1;
+  p.scratch = scratch; p.flags = flags;
+  if (p.left > 0 && scratch && flags && c->ffn_split) {
+    const int parts = std::min(p.n_chunks, ncl_max / p.left);
+    if (parts >= 2 && (size_t)p.left * (parts - 1) * cg * (BM * 256 * 4) <= TC_FFN_SCRATCH_BYTES) p.parts = parts;
+  }
+  const int ncl = p.full > 0 ? ncl_max : p.left * p.parts;
   if (cg == 2)
     launch_pdl_cluster(k_ffn_tc<2>, dim3(ncl * 2), dim3(LN_THREADS), FfnCfg<2>::SMEM_BYTES, st, 2, mXh, mXl, mW1h, mW1l,
                        mW2h, mW2l, mOh, mOl, p);

@@ -79,6 +79,14 @@ def test_fused_ffn_block(eng, M, ff):
         assert torch.isfinite(y).all(), name
         assert _rel(y, ref) < 5e-6, name
     assert _rel(ys[2], ys[1]) < 4e-6
+    # every size above leaves tile groups that do not fill a round of the persistent grid: the fused kernel cut
+    # them along the hidden dimension (ffn_split, partial accumulators through scratch + flags).  Without the
+    # split the same rows are summed in one piece; with it, repeated launches are bit-identical.
+    eng.set_option("ffn_split", "0")
+    y_whole = eng.debug_ffn(X, W1, b1, W2, b2, gamma, beta, mode=2).cpu().double()
+    eng.set_option("ffn_split", "1")
+    assert _rel(y_whole, ref) < 5e-6 and _rel(y_whole, ys[2]) < 4e-6
+    assert torch.equal(eng.debug_ffn(X, W1, b1, W2, b2, gamma, beta, mode=2).cpu().double(), ys[2])
 
 
 def test_whole_path_tc_equals_cuda_core_path(built_lib):
@@ -103,9 +111,12 @@ def test_whole_path_tc_equals_cuda_core_path(built_lib):
 
 
 def test_scheduling_options_do_not_change_results(built_lib):
-    """Engine scheduling options only reorder independent work: the number of concurrent sub-batch branches
-    and CUDA-graph replay vs eager launches must give bit-identical motions; the unfused FFN (same math, the
-    hidden activations round-trip HBM) and the other attention cores agree to fp32 re-association noise."""
+    """Engine scheduling options only reorder independent work: CUDA-graph replay vs eager launches must give
+    bit-identical motions, and so must the number of concurrent sub-batch branches once the fused FFN's
+    hidden-dimension split is off (with it, the rows of the tile groups that do not fill a round are summed
+    piecewise, and which rows those are depends on how the batch is cut); the split itself, the unfused FFN
+    (same math, the hidden activations round-trip HBM) and the other attention cores agree to fp32
+    re-association noise.  Repeated runs are bit-identical in every configuration."""
     from mld_b200 import synth
     from mld_b200.engine import Engine, make_config
     eng = Engine(make_config(), 0)
@@ -119,11 +130,22 @@ def test_scheduling_options_do_not_change_results(built_lib):
     lengths = [196] * B
     base = eng.sample(ctx, noise, lengths, want=("latents",))["latents"].clone()
     assert torch.isfinite(base).all()
-    for name, value, restore in (("branches", "1", "2"), ("branches", "3", "2"), ("graph", "0", "1")):
-        eng.set_option(name, value)
+    eng.set_option("graph", "0")
+    assert torch.equal(eng.sample(ctx, noise, lengths, want=("latents",))["latents"], base), "graph replay vs eager"
+    eng.set_option("graph", "1")
+    eng.set_option("ffn_split", "0")
+    whole = eng.sample(ctx, noise, lengths, want=("latents",))["latents"].clone()
+    assert _rel(whole, base) < 1e-5, "ffn_split"
+    for value in ("1", "3"):
+        eng.set_option("branches", value)
         out = eng.sample(ctx, noise, lengths, want=("latents",))["latents"]
-        assert torch.equal(out, base), f"option {name}={value} changed the result"
-        eng.set_option(name, restore)
+        assert torch.equal(out, whole), f"branches={value} changed the result"
+    eng.set_option("ffn_split", "1")
+    for value in ("1", "3"):
+        eng.set_option("branches", value)
+        out = eng.sample(ctx, noise, lengths, want=("latents",))["latents"]
+        assert _rel(out, base) < 1e-5, f"branches={value} with the split"
+    eng.set_option("branches", "2")
     eng.set_option("ffn_fused", "0")
     out = eng.sample(ctx, noise, lengths, want=("latents",))["latents"]
     assert _rel(out, base) < 1e-5

@@ -160,8 +160,10 @@ def test_ragged_batch_vs_oracle(engines):
 def test_full_size_batch_invariance_and_oracle_subset(engines):
     """BASELINE configs[2] at full size (B=256, 77-token context, 50 DDIM steps).  Size-independent
     properties: (i) every motion is independent, so motion i of the 256-batch equals the same
-    motion sampled in a batch of 4 (bit-exact: no cross-row arithmetic anywhere); (ii) the oracle on
-    that 4-motion subset agrees within the 1e-3 joint gate; (iii) padded frames are zero."""
+    motion sampled in a batch of 4 - bit-exact with whole-tile FFN scheduling (no cross-row arithmetic
+    anywhere), to fp32 re-association noise with the default hidden-dimension split of leftover tiles
+    (which rows are summed piecewise depends on the batch size); (ii) the oracle on that 4-motion subset
+    agrees within the 1e-3 joint gate; (iii) padded frames are zero."""
     eng = engines["text"]
     B, S = 256, 77
     lengths = [196] * B
@@ -173,9 +175,17 @@ def test_full_size_batch_invariance_and_oracle_subset(engines):
     small = eng.sample(sub_ctx, noise[idx], sub_len, want=("latents", "feats", "joints"))
     small = {k: v.clone() for k, v in small.items()}
     big = eng.sample(ctx, noise, lengths, want=("latents", "feats", "joints"))
-    assert torch.equal(big["latents"][:, idx], small["latents"])
-    assert torch.equal(big["joints"][idx], small["joints"])
+    assert float((big["latents"][:, idx] - small["latents"]).abs().max() / small["latents"].abs().max()) < 1e-4
+    assert _joint_err(big["joints"][idx], [small["joints"][i, :n].cpu() for i, n in enumerate(sub_len)], sub_len) < 2e-4
     assert float(big["feats"][1, 120:].abs().max()) == 0.0
+    eng.set_option("ffn_split", "0")
+    try:
+        small0 = {k: v.clone() for k, v in eng.sample(sub_ctx, noise[idx], sub_len, want=("latents", "joints")).items()}
+        big0 = eng.sample(ctx, noise, lengths, want=("latents", "joints"))
+        assert torch.equal(big0["latents"][:, idx], small0["latents"])
+        assert torch.equal(big0["joints"][idx], small0["joints"])
+    finally:
+        eng.set_option("ffn_split", "1")
     jo, _, _ = O.mld_forward(engines["dsd"], O.DenoiserCfg(), engines["vsd"], O.VaeCfg(), O.DDIMScheduler(), 50,
                              sub_ctx, noise[idx], sub_len, engines["mean"], engines["std"])
     assert _joint_err(small["joints"], jo, sub_len) < 1e-3

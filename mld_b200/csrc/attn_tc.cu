@@ -36,6 +36,8 @@
 #include <stdlib.h>
 
 #include "ops.cuh"
+#include <stdlib.h>
+#include <string.h>
 #include "tc_common.cuh"
 
 namespace {
@@ -60,11 +62,13 @@ struct AtcParams {
   __half* out_hi; __half* out_lo; int ld_out;
   float scale_log2e;       // log2(e) / sqrt(head_dim)
   long long* tl;           // debug timeline (nullptr normally)
+  int reverse;             // walk the items from the last one down (see tc_attention)
 };
 
 struct Item { int s, h, qt; };
 __device__ __forceinline__ Item decode_item(int item, const AtcParams& p) {
   Item it;
+  if (p.reverse) item = p.nseq * p.heads * p.n_qt - 1 - item;
   it.qt = item % p.n_qt;
   const int sh = item / p.n_qt;
   it.h = sh % p.heads;
@@ -98,9 +102,9 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
   uint64_t* s_empty = s_full + 2;           // [2]
   uint64_t* p_full = s_full + 4;            // [2]
   uint64_t* p_empty = s_full + 6;           // [2]
-  uint64_t* o_full = s_full + 8;            // [2]
-  uint64_t* o_empty = s_full + 10;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 12);
+  uint64_t* o_full = s_full + 8;            // [4]
+  uint64_t* o_empty = s_full + 12;          // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 16);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   int tl_n = 0;                                       // debug-timeline event counter of this warp
@@ -108,6 +112,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
   const int items = p.nseq * p.heads * p.n_qt;
   const int nlocal = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int nkb = p.nkb, SB = p.SB, QB = p.QB, RS = p.RS;
+  constexpr int NOB = 2;                              // O accumulators in TMEM (one per softmax group)
   const int scols = nkb * KBLK;                       // TMEM columns of one score buffer
 
   if (threadIdx.x == 0) {
@@ -115,8 +120,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       mbar_init(smem_u32(&q_full[i]), 1);  mbar_init(smem_u32(&q_empty[i]), 1);
       mbar_init(smem_u32(&s_full[i]), 1);  mbar_init(smem_u32(&s_empty[i]), 8);
       mbar_init(smem_u32(&p_full[i]), 8);  mbar_init(smem_u32(&p_empty[i]), 1);
-      mbar_init(smem_u32(&o_full[i]), 1);  mbar_init(smem_u32(&o_empty[i]), 8);
     }
+    for (int i = 0; i < 4; ++i) { mbar_init(smem_u32(&o_full[i]), 1);  mbar_init(smem_u32(&o_empty[i]), 8); }
     for (int i = 0; i < MAX_RS; ++i) { mbar_init(smem_u32(&r_full[i]), 1); mbar_init(smem_u32(&r_empty[i]), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmQh); tma_prefetch_desc(&tmQl); tma_prefetch_desc(&tmKh); tma_prefetch_desc(&tmKl);
@@ -251,10 +256,10 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
     const uint32_t idesc_o = make_idesc(64, 128, true);
     const uint32_t sP_u = smem_u32(sP);
     for (int j = 0; j < nlocal; ++j) {
-      const int ob = j & 1;
+      const int ob = j % NOB;
       // ring position of V(j, 0): after K(j + 1) with two score buffers - except for the last item, which has none
       const int rc0 = (SB == 2 && j + 1 < nlocal) ? (2 * j + 2) * nkb : (2 * j + 1) * nkb;
-      mbar_wait(smem_u32(&o_empty[ob]), (((uint32_t)j >> 1) & 1u) ^ 1u);
+      mbar_wait(smem_u32(&o_empty[ob]), (((uint32_t)(j / NOB)) & 1u) ^ 1u);
       tc_fence_after();
       for (int kb = 0; kb < nkb; ++kb) {
         const int pseq = j * nkb + kb, pb = pseq & 1;
@@ -300,9 +305,46 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
     float* const red_max = s_red + g * 512;             // [half][row]
     float* const red_sum = red_max + 256;
     auto group_sync = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory"); };
+    // this warp's half of the O row / sum -> split16 -> global
+    auto epilogue = [&](int jj, float sum) {
+      const Item it = decode_item((int)blockIdx.x + jj * (int)gridDim.x, p);
+      const int ob = jj % NOB;
+      const int rows_valid = min(128, p.Lq - it.qt * 128);
+      const bool active = q * 32 < rows_valid;
+      mbar_wait(smem_u32(&o_full[ob]), ((uint32_t)(jj / NOB)) & 1u);
+      tc_fence_after();
+      tl_event(p.tl, tl_n, 34, jj);                                    // softmax: O(jj) ready
+      if (active) {
+        const float inv = 1.0f / sum;
+        constexpr int OC = HD / 2;                           // O columns per warp
+        const uint32_t o_addr = tmem_base + lane_addr + (uint32_t)(SB * scols + ob * HD + hf * OC);
+        const int64_t o = ((int64_t)it.s * p.Lq + it.qt * 128 + row) * p.ld_out + it.h * HD + hf * OC;
+        uint4* const dh = reinterpret_cast<uint4*>(p.out_hi + o);
+        uint4* const dl = reinterpret_cast<uint4*>(p.out_lo + o);
+#pragma unroll
+        for (int c = 0; c < OC / 16; ++c) {
+          uint32_t r[16];
+          tmem_ld16(o_addr + (uint32_t)(c * 16), r);
+          uint32_t oh[8], ol[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            split2(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv, oh[i], ol[i]);
+          if (row < rows_valid) {
+            dh[2 * c] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+            dh[2 * c + 1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
+            dl[2 * c] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+            dl[2 * c + 1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      tl_event(p.tl, tl_n, 35, jj);                                    // softmax: epilogue done
+      if (lane == 0) mbar_arrive(smem_u32(&o_empty[ob]));
+    };
     for (int j = g; j < nlocal; j += 2) {
       const Item it = decode_item((int)blockIdx.x + j * (int)gridDim.x, p);
-      const int sb = j % SB, ob = j & 1;
+      const int sb = j % SB;
       const int rows_valid = min(128, p.Lq - it.qt * 128);
       const bool active = q * 32 < rows_valid;          // warp-uniform: this warp owns real query rows
       int nk = p.Lk;
@@ -372,37 +414,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       tl_event(p.tl, tl_n, 33, j);                                     // softmax: pass 2 done (P written)
       group_sync();
       sum += red_sum[(hf ^ 1) * 128 + row];
-      // ---- this warp's half of the O row / sum -> split16 -> global
-      mbar_wait(smem_u32(&o_full[ob]), ((uint32_t)j >> 1) & 1u);
-      tc_fence_after();
-      tl_event(p.tl, tl_n, 34, j);                                     // softmax: O(j) ready
-      if (active) {
-        const float inv = 1.0f / sum;
-        constexpr int OC = HD / 2;                           // O columns per warp
-        const uint32_t o_addr = tmem_base + lane_addr + (uint32_t)(SB * scols + ob * HD + hf * OC);
-        const int64_t o = ((int64_t)it.s * p.Lq + it.qt * 128 + row) * p.ld_out + it.h * HD + hf * OC;
-        uint4* const dh = reinterpret_cast<uint4*>(p.out_hi + o);
-        uint4* const dl = reinterpret_cast<uint4*>(p.out_lo + o);
-#pragma unroll
-        for (int c = 0; c < OC / 16; ++c) {
-          uint32_t r[16];
-          tmem_ld16(o_addr + (uint32_t)(c * 16), r);
-          uint32_t oh[8], ol[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            split2(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv, oh[i], ol[i]);
-          if (row < rows_valid) {
-            dh[2 * c] = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-            dh[2 * c + 1] = make_uint4(oh[4], oh[5], oh[6], oh[7]);
-            dl[2 * c] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
-            dl[2 * c + 1] = make_uint4(ol[4], ol[5], ol[6], ol[7]);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      tl_event(p.tl, tl_n, 35, j);                                     // softmax: epilogue done
-      if (lane == 0) mbar_arrive(smem_u32(&o_empty[ob]));
+      epilogue(j, sum);
     }
   }
   tc_fence_before();
@@ -495,6 +507,11 @@ bool tc_attention(const AttnArgs& a, cudaStream_t st) {
   p.out_hi = a.out.hi; p.out_lo = a.out.lo(); p.ld_out = a.out.cols;
   p.scale_log2e = 1.4426950408889634f / sqrtf((float)a.hd);
   p.tl = tc::mldb_timeline_buffer();
+  // Snake order across the per-layer kernels: the GEMMs walk the token tiles upwards, attention and the fused FFN
+  // downwards, so every kernel starts on the rows its producer wrote LAST - those are still in the 126 MB L2,
+  // the rows written first (41-124 MB earlier) are not.  MLDB_SNAKE=0 turns it off (A/B).
+  static const int snake = [] { const char* e = getenv("MLDB_SNAKE"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
+  p.reverse = snake;
   const int items = a.nseq * a.heads * p.n_qt;
   const int grid = items < g_sm_count ? items : g_sm_count;
   if (a.hd == 64)

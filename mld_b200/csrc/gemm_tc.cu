@@ -30,6 +30,7 @@
 #include <stdlib.h>
 
 #include <string>
+#include <string.h>
 
 #include "tc_common.cuh"
 
@@ -689,7 +690,7 @@ struct FfnParams {
   int full, left, parts;
   float* scratch;              // [slot][64 column groups][128 rows][4] fp32 partial accumulators of the pieces
   int* flags;                  // [slot] 1 = partial written (reset by the reader)
-  int stagger;                 // experiment: start-up delay of cluster c = (c & 3) * stagger cycles
+  int reverse;                 // walk the tile groups from the last one down (snake order, see tc_attention)
   long long* tl;
   float inv_s1, inv_s2;
   const float* b1; const float* b2; const float* gamma; const float* beta;
@@ -759,13 +760,15 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   // (adds the contributors' accumulators in piece order, then bias + residual + LayerNorm as for a whole tile).
   // Contributors have lower cluster ids than their finisher, so they are scheduled no later than it.
   struct Item { int mg, c0, c1, mode, piece0; };             // mode: 0 whole tile, 1 contributor, 2 finisher
+  const int ngroups = (p.m_tiles + CG - 1) / CG;
+  auto rev = [&](int grp) { return p.reverse ? ngroups - 1 - grp : grp; };
   const int nlocal = p.full + (cid < p.left * p.parts ? 1 : 0);
   auto item = [&](int j) -> Item {
-    if (j < p.full) return Item{cid + j * ncl, 0, NC, 0, 0};
+    if (j < p.full) return Item{rev(cid + j * ncl), 0, NC, 0, 0};
     const int t = cid / p.parts, part = cid - t * p.parts;
     const int c0 = (part * NC + p.parts - 1) / p.parts, c1 = ((part + 1) * NC + p.parts - 1) / p.parts;
     const int slot0 = (t * (p.parts - 1)) * CG + rank;       // slot of piece k of this CTA's rows: slot0 + k * CG
-    return Item{p.full * ncl + t, c0, c1, p.parts == 1 ? 0 : (part == p.parts - 1 ? 2 : 1), p.parts == 1 ? 0 : slot0 + (part == p.parts - 1 ? 0 : part * CG)};
+    return Item{rev(p.full * ncl + t), c0, c1, p.parts == 1 ? 0 : (part == p.parts - 1 ? 2 : 1), p.parts == 1 ? 0 : slot0 + (part == p.parts - 1 ? 0 : part * CG)};
   };
 
   if (threadIdx.x == 0) {
@@ -801,10 +804,6 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
   tl_event(p.tl, tl_n, 41);                       // the previous kernel has completed
-  if (p.stagger > 0 && warp == 0) {               // only the producer is held back: everything else follows it
-    const long long t_end = clock64() + (long long)(cid & 3) * p.stagger;
-    while (clock64() < t_end) __nanosleep(200);
-  }
 
   // arrive on a barrier that lives in the leader CTA (2-SM) or in this CTA (1-SM)
   auto arrive_leader = [&](uint64_t* bar) {
@@ -1271,7 +1270,6 @@ bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, 
   p.res_hi = l2.res.hi; p.res_lo = l2.res.hi ? l2.res.lo() : nullptr; p.ld_res = l2.res.cols;
   p.out_hi = l2.out.hi; p.out_lo = l2.out.lo(); p.ld_out = l2.out.cols;
   p.tma_out = 1;
-  { const char* e = getenv("MLDB_FFN_STAGGER"); p.stagger = e ? atoi(e) : 0; }
   const int groups = (m_tiles + cg - 1) / cg;
   const int ncl_max = c->sm_count / cg;
   // whole rounds of tile groups, then the leftover groups cut along the hidden dimension so that the last
@@ -1284,6 +1282,8 @@ bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, 
     if (parts >= 2 && (size_t)p.left * (parts - 1) * cg * (BM * 256 * 4) <= TC_FFN_SCRATCH_BYTES) p.parts = parts;
   }
   const int ncl = p.full > 0 ? ncl_max : p.left * p.parts;
+  static const int snake = [] { const char* e = getenv("MLDB_SNAKE"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
+  p.reverse = snake;
   if (cg == 2)
     launch_pdl_cluster(k_ffn_tc<2>, dim3(ncl * 2), dim3(LN_THREADS), FfnCfg<2>::SMEM_BYTES, st, 2, mXh, mXl, mW1h, mW1l,
                        mW2h, mW2l, mOh, mOl, p);

@@ -290,7 +290,8 @@ int mldb_reset_kernel_stats(mldb_handle* h);
  *                                        summed in a different order, so they depend on the batch size in the last bits
  *   "branches"   1..4                   concurrent sub-batch branches inside a denoiser step (2)      MLDB_BRANCHES
  *   "graph"      0 | 1                  CUDA-graph replay of the step loop (1)                        MLDB_GRAPH
- * Environment only: MLDB_PDL (programmatic dependent launch, 1). */
+ * Environment only: MLDB_PDL (programmatic dependent launch, 1); MLDB_SNAKE (1: attention and the fused FFN walk
+ * the token tiles downwards, the GEMMs upwards, so every kernel starts on the rows its producer wrote last). */
 int mldb_set_option(mldb_handle* h, const char* name, const char* value);
 
 #ifdef __cplusplus

@@ -247,6 +247,101 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) k_attn_simt(const AttnArgs a) 
   }
 }
 
+// 128-bit version for d = NIT * 256 (the shapes the path uses): a lane owns 8 consecutive columns per 256-column
+// group - 16-byte loads of the split16 residual planes, 2 x 16-byte loads of the fp32 inputs, 16-byte stores
+template <int NIT>
+__global__ void __launch_bounds__(256) k_ln_vec(const LnArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= a.M) return;
+  const int r = warp;
+  const int64_t irow = (a.in_group == 0) ? (int64_t)r
+                                         : (int64_t)(r / a.sel_group) * a.in_group + r % a.sel_group;
+  float v[NIT][8];
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    const int n = i * 256 + lane * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[i][k] = 0.0f;
+    if (a.c) {
+      const float4 c0 = *reinterpret_cast<const float4*>(a.c + irow * a.ldc + n), c1 = *reinterpret_cast<const float4*>(a.c + irow * a.ldc + n + 4);
+      v[i][0] = c0.x; v[i][1] = c0.y; v[i][2] = c0.z; v[i][3] = c0.w; v[i][4] = c1.x; v[i][5] = c1.y; v[i][6] = c1.z; v[i][7] = c1.w;
+    }
+    if (a.res.hi) {
+      const int64_t o = irow * a.res.cols + n;
+      const uint4 h = *reinterpret_cast<const uint4*>(a.res.hi + o), l = *reinterpret_cast<const uint4*>(a.res.lo() + o);
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
+        const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
+        v[i][2 * k] += hf.x + lf.x;
+        v[i][2 * k + 1] += hf.y + lf.y;
+      }
+    }
+    if (a.rowvec) {
+      const float* rv = a.rowvec + (int64_t)(irow / a.rv_group) * a.d + n;
+      const float4 r0 = *reinterpret_cast<const float4*>(rv), r1 = *reinterpret_cast<const float4*>(rv + 4);
+      v[i][0] += r0.x; v[i][1] += r0.y; v[i][2] += r0.z; v[i][3] += r0.w; v[i][4] += r1.x; v[i][5] += r1.y; v[i][6] += r1.z; v[i][7] += r1.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[i][k];
+  }
+  const float inv_d = 1.0f / (float)a.d;
+  auto normalise = [&](const float* gamma, const float* beta) {
+    float sum = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += v[i][k];
+    const float mean = warp_sum(sum) * inv_d;
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float dlt = v[i][k] - mean; q += dlt * dlt; }
+    const float rstd = rsqrtf(warp_sum(q) * inv_d + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int n = i * 256 + lane * 8;
+      const float4 g0 = *reinterpret_cast<const float4*>(gamma + n), g1 = *reinterpret_cast<const float4*>(gamma + n + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(beta + n), b1 = *reinterpret_cast<const float4*>(beta + n + 4);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[i][k] = (v[i][k] - mean) * rstd * g[k] + b[k];
+    }
+  };
+  (void)s;
+  normalise(a.gamma, a.beta);
+  if (a.gamma2) normalise(a.gamma2, a.beta2);   // stack-final LayerNorm on top (cross_attention.py:62-63)
+#pragma unroll
+  for (int i = 0; i < NIT; ++i) {
+    const int n = i * 256 + lane * 8;
+    if (a.out.hi) {
+      uint32_t ph[4], pl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __half h0, l0, h1, l1;
+        split_f32(v[i][2 * k], h0, l0);
+        split_f32(v[i][2 * k + 1], h1, l1);
+        const __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+        ph[k] = *reinterpret_cast<const uint32_t*>(&hh);
+        pl[k] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      const int64_t o = (int64_t)r * a.out.cols + n;
+      *reinterpret_cast<uint4*>(a.out.hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+      *reinterpret_cast<uint4*>(a.out.lo() + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+    }
+    if (a.out_f32) {
+      float* dst = a.out_f32 + (int64_t)r * a.ld_out + n;
+      *reinterpret_cast<float4*>(dst) = make_float4(v[i][0], v[i][1], v[i][2], v[i][3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(v[i][4], v[i][5], v[i][6], v[i][7]);
+    }
+  }
+}
+
 }  // namespace
 
 void simt_gemm(const GemmArgs& a, cudaStream_t st) {
@@ -257,7 +352,16 @@ void simt_gemm(const GemmArgs& a, cudaStream_t st) {
 void simt_ln(const LnArgs& a, cudaStream_t st) {
   const int rows_per_block = 8;
   dim3 grid((a.M + rows_per_block - 1) / rows_per_block);
-  if (a.d <= 256) launch_pdl(k_ln<8>, grid, dim3(256), 0, st, a);
+  // the 128-bit version needs 16-byte aligned rows everywhere it touches
+  const bool vec_ok = (a.d == 256 || a.d == 512) && (!a.c || (a.ldc % 4 == 0 && ((uintptr_t)a.c & 15) == 0)) &&
+                      (!a.res.hi || (a.res.cols % 8 == 0 && ((uintptr_t)a.res.hi & 15) == 0 && (a.res.plane_stride % 8) == 0)) &&
+                      (!a.out.hi || (a.out.cols % 8 == 0 && ((uintptr_t)a.out.hi & 15) == 0 && (a.out.plane_stride % 8) == 0)) &&
+                      (!a.out_f32 || (a.ld_out % 4 == 0 && ((uintptr_t)a.out_f32 & 15) == 0)) &&
+                      (!a.rowvec || ((uintptr_t)a.rowvec & 15) == 0) && ((uintptr_t)a.gamma & 15) == 0 &&
+                      ((uintptr_t)a.beta & 15) == 0 && (!a.gamma2 || (((uintptr_t)a.gamma2 & 15) == 0 && ((uintptr_t)a.beta2 & 15) == 0));
+  if (vec_ok && a.d == 256) launch_pdl(k_ln_vec<1>, grid, dim3(256), 0, st, a);
+  else if (vec_ok) launch_pdl(k_ln_vec<2>, grid, dim3(256), 0, st, a);
+  else if (a.d <= 256) launch_pdl(k_ln<8>, grid, dim3(256), 0, st, a);
   else if (a.d <= 512) launch_pdl(k_ln<16>, grid, dim3(256), 0, st, a);
   else launch_pdl(k_ln<32>, grid, dim3(256), 0, st, a);
 }

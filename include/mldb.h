@@ -283,7 +283,7 @@ int mldb_reset_kernel_stats(mldb_handle* h);
  * identical (gemm, attn: to fp32 re-association noise) for every setting (tests/test_gpu_kernels.py).
  *   "gemm"       "tc" | "simt"          tcgen05 kernels (default) or the CUDA-core reference kernels  MLDB_GEMM
  *   "attn"       "tc" | "mma" | "simt"  attention core: tcgen05 (default), mma.sync, CUDA cores       MLDB_ATTN
- *   "ffn_fused"  0 | 1                  fused FFN kernel k_ffn_tc (default 1)
+ *   "ffn_fused"  0 | 1                  fused FFN kernel k_ffn_tc (default 1)                         MLDB_FFN_FUSED
  *   "ffn_split"  0 | 1                  fused FFN: cut the tile groups that do not fill a whole round of the
  *                                        persistent grid along the hidden dimension (default 1; env MLDB_FFN_SPLIT).
  *                                        Results stay bit-identical run to run, but the rows of a split tile are

@@ -57,6 +57,7 @@ struct AtcParams {
   int nkb, rem;            // key blocks; keys (multiple of 16) in the last block
   int QR;                  // rows of the Q box (multiple of 8, <= 128)
   int QB, SB, RS;          // Q buffers, score buffers, ring slots
+  int NOB;                 // O accumulators in TMEM: 2, or 4 when 4 * HD columns fit next to the score buffers
   int q_col0, k_col0, v_col0;
   const int32_t* lengths; int kv_prefix, len_mod, seq0;
   __half* out_hi; __half* out_lo; int ld_out;
@@ -111,8 +112,7 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
   tl_event(p.tl, tl_n, 40);                       // kernel entry
   const int items = p.nseq * p.heads * p.n_qt;
   const int nlocal = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int nkb = p.nkb, SB = p.SB, QB = p.QB, RS = p.RS;
-  constexpr int NOB = 2;                              // O accumulators in TMEM (one per softmax group)
+  const int nkb = p.nkb, SB = p.SB, QB = p.QB, RS = p.RS, NOB = p.NOB;
   const int scols = nkb * KBLK;                       // TMEM columns of one score buffer
 
   if (threadIdx.x == 0) {
@@ -342,6 +342,8 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       tl_event(p.tl, tl_n, 35, jj);                                    // softmax: epilogue done
       if (lane == 0) mbar_arrive(smem_u32(&o_empty[ob]));
     };
+    int pend = -1;                                       // item whose epilogue is still owed (NOB == 4)
+    float pend_sum = 0.0f;
     for (int j = g; j < nlocal; j += 2) {
       const Item it = decode_item((int)blockIdx.x + j * (int)gridDim.x, p);
       const int sb = j % SB;
@@ -371,6 +373,11 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       mx = fmaxf(mx, red_max[(hf ^ 1) * 128 + row]);
       const float mc = (mx == -INFINITY) ? 0.0f : mx * sc;
       // ---- pass 2: P = exp2(sc * s - sc * max) (unnormalised), fp32 partial row sum, P -> shared memory
+      // The two groups take turns on the p_empty barriers, so each sees only every other phase: its parity wait
+      // for "PV(pseq - 2) done" is only correct if the phase before that one (this group's own previous item)
+      // has completed - otherwise the wait aliases and passes at once.  Without the deferred epilogue that is
+      // implied (the group has read O(j - 2)); with it, it is checked here - long satisfied in steady state.
+      if (NOB == 4 && pend >= 0) mbar_wait(smem_u32(&o_full[pend % NOB]), ((uint32_t)(pend / NOB)) & 1u);
       float sum = 0.0f;
 #pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb) {
@@ -414,8 +421,17 @@ k_attn_tc(const __grid_constant__ CUtensorMap tmQh, const __grid_constant__ CUte
       tl_event(p.tl, tl_n, 33, j);                                     // softmax: pass 2 done (P written)
       group_sync();
       sum += red_sum[(hf ^ 1) * 128 + row];
-      epilogue(j, sum);
+      // ---- epilogue.  With four O accumulators the epilogue of this group's PREVIOUS item runs here instead
+      // (its PV chain retired long ago), so the group never waits for the tensor pipe between its softmax
+      // passes and its stores: the wait for O(j) used to be ~2.3k of the ~10k cycles a group spends per item.
+      if (NOB == 4) {
+        if (pend >= 0) epilogue(pend, pend_sum);
+        pend = j; pend_sum = sum;
+      } else {
+        epilogue(j, sum);
+      }
     }
+    if (pend >= 0) epilogue(pend, pend_sum);
   }
   tc_fence_before();
   __syncthreads();
@@ -452,6 +468,8 @@ bool plan_shape(const AttnArgs& a, AtcParams* p) {
   const int scols = p->nkb * KBLK;
   if (scols + 2 * a.hd > 512) return false;
   p->SB = (2 * scols + 2 * a.hd <= 512) ? 2 : 1;
+  static const int max_nob = [] { const char* e = getenv("MLDB_ATTN_NOB"); return e ? atoi(e) : 4; }();   // A/B knob
+  p->NOB = (max_nob >= 4 && p->SB * scols + 4 * a.hd <= 512) ? 4 : 2;
   const int q_bytes = 2 * ns * p->QR * 128, slot = 2 * ns * KBLK * 128;
   const int fixed = 1024 + 2 * P_BYTES + RED_BYTES + 512;   // alignment slack + P ring + exchange buffers + barriers
   for (int qb = 2; qb >= 1; --qb) {

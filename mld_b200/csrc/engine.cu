@@ -659,6 +659,8 @@ extern "C" int mldb_create(const mldb_config* cfg, int device, mldb_handle** out
   if (e != cudaSuccess) { mldb_destroy(h); FAIL(MLDB_ERR_CUDA, "ffn scratch: %s", cudaGetErrorString(e)); }
   env = getenv("MLDB_FFN_SPLIT");
   if (env) tc_set_ffn_split(h->tc, atoi(env) != 0);
+  env = getenv("MLDB_FFN_FUSED");
+  if (env) tc_set_ffn_fused(h->tc, atoi(env) != 0);
   *out = h;
   return MLDB_OK;
 }

@@ -64,16 +64,20 @@ struct AtcParams {
   float scale_log2e;       // log2(e) / sqrt(head_dim)
   long long* tl;           // debug timeline (nullptr normally)
   int reverse;             // walk the items from the last one down (see tc_attention)
+  int items, heads_log2;   // nseq * heads * n_qt; log2(heads) or -1
 };
 
 struct Item { int s, h, qt; };
 __device__ __forceinline__ Item decode_item(int item, const AtcParams& p) {
   Item it;
-  if (p.reverse) item = p.nseq * p.heads * p.n_qt - 1 - item;
-  it.qt = item % p.n_qt;
-  const int sh = item / p.n_qt;
-  it.h = sh % p.heads;
-  it.s = sh / p.heads;
+  if (p.reverse) item = p.items - 1 - item;
+  // runtime integer divisions showed up with ~10 % of this kernel's stall samples: one query tile and a
+  // power-of-two head count (every shipped config) need none
+  int sh = item;
+  it.qt = 0;
+  if (p.n_qt > 1) { sh = item / p.n_qt; it.qt = item - sh * p.n_qt; }
+  if (p.heads_log2 >= 0) { it.s = sh >> p.heads_log2; it.h = sh & (p.heads - 1); }
+  else { it.s = sh / p.heads; it.h = sh - it.s * p.heads; }
   return it;
 }
 
@@ -530,6 +534,9 @@ bool tc_attention(const AttnArgs& a, cudaStream_t st) {
   // the rows written first (41-124 MB earlier) are not.  MLDB_SNAKE=0 turns it off (A/B).
   static const int snake = [] { const char* e = getenv("MLDB_SNAKE"); return (e && !strcmp(e, "0")) ? 0 : 1; }();
   p.reverse = snake;
+  p.items = p.nseq * p.heads * p.n_qt;
+  p.heads_log2 = -1;
+  for (int k = 0; k < 8; ++k) if ((1 << k) == p.heads) p.heads_log2 = k;
   const int items = a.nseq * a.heads * p.n_qt;
   const int grid = items < g_sm_count ? items : g_sm_count;
   if (a.hd == 64)

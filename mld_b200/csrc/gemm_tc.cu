@@ -220,8 +220,28 @@ __device__ __forceinline__ void stage_and_store(uint8_t* sb2, const uint32_t (&p
 // E[x-K]^2 does not cancel); the four quarters of a row are merged with the pairwise (Chan) update through
 // shared memory in a FIXED order, so every warp derives the same mean / rstd; the pre-norm values are parked
 // in TMEM between the passes.  The residual is loaded (coalesced pattern) before the accumulator is awaited.
-struct LnResidual { uint4 gh[4], gl[4]; };           // one 32-column chunk of both planes in flight (32 registers)
-// r[32] (fp32 bits) += one fp16 plane of the same 32 columns (row-owner layout: 4 x 16 B)
+// The residual of one 32-column chunk (both planes, 2 x 2 KB) is pulled into the warp's staging tile by TMA - the
+// same SWIZZLE_64B 32 x 32 boxes the output leaves through - and read back row by row.  (As plain 16-byte loads
+// through a register transpose this was the LayerNorm epilogue's hot spot: 24 % of the out-projection kernel's stall
+// samples sat on the load instruction, most of them LG-throttle.)  One mbarrier per warp; `phase` is its parity.
+struct LnResidual { uint32_t bar; uint32_t phase; uint4 gh[4], gl[4]; };   // gh / gl: the register path (fused FFN)
+// r[32] (fp32 bits) += one fp16 plane of the same 32 columns, read from this thread's row of a staging tile
+__device__ __forceinline__ void add_plane_stg(uint32_t (&r)[32], const uint8_t* stg, int lane) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 pv = *reinterpret_cast<const uint4*>(stg + stg_off(lane, i));
+    const uint32_t w[4] = {pv.x, pv.y, pv.z, pv.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      const int e = i * 8 + j * 2;
+      r[e] = __float_as_uint(__uint_as_float(r[e]) + f.x);
+      r[e + 1] = __float_as_uint(__uint_as_float(r[e + 1]) + f.y);
+    }
+  }
+}
+// The fused FFN keeps the register path: its staging is the Hs buffer, which the F2 chain reads until the accumulator
+// is complete, so a TMA load could only be requested after that wait; plain loads can be requested before it.
 __device__ __forceinline__ void add_plane(uint32_t (&r)[32], const uint4 (&pv)[4]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -235,17 +255,31 @@ __device__ __forceinline__ void add_plane(uint32_t (&r)[32], const uint4 (&pv)[4
     }
   }
 }
-__device__ __forceinline__ void ln16_issue_residual(LnResidual& t, const __half* res_hi, const __half* res_lo, int ld_res,
-                                                    int wrow0, int col, int rows_valid, int lane) {
+__device__ __forceinline__ void ln16_issue_residual_ldg(LnResidual& t, const __half* res_hi, const __half* res_lo, int ld_res,
+                                                        int wrow0, int col, int rows_valid, int lane) {
   if (res_hi == nullptr) return;
   load_plane_issue(res_hi + (int64_t)wrow0 * ld_res + col, ld_res, rows_valid, lane, t.gh);
   load_plane_issue(res_lo + (int64_t)wrow0 * ld_res + col, ld_res, rows_valid, lane, t.gl);
 }
+// the staging tile must be idle: its TMA stores read (cp.async.bulk.wait_group.read 0 by lane 0) and this warp's
+// own reads of it done (program order + __syncwarp)
+__device__ __forceinline__ void ln16_issue_residual(const LnResidual& t, bool has_res, uint8_t* stg, const CUtensorMap* mRh,
+                                                    const CUtensorMap* mRl, int wrow0, int col, int lane) {
+  if (!has_res) return;
+  __syncwarp();
+  if (lane == 0) {
+    fence_proxy_async_smem();                        // generic-proxy reads / writes of the tile -> async-proxy writes
+    mbar_expect_tx(t.bar, 4096);
+    tma_load_2d(smem_u32(stg), mRh, t.bar, col, wrow0);          // rows >= M are zero-filled (and counted)
+    tma_load_2d(smem_u32(stg + 2048), mRl, t.bar, col, wrow0);
+  }
+}
 // trow: TMEM address of this thread's row at the tile's column cb = cq * 64.  stg: this warp's staging
 // (4 KB with WIDE_STG: both planes transposed at once and the TMA-store pair; else 2 KB).  s_vec*: bias / gamma /
 // beta of the 256 columns.  s_part: [4 quarters][mean | M2][128 rows].
-template <bool WIDE_STG>
-__device__ __forceinline__ void ln16_finish(LnResidual& t, const __half* res_hi, const __half* res_lo, int ld_res, uint32_t trow, int cq, int row, int lane, uint8_t* stg,
+template <bool WIDE_STG, bool RES_TMA>
+__device__ __forceinline__ void ln16_finish(LnResidual& t, bool has_res, const CUtensorMap* mRh, const CUtensorMap* mRl,
+                                            const __half* res_hi, const __half* res_lo, int ld_res, uint32_t trow, int cq, int row, int lane, uint8_t* stg,
                                             const float* s_bias, const float* s_gamma, const float* s_beta, float* s_part,
                                             float sc, int wrow0, int rows_valid, bool tma_out, const CUtensorMap* mOh,
                                             const CUtensorMap* mOl, __half* out_hi, __half* out_lo, int ld_out,
@@ -288,15 +322,21 @@ __device__ __forceinline__ void ln16_finish(LnResidual& t, const __half* res_hi,
       r[4 * i + 2] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 2]), sc, b.z));
       r[4 * i + 3] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 3]), sc, b.w));
     }
-    if (res_hi != nullptr) {
-      // the first chunk's planes were requested before the accumulator was awaited; the second chunk's are
-      // requested as soon as the first one's registers are free and arrive under the first chunk's statistics
+    if (has_res && RES_TMA) {
+      // the first chunk was requested before the accumulator was awaited; the second one is requested as soon as
+      // the first has been read out of the tile and arrives under the first chunk's statistics
+      mbar_wait(t.bar, t.phase);
+      t.phase ^= 1u;
+      add_plane_stg(r, stg, lane);
+      add_plane_stg(r, stg + 2048, lane);
+      if (c == 0) ln16_issue_residual(t, true, stg, mRh, mRl, wrow0, cb + 32, lane);
+    } else if (has_res) {
       uint4 rv[4];
       plane_to_rows(stg, t.gh, lane, rv);
       add_plane(r, rv);
       plane_to_rows(stg + (WIDE_STG ? 2048 : 0), t.gl, lane, rv);
       add_plane(r, rv);
-      if (c == 0) ln16_issue_residual(t, res_hi, res_lo, ld_res, wrow0, cb + 32, rows_valid, lane);
+      if (c == 0) ln16_issue_residual_ldg(t, res_hi, res_lo, ld_res, wrow0, cb + 32, rows_valid, lane);
     }
     if (c == 0) {                                  // shift: the mean of the first chunk
       float acc = 0.0f;
@@ -368,6 +408,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           const __grid_constant__ CUtensorMap tmA2h, const __grid_constant__ CUtensorMap tmA2l,
           const __grid_constant__ CUtensorMap tmWh, const __grid_constant__ CUtensorMap tmWl,
           const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
+          const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl,   // residual (EPI_LN)
           const TcParams p) {
   constexpr bool LN = EPI == EPI_LN;
   static_assert(!LN || BN == 256, "the LayerNorm epilogue covers a full 256-wide row");
@@ -392,6 +433,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
   uint64_t* bar_tfull = bars + 2 * STAGES;      // [2]
   uint64_t* bar_tempty = bars + 2 * STAGES + 2; // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* bar_res = bars + 12;                // [LN_WARPS] residual tile landed (one per LayerNorm warp)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   int tl_n = 0;                                     // debug-timeline event counter of this warp
@@ -410,6 +452,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       mbar_init(smem_u32(&bar_tfull[s]), 1);
       mbar_init(smem_u32(&bar_tempty[s]), EMPTY_ARRIVALS);    // 2-SM: the leader's barrier collects both CTAs' warps
     }
+    if (LN)
+      for (int s = 0; s < LN_WARPS; ++s) mbar_init(smem_u32(&bar_res[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmA1h); tma_prefetch_desc(&tmA1l); tma_prefetch_desc(&tmWh); tma_prefetch_desc(&tmWl);
   }
@@ -572,11 +616,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       __half* const ohi = p.out_hi;
       __half* const olo = p.out_lo;
       const int64_t obase = orow * p.ld_out + p.out_col0;
+      float4 bb[8];                                  // DEEP: this chunk's bias values
       // one 32-column chunk: accumulator registers -> bias / activation -> split16 -> global
       auto chunk = [&](const uint32_t (&r)[32], int c) {
         const int nb = n0 + hf * (BN / 2) + c * 32;
         if constexpr (EPI == EPI_FAST) {
-          epi_chunk_fast<ACT>(r, v, DEEP ? p.bias + nb : s_bias + nb, inv_scale);
+          epi_chunk_fast<ACT>(r, v, DEEP ? reinterpret_cast<const float*>(bb) : s_bias + nb, inv_scale);
           uint32_t ph[16], pl[16];
           pack_split(v, ph, pl);
           if (CG == 2 && p.tma_out) {
@@ -622,6 +667,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       };
 #pragma unroll 1
       for (int c = 0; c < CH; ++c) {
+        if (EPI == EPI_FAST && DEEP) {               // the chunk's bias (global, L1-resident) rides under the TMEM load:
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + hf * (BN / 2) + c * 32);   // read on first use it
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bb[i] = __ldg(b4 + i);                                          // was 10 % of the stalls
+        }
         tmem_ld32(trow + c * 32, r);               // warp-collective: no divergence around it
         chunk(r, c);
       }
@@ -640,6 +690,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
     const int cq = (warp - 2) >> 2;                  // column quarter of the row
     const int row = q * 32 + lane;
     uint8_t* const stg = s_stage + (warp - 2) * Cfg::STG_WARP;
+    const bool has_res = p.res_hi != nullptr;        // warp-uniform
+    LnResidual t{smem_u32(&bar_res[warp - 2]), 0u};
     for (int it = 0; it < nlocal; ++it) {
       const int as = it & 1;
       int m0, n0;
@@ -647,13 +699,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cq * 64);
       const int wrow0 = m0 + q * 32;
       const int rows_valid = min(32, p.M - wrow0);
-      LnResidual t;
-      ln16_issue_residual(t, p.res_hi, p.res_lo, p.ld_res, wrow0, cq * 64, rows_valid, lane);
+      ln16_issue_residual(t, has_res, stg, &tmRh, &tmRl, wrow0, cq * 64, lane);
       tl_event(p.tl, tl_n, 6, it);                                     // LN epilogue: residual loads issued, waiting for tile `it`
       mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       tl_event(p.tl, tl_n, 4, it);
-      ln16_finish<CG == 2>(t, p.res_hi, p.res_lo, p.ld_res, trow, cq, row, lane, stg, s_bias, s_gamma, s_beta, s_part, p.inv_scale, wrow0,
+      ln16_finish<CG == 2, true>(t, has_res, &tmRh, &tmRl, p.res_hi, p.res_lo, p.ld_res, trow, cq, row, lane, stg, s_bias, s_gamma, s_beta, s_part, p.inv_scale, wrow0,
                            rows_valid, CG == 2 && p.tma_out, &tmOh, &tmOl, p.out_hi, p.out_lo, p.ld_out, p.tl, tl_n);
       tc_fence_before();
       __syncwarp();
@@ -949,6 +1000,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
     uint8_t* const stg = hs + (warp - 2) * 4096;     // LayerNorm staging lives in the (then idle) Hs buffer
     uint32_t r[32];
     float v[32];
+    const bool has_res = p.res_hi != nullptr;
     int g = 0;                                       // hidden chunks handled so far
     for (int j = 0; j < nlocal; ++j) {
       const Item it = item(j);
@@ -1011,7 +1063,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       const int wrow0 = m0 + q * 32;
       const int rows_valid = min(32, p.M - wrow0);
       LnResidual t;
-      ln16_issue_residual(t, p.res_hi, p.res_lo, p.ld_res, wrow0, cq * 64, rows_valid, lane);
+      ln16_issue_residual_ldg(t, p.res_hi, p.res_lo, p.ld_res, wrow0, cq * 64, rows_valid, lane);
       mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);      // all F2 MMAs retired: acc2 complete, Hs idle
       tc_fence_after();
       tl_event(p.tl, tl_n, 15, j);                                   // LN tail: acc2 ready
@@ -1030,7 +1082,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         }
         __syncwarp();
       }
-      ln16_finish<true>(t, p.res_hi, p.res_lo, p.ld_res, trow2, cq, row, lane, stg,
+      ln16_finish<true, false>(t, has_res, nullptr, nullptr, p.res_hi, p.res_lo, p.ld_res, trow2, cq, row, lane, stg,
                         s_b2, s_gamma, s_beta, s_part, p.inv_s2, wrow0, rows_valid, p.tma_out != 0, &tmOh, &tmOl,
                         p.out_hi, p.out_lo, p.ld_out, p.tl, tl_n,
                         nparts > 0 ? p.scratch + (size_t)it.piece0 * (BM * 256) : nullptr, nparts, (size_t)CG * (BM * 256));
@@ -1198,9 +1250,13 @@ bool tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   const bool fast = !ln && g.out.hi && !g.out_f32 && !g.addtab && !g.zero_lengths && g.in_group >= g.M &&
                     g.out_group == 0 && g.out_off == 0 && g.w.N % bn == 0 && g.w.bias != nullptr &&
                     (g.act == ACT_NONE || g.act == ACT_GELU);
+  CUtensorMap mRh = mA1h, mRl = mA1l;             // residual of the LayerNorm epilogue: same 32 x 32 SWIZZLE_64B boxes
   if (cl == 2 && ln) {
     if (!make_map_out(c, &mOh, ln->out.hi, g.M, 256, ln->out.cols) || !make_map_out(c, &mOl, ln->out.lo(), g.M, 256, ln->out.cols))
       return map_fail("gemm ln out", g.M, g.w.N, g.w.K);
+    if (ln->res.hi && (!make_map_out(c, &mRh, ln->res.hi, g.M, 256, ln->res.cols) ||
+                       !make_map_out(c, &mRl, ln->res.lo(), g.M, 256, ln->res.cols)))
+      return map_fail("gemm ln residual", g.M, g.w.N, g.w.K);
     p.tma_out = 1;
   } else if (cl == 2 && fast) {
     if (!make_map_out(c, &mOh, g.out.hi + g.out_col0, g.M, g.w.N, g.out.cols) ||
@@ -1213,7 +1269,7 @@ bool tc_gemm(TcCtx* c, const GemmArgs& g, const LnArgs* ln, cudaStream_t st) {
   dim3 grid(ncl * cl);
 #define MLDB_LAUNCH(BN_, CL_, ...)                                                                                       \
   launch_pdl_cluster(k_gemm_tc<BN_, CL_, __VA_ARGS__>, grid, dim3(threads_of<__VA_ARGS__>()), smem_of<BN_, CL_, __VA_ARGS__>(), st, CL_, \
-                     mA1h, mA1l, mA2h, mA2l, mWh, mWl, mOh, mOl, p)
+                     mA1h, mA1l, mA2h, mA2l, mWh, mWl, mOh, mOl, mRh, mRl, p)
 #define MLDB_LAUNCH_SHAPE(...)                                                                        \
   do {                                                                                                \
     if (bn == 256) { if (cl == 2) MLDB_LAUNCH(256, 2, __VA_ARGS__); else MLDB_LAUNCH(256, 1, __VA_ARGS__); } \

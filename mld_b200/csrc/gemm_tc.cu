@@ -134,26 +134,6 @@ __device__ __forceinline__ void store_plane_coalesced(uint8_t* stg, const uint32
   }
   __syncwarp();
 }
-// global (coalesced pattern: lane -> row i*8 + lane/4, 16-B slot lane%4) -> g[4]
-__device__ __forceinline__ void load_plane_issue(const __half* gbase, int64_t ld, int rows_valid, int lane, uint4 (&g)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = i * 8 + (lane >> 2), qq = lane & 3;
-    g[i] = (rr < rows_valid) ? *reinterpret_cast<const uint4*>(gbase + (int64_t)rr * ld + qq * 8) : make_uint4(0, 0, 0, 0);
-  }
-}
-// g[4] (coalesced pattern) -> rowv[4] (row-owner layout) through a 2 KB staging tile
-__device__ __forceinline__ void plane_to_rows(uint8_t* stg, const uint4 (&g)[4], int lane, uint4 (&rowv)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int rr = i * 8 + (lane >> 2), qq = lane & 3;
-    *reinterpret_cast<uint4*>(stg + stg_off(rr, qq)) = g[i];
-  }
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < 4; ++j) rowv[j] = *reinterpret_cast<const uint4*>(stg + stg_off(lane, j));
-  __syncwarp();
-}
 // fp32 x32 -> packed split16 words (hi and lo planes)
 __device__ __forceinline__ void pack_split(const float (&v)[32], uint32_t (&ph)[16], uint32_t (&pl)[16]) {
 #pragma unroll
@@ -198,7 +178,28 @@ __device__ __forceinline__ void ln_norm_chunk(const uint32_t (&r)[32], float (&v
 template <int PENDING = 1>
 __device__ __forceinline__ void stage_and_store(uint8_t* sb2, const uint32_t (&ph)[16], const uint32_t (&pl)[16], int lane,
                                                 const CUtensorMap* mh, const CUtensorMap* ml, int col, int row0) {
-  if (lane == 0) tma_store_wait_read<PENDING>();
+  if constexpr (PENDING < 0) {
+    // ONE 4 KB tile used as two 2 KB halves with a bulk group per PLANE: the hi half is rewritten while the lo
+    // store of the previous chunk may still be reading its half (and vice versa).  With one group per chunk and
+    // wait_group.read 0 the warp waited for the TMA engine on every chunk (22 % of the QKV kernel's stall samples).
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(sb2 + stg_off(lane, j)) = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { tma_store_2d(mh, smem_u32(sb2), col, row0); tma_store_commit(); tma_store_wait_read<1>(); }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(sb2 + 2048 + stg_off(lane, j)) = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) { tma_store_2d(ml, smem_u32(sb2 + 2048), col, row0); tma_store_commit(); }
+    return;
+  }
+  if (lane == 0) tma_store_wait_read<PENDING < 0 ? 0 : PENDING>();
   __syncwarp();
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -224,7 +225,7 @@ __device__ __forceinline__ void stage_and_store(uint8_t* sb2, const uint32_t (&p
 // same SWIZZLE_64B 32 x 32 boxes the output leaves through - and read back row by row.  (As plain 16-byte loads
 // through a register transpose this was the LayerNorm epilogue's hot spot: 24 % of the out-projection kernel's stall
 // samples sat on the load instruction, most of them LG-throttle.)  One mbarrier per warp; `phase` is its parity.
-struct LnResidual { uint32_t bar; uint32_t phase; uint4 gh[4], gl[4]; };   // gh / gl: the register path (fused FFN)
+struct LnResidual { uint32_t bar; uint32_t phase; };
 // r[32] (fp32 bits) += one fp16 plane of the same 32 columns, read from this thread's row of a staging tile
 __device__ __forceinline__ void add_plane_stg(uint32_t (&r)[32], const uint8_t* stg, int lane) {
 #pragma unroll
@@ -239,27 +240,6 @@ __device__ __forceinline__ void add_plane_stg(uint32_t (&r)[32], const uint8_t* 
       r[e + 1] = __float_as_uint(__uint_as_float(r[e + 1]) + f.y);
     }
   }
-}
-// The fused FFN keeps the register path: its staging is the Hs buffer, which the F2 chain reads until the accumulator
-// is complete, so a TMA load could only be requested after that wait; plain loads can be requested before it.
-__device__ __forceinline__ void add_plane(uint32_t (&r)[32], const uint4 (&pv)[4]) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const uint32_t w[4] = {pv[i].x, pv[i].y, pv[i].z, pv[i].w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
-      const int e = i * 8 + j * 2;
-      r[e] = __float_as_uint(__uint_as_float(r[e]) + f.x);
-      r[e + 1] = __float_as_uint(__uint_as_float(r[e + 1]) + f.y);
-    }
-  }
-}
-__device__ __forceinline__ void ln16_issue_residual_ldg(LnResidual& t, const __half* res_hi, const __half* res_lo, int ld_res,
-                                                        int wrow0, int col, int rows_valid, int lane) {
-  if (res_hi == nullptr) return;
-  load_plane_issue(res_hi + (int64_t)wrow0 * ld_res + col, ld_res, rows_valid, lane, t.gh);
-  load_plane_issue(res_lo + (int64_t)wrow0 * ld_res + col, ld_res, rows_valid, lane, t.gl);
 }
 // the staging tile must be idle: its TMA stores read (cp.async.bulk.wait_group.read 0 by lane 0) and this warp's
 // own reads of it done (program order + __syncwarp)
@@ -277,9 +257,8 @@ __device__ __forceinline__ void ln16_issue_residual(const LnResidual& t, bool ha
 // trow: TMEM address of this thread's row at the tile's column cb = cq * 64.  stg: this warp's staging
 // (4 KB with WIDE_STG: both planes transposed at once and the TMA-store pair; else 2 KB).  s_vec*: bias / gamma /
 // beta of the 256 columns.  s_part: [4 quarters][mean | M2][128 rows].
-template <bool WIDE_STG, bool RES_TMA>
-__device__ __forceinline__ void ln16_finish(LnResidual& t, bool has_res, const CUtensorMap* mRh, const CUtensorMap* mRl,
-                                            const __half* res_hi, const __half* res_lo, int ld_res, uint32_t trow, int cq, int row, int lane, uint8_t* stg,
+template <bool WIDE_STG>
+__device__ __forceinline__ void ln16_finish(LnResidual& t, bool has_res, const CUtensorMap* mRh, const CUtensorMap* mRl, uint32_t trow, int cq, int row, int lane, uint8_t* stg,
                                             const float* s_bias, const float* s_gamma, const float* s_beta, float* s_part,
                                             float sc, int wrow0, int rows_valid, bool tma_out, const CUtensorMap* mOh,
                                             const CUtensorMap* mOl, __half* out_hi, __half* out_lo, int ld_out,
@@ -322,21 +301,14 @@ __device__ __forceinline__ void ln16_finish(LnResidual& t, bool has_res, const C
       r[4 * i + 2] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 2]), sc, b.z));
       r[4 * i + 3] = __float_as_uint(fmaf(__uint_as_float(r[4 * i + 3]), sc, b.w));
     }
-    if (has_res && RES_TMA) {
-      // the first chunk was requested before the accumulator was awaited; the second one is requested as soon as
-      // the first has been read out of the tile and arrives under the first chunk's statistics
+    if (has_res) {
+      // the first chunk was requested before (GEMM) / right after (fused FFN) the accumulator wait; the second one
+      // is requested as soon as the first has been read out of the tile and arrives under the first chunk's statistics
       mbar_wait(t.bar, t.phase);
       t.phase ^= 1u;
       add_plane_stg(r, stg, lane);
       add_plane_stg(r, stg + 2048, lane);
       if (c == 0) ln16_issue_residual(t, true, stg, mRh, mRl, wrow0, cb + 32, lane);
-    } else if (has_res) {
-      uint4 rv[4];
-      plane_to_rows(stg, t.gh, lane, rv);
-      add_plane(r, rv);
-      plane_to_rows(stg + (WIDE_STG ? 2048 : 0), t.gl, lane, rv);
-      add_plane(r, rv);
-      if (c == 0) ln16_issue_residual_ldg(t, res_hi, res_lo, ld_res, wrow0, cb + 32, rows_valid, lane);
     }
     if (c == 0) {                                  // shift: the mean of the first chunk
       float acc = 0.0f;
@@ -372,7 +344,7 @@ __device__ __forceinline__ void ln16_finish(LnResidual& t, bool has_res, const C
     uint32_t ph[16], pl[16];
     pack_split(v, ph, pl);
     if (WIDE_STG && tma_out) {
-      stage_and_store<0>(stg, ph, pl, lane, mOh, mOl, cb + c * 32, wrow0);
+      stage_and_store<-1>(stg, ph, pl, lane, mOh, mOl, cb + c * 32, wrow0);
     } else {
       const int64_t o = (int64_t)wrow0 * ld_out + cb + c * 32;
       store_plane_coalesced(stg, ph, out_hi + o, ld_out, rows_valid, lane);
@@ -625,7 +597,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
           uint32_t ph[16], pl[16];
           pack_split(v, ph, pl);
           if (CG == 2 && p.tma_out) {
-            stage_and_store<DEEP ? 0 : 1>(stg + tbuf * 4096, ph, pl, lane, &tmOh, &tmOl, nb, wrow0);   // the map clips rows >= M
+            stage_and_store<DEEP ? -1 : 1>(stg + tbuf * 4096, ph, pl, lane, &tmOh, &tmOl, nb, wrow0);   // the map clips rows >= M
             if (!DEEP) tbuf ^= 1;
           } else {
             const int64_t o = (int64_t)wrow0 * p.ld_out + p.out_col0 + nb;
@@ -704,7 +676,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA1h, const __grid_constant__ CUt
       mbar_wait(smem_u32(&bar_tfull[as]), ((uint32_t)it >> 1) & 1u);
       tc_fence_after();
       tl_event(p.tl, tl_n, 4, it);
-      ln16_finish<CG == 2, true>(t, has_res, &tmRh, &tmRl, p.res_hi, p.res_lo, p.ld_res, trow, cq, row, lane, stg, s_bias, s_gamma, s_beta, s_part, p.inv_scale, wrow0,
+      ln16_finish<CG == 2>(t, has_res, &tmRh, &tmRl, trow, cq, row, lane, stg, s_bias, s_gamma, s_beta, s_part, p.inv_scale, wrow0,
                            rows_valid, CG == 2 && p.tma_out, &tmOh, &tmOl, p.out_hi, p.out_lo, p.ld_out, p.tl, tl_n);
       tc_fence_before();
       __syncwarp();
@@ -761,7 +733,7 @@ struct FfnCfg {
   static constexpr int HS_BYTES = 65536;                 // [plane][k-block][128 rows x 128 B]; also the
                                                          // LayerNorm epilogue's staging (Hs is idle then)
   static constexpr int TMEM_COLS = 512;                  // acc1 x 2 (128 cols each) + acc2 (256 cols)
-  static constexpr int AUX_BYTES = MAX_N * 4 + 3 * 256 * 4 + 8 * 128 * 4 + 256;
+  static constexpr int AUX_BYTES = MAX_N * 4 + 3 * 256 * 4 + 8 * 128 * 4 + 384;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + HS_BYTES + AUX_BYTES + 1024;
 };
 
@@ -776,7 +748,8 @@ __global__ void __launch_bounds__(LN_THREADS, 1)
 k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUtensorMap tmXl,
          const __grid_constant__ CUtensorMap tmW1h, const __grid_constant__ CUtensorMap tmW1l,
          const __grid_constant__ CUtensorMap tmW2h, const __grid_constant__ CUtensorMap tmW2l,
-         const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl, const FfnParams p) {
+         const __grid_constant__ CUtensorMap tmOh, const __grid_constant__ CUtensorMap tmOl,
+         const __grid_constant__ CUtensorMap tmRh, const __grid_constant__ CUtensorMap tmRl, const FfnParams p) {
   using Cfg = FfnCfg<CG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -798,6 +771,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
   uint64_t* bar_a2full = bars + 14;           // tile's acc2 complete (MMA commit, both CTAs)
   uint64_t* bar_a2empty = bars + 15;          // ... and drained by the LayerNorm epilogue (2-SM: leader's)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* bar_res = bars + 17;              // [LN_WARPS] residual tile landed (one per epilogue warp)
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
   int tl_n = 0;                                     // debug-timeline event counter of this warp
@@ -835,6 +809,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
     mbar_init(smem_u32(bar_hempty), 1);
     mbar_init(smem_u32(bar_a2full), 1);
     mbar_init(smem_u32(bar_a2empty), LN_WARPS * CG);
+    for (int s = 0; s < LN_WARPS; ++s) mbar_init(smem_u32(&bar_res[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     tma_prefetch_desc(&tmXh); tma_prefetch_desc(&tmXl); tma_prefetch_desc(&tmW1h);
     tma_prefetch_desc(&tmW1l); tma_prefetch_desc(&tmW2h); tma_prefetch_desc(&tmW2l);
@@ -1001,6 +976,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
     uint32_t r[32];
     float v[32];
     const bool has_res = p.res_hi != nullptr;
+    LnResidual t{smem_u32(&bar_res[warp - 2]), 0u};
     int g = 0;                                       // hidden chunks handled so far
     for (int j = 0; j < nlocal; ++j) {
       const Item it = item(j);
@@ -1062,11 +1038,11 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       // through shared memory); the first residual chunk is requested before the accumulator is awaited
       const int wrow0 = m0 + q * 32;
       const int rows_valid = min(32, p.M - wrow0);
-      LnResidual t;
-      ln16_issue_residual_ldg(t, p.res_hi, p.res_lo, p.ld_res, wrow0, cq * 64, rows_valid, lane);
       mbar_wait(smem_u32(bar_a2full), (uint32_t)j & 1u);      // all F2 MMAs retired: acc2 complete, Hs idle
       tc_fence_after();
       tl_event(p.tl, tl_n, 15, j);                                   // LN tail: acc2 ready
+      // the residual tile lands in Hs (this warp's staging), which the F2 chain has only now finished reading
+      ln16_issue_residual(t, has_res, stg, &tmRh, &tmRl, wrow0, cq * 64, lane);
       const int nparts = it.mode == 2 ? p.parts - 1 : 0;
       if (nparts > 0) {                                      // finisher: the contributors' partials must have landed
         if (lane == 0) {
@@ -1082,7 +1058,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         }
         __syncwarp();
       }
-      ln16_finish<true, false>(t, has_res, nullptr, nullptr, p.res_hi, p.res_lo, p.ld_res, trow2, cq, row, lane, stg,
+      ln16_finish<true>(t, has_res, &tmRh, &tmRl, trow2, cq, row, lane, stg,
                         s_b2, s_gamma, s_beta, s_part, p.inv_s2, wrow0, rows_valid, p.tma_out != 0, &tmOh, &tmOl,
                         p.out_hi, p.out_lo, p.ld_out, p.tl, tl_n,
                         nparts > 0 ? p.scratch + (size_t)it.piece0 * (BM * 256) : nullptr, nparts, (size_t)CG * (BM * 256));
@@ -1307,7 +1283,7 @@ bool tc_ffn_supported(const TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, co
   return true;
 }
 bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, float* scratch, int* flags, cudaStream_t st) {
-  CUtensorMap mXh, mXl, mW1h, mW1l, mW2h, mW2l, mOh, mOl;
+  CUtensorMap mXh, mXl, mW1h, mW1l, mW2h, mW2l, mOh, mOl, mRh, mRl;
   const int m_tiles = (g1.M + BM - 1) / BM;
   const int cg = (m_tiles >= 2 && c->sm_count % 2 == 0) ? 2 : 1;
   const bool ok = make_map(c, &mXh, g1.a1.hi, g1.M, g1.K1, BM) && make_map(c, &mXl, g1.a1.lo(), g1.M, g1.K1, BM) &&
@@ -1318,6 +1294,9 @@ bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, 
                   make_map_out(c, &mOh, l2.out.hi, g1.M, 256, l2.out.cols) &&
                   make_map_out(c, &mOl, l2.out.lo(), g1.M, 256, l2.out.cols);
   if (!ok) return map_fail("ffn", g1.M, g1.w.N, g1.w.K);
+  mRh = mOh; mRl = mOl;
+  if (l2.res.hi && (!make_map_out(c, &mRh, l2.res.hi, g1.M, 256, l2.res.cols) || !make_map_out(c, &mRl, l2.res.lo(), g1.M, 256, l2.res.cols)))
+    return map_fail("ffn residual", g1.M, g1.w.N, g1.w.K);
   FfnParams p{};
   p.M = g1.M; p.m_tiles = m_tiles; p.n_chunks = g1.w.N / FfnCfg<1>::CHUNK;
   p.tl = tc::mldb_timeline_buffer();
@@ -1342,9 +1321,9 @@ bool tc_ffn(TcCtx* c, const GemmArgs& g1, const GemmArgs& g2, const LnArgs& l2, 
   p.reverse = snake;
   if (cg == 2)
     launch_pdl_cluster(k_ffn_tc<2>, dim3(ncl * 2), dim3(LN_THREADS), FfnCfg<2>::SMEM_BYTES, st, 2, mXh, mXl, mW1h, mW1l,
-                       mW2h, mW2l, mOh, mOl, p);
+                       mW2h, mW2l, mOh, mOl, mRh, mRl, p);
   else
     launch_pdl(k_ffn_tc<1>, dim3(ncl), dim3(LN_THREADS), FfnCfg<1>::SMEM_BYTES, st, mXh, mXl, mW1h, mW1l, mW2h, mW2l,
-               mOh, mOl, p);
+               mOh, mOl, mRh, mRl, p);
   return true;
 }

@@ -1370,8 +1370,7 @@ static int run_decode(mldb_handle* h, const float* z, const int32_t* lengths, in
     k_mem_tokens<<<nblk((int64_t)c.n_lat * B * d), 256, 0, s>>>(p->mem, p->latents, c.n_lat, B, d);
     kcount(h, MLDB_KSTAT_MISC);
     // queries = zeros + PE rows (mld_vae.py:190,224; actor_vae.py:219-225)
-    k_rows_to_split<<<nblk((int64_t)B * T * d), 256, 0, s>>>(p->ws.x0, nullptr, 0, B * T, d, T, T, 0, 0, h->vae_dec_pe);
-    kcount(h, MLDB_KSTAT_MISC);
+    rows_to_split(h, p->ws.x0, nullptr, 0, B * T, d, T, T, 0, 0, h->vae_dec_pe, 0, s);
     SeqInfo si; si.lengths = p->lengths; si.kv_prefix = 0;
     ActBuf x = run_stack(h, h->vdec, p->ws.x0, p->mem, p->ws, si, s);
     if (h->vdec.norm.g) {

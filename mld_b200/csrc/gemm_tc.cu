@@ -263,7 +263,7 @@ __device__ __forceinline__ void ln16_finish(LnResidual& t, bool has_res, const C
                                             float sc, int wrow0, int rows_valid, bool tma_out, const CUtensorMap* mOh,
                                             const CUtensorMap* mOl, __half* out_hi, __half* out_lo, int ld_out,
                                             long long* tl, int& tl_n, const float* part0 = nullptr, int nparts = 0,
-                                            size_t part_stride = 0) {
+                                            size_t part_stride = 0, bool defer_drain = false) {
   const int cb = cq * 64;
   uint32_t r[32];
   float v[32];
@@ -354,7 +354,14 @@ __device__ __forceinline__ void ln16_finish(LnResidual& t, bool has_res, const C
   // the staging is the next tile's transpose buffer and s_part its statistics: the TMA engine must have read
   // the former, every warp the latter
   tl_event(tl, tl_n, 18);                           // LayerNorm: normalised, stores issued
+  if (defer_drain) return;                          // the caller drains (ln16_drain) before the staging is touched again
   if (WIDE_STG && tma_out && lane == 0) tma_store_wait_read<0>();
+  ln_bar_sync();
+}
+// the drain ln16_finish leaves to the caller with defer_drain: every warp's TMA stores have read their staging tile
+// and every warp is past its partial statistics
+__device__ __forceinline__ void ln16_drain(int lane) {
+  if (lane == 0) tma_store_wait_read<0>();
   ln_bar_sync();
 }
 
@@ -977,6 +984,7 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
     float v[32];
     const bool has_res = p.res_hi != nullptr;
     LnResidual t{smem_u32(&bar_res[warp - 2]), 0u};
+    bool drain_pending = false;                      // the last LayerNorm tail's staging drain is still owed
     int g = 0;                                       // hidden chunks handled so far
     for (int j = 0; j < nlocal; ++j) {
       const Item it = item(j);
@@ -995,6 +1003,9 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
         __syncwarp();
         if (lane == 0) arrive_leader(&bar_a1empty[b]);
         mbar_wait(smem_u32(bar_hempty), ((uint32_t)g & 1u) ^ 1u);     // F2(g - 1) has read Hs
+        // Hs doubles as the LayerNorm staging: the previous tile's output stores must have read it.  That drain
+        // (~2.7k cycles) is taken here, under this chunk's TMEM load and GELU, instead of at the end of the tail.
+        if (drain_pending) { ln16_drain(lane); drain_pending = false; }
         // this thread's row of k-block cq / 2, 64-byte half cq % 2: 4 x 16 B per plane, 16-B index XOR (row & 7)
         // (SWIZZLE_128B)
         uint8_t* const hrow = hs + (cq >> 1) * 16384 + row * 128;
@@ -1061,15 +1072,18 @@ k_ffn_tc(const __grid_constant__ CUtensorMap tmXh, const __grid_constant__ CUten
       ln16_finish<true>(t, has_res, &tmRh, &tmRl, trow2, cq, row, lane, stg,
                         s_b2, s_gamma, s_beta, s_part, p.inv_s2, wrow0, rows_valid, p.tma_out != 0, &tmOh, &tmOl,
                         p.out_hi, p.out_lo, p.ld_out, p.tl, tl_n,
-                        nparts > 0 ? p.scratch + (size_t)it.piece0 * (BM * 256) : nullptr, nparts, (size_t)CG * (BM * 256));
+                        nparts > 0 ? p.scratch + (size_t)it.piece0 * (BM * 256) : nullptr, nparts, (size_t)CG * (BM * 256),
+                        /*defer_drain=*/nparts == 0);
+      drain_pending = nparts == 0;
       if (nparts > 0 && threadIdx.x == 64)                   // everyone is past its partial loads: re-arm the flags
         for (int pp = 0; pp < nparts; ++pp) p.flags[it.piece0 + pp * CG] = 0;
-      // (ln16_finish ends with a barrier over the sixteen warps: Hs - the staging - is free for the next E1)
+      // (the staging drain + barrier that frees Hs for the next E1 is deferred to that E1's first Hs write)
       tc_fence_before();
       __syncwarp();
       tl_event(p.tl, tl_n, 16, j);                                   // LN tail done
       if (lane == 0) arrive_leader(bar_a2empty);
     }
+    if (drain_pending && lane == 0) tma_store_wait_read<0>();   // the last tile's stores still read this CTA's shared memory
   }
   tc_fence_before();
   __syncthreads();
